@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- batched sim-steps/s of the hydrodynamic force path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "rm3_irregular_ensemble"): SURVEY.md section 8(d) -- RM3-shaped two-body design
+(D = 12, L = 1001 radiation lags over 60 s, dt = 0.01 s, excitation IRF +-30 s -> 6000 lags), JONSWAP
+Hs 2.5 m / Tp 8 s / gamma 3.3, 1000 spectrum components, one random-phase realisation per instance
+(seed 1 + global instance index), 16384 instances PER GPU (weak scaling: instances are independent, tables are
+replicated, no data-path collective).  A "step" is one lock-step force evaluation of every instance:
+hydrostatics + radiation convolution + excitation convolution + total.  The velocity-history window is
+pre-filled (>= 6000 steps) before anything is timed, so the timed steps are steady state.
+
+value : instance-steps/s with the step's pose/velocity already resident in HBM (hc_step_device), timed with CUDA
+        events on the ensemble's stream, max over ranks.
+e2e   : the same through the host-buffer C-ABI call (hc_step): pinned host pose/velocity -> H2D -> kernels -> D2H
+        force, every step, wall clock around K synchronous calls, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 0.01
+DOFS = 12
+RIRF_STEPS = 1001
+EXC_STEPS = 6000
+SEA = dict(Hs=2.5, Tp=8.0, gamma=3.3, fmin=0.001, fmax=1.0, nfreq=1000, ramp=20.0)
+SNAP = 1e-9
+GVEC = (0.0, 0.0, -9.81)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="instances per GPU")
+    ap.add_argument("--prefill", type=int, default=-1, help="untimed steps to fill the history window (-1 = auto)")
+    ap.add_argument("--faithful", action="store_true", help="bracket_snap = 0 (bit-faithful bracketing)")
+    ap.add_argument("--rad-chunk", type=int, default=0)
+    ap.add_argument("--exc-chunk", type=int, default=0)
+    ap.add_argument("--cpu-instances", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=200)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def motion(amp, om, t, nb, offset=0):
+    ph = 0.01 * (offset + np.arange(nb))[:, None]
+    return amp * np.sin(om * t + ph), amp * om * np.cos(om * t + ph)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the radiation kernel from the committed ncu --set full capture, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return d
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (line-faithful port of the reference's CPU path) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_arm(n_inst, n_steps, prefill, quiet=False):
+    from hydrochrono_b200 import synth
+    from oracle import hc_oracle as orc
+    raw = synth.rm3_like()
+    T = orc.Tables(raw)
+    cores = orc.num_threads()
+    amp, om = synth.prescribed_motion(DOFS)
+    duration = (prefill + 2 * n_steps + 64) * DT
+    insts = []
+    for i in range(n_inst):
+        inst = orc.Instance(T, omp_mode=0)
+        inst.set_irregular(dt=DT, duration=duration, ramp=SEA["ramp"], Hs=SEA["Hs"], Tp=SEA["Tp"], fmin=SEA["fmin"],
+                           fmax=SEA["fmax"], nfreq=SEA["nfreq"], gamma=SEA["gamma"], seed=1 + i,
+                           share_irf_from=insts[0] if insts else None)
+        insts.append(inst)
+    # untimed: fill the velocity-history window (instances across cores)
+    orc.bench_steps(insts, prefill, 0.0, DT, 1, amp, om, GVEC)
+    t0 = prefill * DT
+    sec_best, _ = orc.bench_steps(insts, n_steps, t0, DT, 1, amp, om, GVEC)
+    best = n_inst * n_steps / sec_best
+    # reference-style threading: instances one after another, OpenMP across radiation lags (hydro_forces.cpp:593-647)
+    n_ref = max(1, min(n_inst, 4))
+    ref_steps = max(10, n_steps // 4)
+    sec_ref, _ = orc.bench_steps(insts[:n_ref], ref_steps, t0 + n_steps * DT, DT, 0, amp, om, GVEC)
+    ref_style = n_ref * ref_steps / sec_ref
+    return {"value": best, "unit": "instance-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d instances x %d steady-state steps after a %d-step history prefill, one instance per thread "
+                      "(best effort); reference-style threading (OpenMP across lags, instances serial): %.1f "
+                      "instance-steps/s on %d instances x %d steps" % (n_inst, n_steps, prefill, ref_style, n_ref,
+                                                                       ref_steps),
+            "reference_style_value": ref_style}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    prefill = args.prefill if args.prefill >= 0 else 6010
+    t0 = time.time()
+    res = None
+    vals = []
+    for _ in range(max(1, min(args.steps, 3)) if args.steps < 10 else 1):
+        res = cpu_arm(args.cpu_instances, args.cpu_steps, prefill)
+        vals.append(res["value"])
+    v = float(np.median(vals))
+    line = {
+        "metric": "batched sim-steps/sec (RM3 irregular ensemble)", "value": v, "unit": "instance-steps/s",
+        "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "rm3_irregular_ensemble", "instances_per_gpu": args.batch, "dofs": DOFS,
+                   "rirf_steps": RIRF_STEPS, "exc_irf_steps": EXC_STEPS, "dt": DT, "sea_state": SEA,
+                   "note": "reference CPU path (oracle port; the reference itself needs Chrono/Eigen/HDF5 and cannot "
+                           "be built here) on a bounded sample of the same workload; ms_per_step is the time the CPU "
+                           "would need for one lock-step of all instances_per_gpu instances"},
+        "cpu_baseline": res,
+        "e2e": {"value": v, "unit": "instance-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    line["cpu_baseline"]["value"] = v
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hydrochrono_b200 as hc
+    from hydrochrono_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hydro force path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    prefill = args.prefill if args.prefill >= 0 else 6010
+    snap = 0.0 if args.faithful else SNAP
+    total_steps = prefill + 2 * (W + K) + 128
+    raw = synth.rm3_like()
+    T = hc.Tables.from_raw(raw)
+    stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
+    ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
+                      exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream)
+    seeds = (1 + rank * B + np.arange(B)).astype(np.int32)
+    t_setup = time.time()
+    ens.set_waves_irregular(dt=DT, duration=total_steps * DT, ramp=SEA["ramp"], Hs=SEA["Hs"], Tp=SEA["Tp"],
+                            fmin=SEA["fmin"], fmax=SEA["fmax"], nfreq=SEA["nfreq"], gamma=SEA["gamma"], seeds=seeds)
+    eta_s = ens.profile()["eta_synthesis_seconds"]
+    nf, n_eta, le = ens.irregular_sizes()
+    assert le == [EXC_STEPS, EXC_STEPS], le
+
+    amp, om = synth.prescribed_motion(DOFS)
+    NBUF = 8
+    h_pose = [torch.empty((B, DOFS), dtype=torch.float64).pin_memory() for _ in range(NBUF)]
+    h_vel = [torch.empty((B, DOFS), dtype=torch.float64).pin_memory() for _ in range(NBUF)]
+    h_force = torch.empty((B, DOFS), dtype=torch.float64).pin_memory()
+    for i in range(NBUF):
+        p, v = motion(amp, om, i * DT, B, rank * B)
+        h_pose[i].copy_(torch.from_numpy(p))
+        h_vel[i].copy_(torch.from_numpy(v))
+    d_pose = [x.to(dev) for x in h_pose]
+    d_vel = [x.to(dev) for x in h_vel]
+    d_force = torch.empty((B, DOFS), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    step_no = [0]
+
+    def dev_step():
+        n = step_no[0]
+        ens.step_device(n * DT, d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC)
+        step_no[0] = n + 1
+
+    def host_step():
+        n = step_no[0]
+        ens.step(n * DT, h_pose[n % NBUF].numpy(), h_vel[n % NBUF].numpy(), GVEC, out=h_force.numpy())
+        step_no[0] = n + 1
+
+    # ---- untimed: fill the radiation history window -----------------------------------------------
+    for _ in range(prefill):
+        dev_step()
+    ens.sync()
+    assert ens.history_len() >= min(prefill, 6000), ens.history_len()
+    setup_s = time.time() - t_setup
+
+    # ---- device-resident leg (value) -----------------------------------------------------------------
+    for _ in range(W):
+        dev_step()
+    ens.sync()
+    sampler = ClockSampler(local_rank)
+    launches0 = ens.profile()["kernel_launches"]
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)                              # CUDA events on the launching stream
+    for _ in range(K):
+        dev_step()
+    ev1.record(stream)
+    ens.sync()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t0
+    t_dev = ev0.elapsed_time(ev1) * 1e-3
+    barrier()
+    clocks = sampler.stop()
+    launches = ens.profile()["kernel_launches"] - launches0
+    t_dev = max_over_ranks(t_dev)
+
+    # ---- end-to-end leg (host buffers through hc_step) -----------------------------------------------
+    for _ in range(W):
+        host_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        host_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(t_e2e)
+    checksum = float(h_force.numpy()[:, 2].sum())
+
+    # ---- per-kernel device times (CUDA events on the ensemble's stream; graph off while profiling) ----
+    ens.set_profiling(True)
+    nprof = min(max(K // 4, 20), 100)
+    for _ in range(3):
+        dev_step()
+    ens.sync()
+    ens.kernel_ms(reset=True)
+    for _ in range(nprof):
+        dev_step()
+    ens.sync()
+    kms = ens.kernel_ms(reset=True)
+    ens.set_profiling(False)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        rows = RIRF_STEPS if snap > 0 else 2 * RIRF_STEPS      # distinct history rows touched per step
+        rad_bytes = B * (8 * DOFS * rows + 8 * DOFS * 3) + 8 * DOFS * DOFS * RIRF_STEPS
+        exc_bytes = B * 8 * (EXC_STEPS + 1) + 8 * (DOFS + 2) * EXC_STEPS
+        ach = rad_bytes / (kms["radiation"] * 1e-3) / 1e9
+        ach_exc = exc_bytes / (kms["excitation"] * 1e-3) / 1e9 if kms["excitation"] > 0 else None
+        traffic = ncu_traffic()
+        value = world * B * K / t_dev
+        e2e = world * B * K / t_e2e
+        line = {
+            "metric": "batched sim-steps/sec (RM3 irregular ensemble)", "value": value, "unit": "instance-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "rm3_irregular_ensemble", "instances_per_gpu": B, "instances_total": world * B,
+                       "dofs": DOFS, "rirf_steps": RIRF_STEPS, "exc_irf_steps": EXC_STEPS, "dt": DT,
+                       "spectrum_components": nf, "eta_samples": n_eta, "sea_state": SEA,
+                       "bracket_snap": snap, "history_prefill_steps": prefill, "cuda_graph": not args.no_graph,
+                       "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
+                             % (8e-9 * DOFS * B * 6002, 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
+                       "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s); "
+                                 "e2e: wall clock around K synchronous hc_step calls; per-kernel ms: CUDA events inside "
+                                 "the library on the same stream" % t_wall},
+            "e2e": {"value": e2e, "unit": "instance-steps/s", "h2d_bytes_per_step": 2 * B * DOFS * 8 + 64,
+                    "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_radiation<12>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
+                         "kernel_ms": kms["radiation"],
+                         "excitation": {"kernel": "k_excitation<12>", "achieved": ach_exc,
+                                        "frac": (ach_exc / peak) if ach_exc else None,
+                                        "algorithmic_bytes_per_launch": exc_bytes, "kernel_ms": kms["excitation"],
+                                        "traffic": (traffic or {}).get("excitation_dram_bytes_per_launch")}},
+            "kernel_ms": kms,
+            "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},
+            "checksum": checksum,
+        }
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_arm(args.cpu_instances, args.cpu_steps, prefill)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

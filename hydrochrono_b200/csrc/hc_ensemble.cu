@@ -1,0 +1,840 @@
+// Ensemble: device-resident state of B lock-stepped TestHydro instances and the per-step driver.
+//
+// Host-side logic restated from TestHydro (src/hydro_forces.cpp): the time-keyed force cache (:742-755), the
+// duplicate-evaluation guard (:555-557), history push + pruning (:559-577, :327-340) -- all functions of the
+// time values alone, which are shared by every instance, so they run once on the host; everything that touches
+// per-instance data runs in the kernels of hc_kernels.cu.
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <memory>
+
+#include "hc_internal.h"
+#include "hc_kernels.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace hc {
+
+#define CUDA_CHECK(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            fail(HC_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count, bool zero = true) {
+        release();
+        if (count == 0) return;
+        CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+    }
+    void upload(const T* src, size_t count) {
+        alloc(count, false);
+        CUDA_CHECK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void upload(const std::vector<T>& v) { upload(v.data(), v.size()); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    void alloc(size_t bytes) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        CUDA_CHECK(cudaMallocHost(&p, bytes));
+        std::memset(p, 0, bytes);
+    }
+};
+
+enum { EV_BEGIN = 0, EV_PRE, EV_RAD, EV_EXC, EV_END, EV_COUNT };
+
+}  // namespace hc
+
+using namespace hc;
+
+struct hc_ensemble {
+    const hc_tables* T = nullptr;
+    hc_ensemble_opts opts{};
+    int dev = 0, B = 0, Bp = 0, D = 0, N = 0, L = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // static tables on the device
+    DevBuf<double> d_K, d_rirf_t, d_rirf_w, d_ainf;
+    HydrostaticTables hs{};
+
+    // history ring
+    DevBuf<double> d_hist, d_times;
+    int cap = 0, head = -1;
+    std::deque<double> times;         // newest first, mirrors TestHydro::time_history_
+    double prev_time = -1.0;          // hydro_forces.cpp:176
+    bool force_valid = false;
+
+    // radiation plan + partials
+    DevBuf<int> d_pr_new, d_pr_old;
+    DevBuf<double> d_pr_wn, d_pr_wo, d_pr_wd, d_rad_partial;
+    int rad_chunk = 0, rad_nchunk = 0;
+
+    // step I/O
+    DevBuf<StepHeader> d_hdr;
+    DevBuf<double> d_pose, d_vel, d_force, d_comp;
+    PinBuf h_pose, h_vel, h_force;
+
+    // waves
+    int wave_mode = 0;
+    DevBuf<double> d_reg_amp, d_reg_omega, d_reg_mag, d_reg_phase;
+    std::vector<double> reg_mag_h, reg_phase_h, reg_k_h;   // [count][D], [count][D], [count]
+    int reg_count = 0;
+    // irregular
+    hc_irregular_params ip{};
+    std::vector<ExcIrfBody> irf;      // per body, host
+    struct Group { int dof0, nd, Le, chunk0, nchunk; DevBuf<double> tau, fw, w1, w2; DevBuf<int> idx; double tau_first, tau_last; };
+    std::vector<std::unique_ptr<Group>> groups;
+    int exc_chunk = 0, exc_total_chunks = 0, exc_ndmax = 0;
+    DevBuf<double> d_exc_partial, d_eta, d_eta_t, d_omega, d_amp, d_phase;
+    std::vector<double> eta_t_h, freqs_h, widths_h, wavenumbers_h;
+    std::vector<double> S_h;          // [nS][nf]  (nS = 1 shared or B)
+    std::vector<double> phases_h;     // [B][nf]
+    bool per_instance_spectrum = false;
+    int n_eta = 0, nf = 0;
+
+    // graph + profiling
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+    const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev[EV_COUNT] = {};
+    hc_profile_stats prof{};
+    double acc_ms[4] = {0, 0, 0, 0};
+    long long ms_steps = 0;
+    bool events_pending = false;
+
+    ~hc_ensemble() {
+        cudaSetDevice(dev);
+        drop_graph();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    void drop_graph() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
+        graph_exec = nullptr; graph = nullptr; graph_valid = false;
+    }
+    void use_device() const { CUDA_CHECK(cudaSetDevice(dev)); }
+
+    void alloc_ring(int new_cap);
+    void grow_ring();
+    void setup_radiation_chunks();
+    void enqueue_kernels(const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
+    void run_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
+    void collect_events();
+};
+
+// ---------------------------------------------------------------------------------------
+void hc_ensemble::alloc_ring(int new_cap) {
+    d_hist.alloc(size_t(new_cap) * D * Bp);
+    d_times.alloc(new_cap);
+    cap = new_cap;
+    head = -1;
+}
+
+// Ring too small for the step size actually used: double it, keeping the live entries in order.
+void hc_ensemble::grow_ring() {
+    const int old_cap = cap, len = int(times.size());
+    const int new_cap = old_cap * 2;
+    DevBuf<double> nh, nt;
+    nh.alloc(size_t(new_cap) * D * Bp);
+    nt.alloc(new_cap);
+    const size_t row = size_t(D) * Bp;
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    // history index i (0 = newest) moves from slot (head - i) mod old_cap to slot len-1-i
+    for (int i = 0; i < len; ++i) {
+        int s = head - i;
+        if (s < 0) s += old_cap;
+        CUDA_CHECK(cudaMemcpyAsync(nh.p + size_t(len - 1 - i) * row, d_hist.p + size_t(s) * row, row * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(nt.p + (len - 1 - i), d_times.p + s, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    std::swap(d_hist.p, nh.p); std::swap(d_hist.n, nh.n);
+    std::swap(d_times.p, nt.p); std::swap(d_times.n, nt.n);
+    cap = new_cap;
+    head = len - 1;
+    drop_graph();
+}
+
+void hc_ensemble::setup_radiation_chunks() {
+    const int tiles = (Bp + kTileInst - 1) / kTileInst;
+    int chunk = opts.rad_chunk;
+    if (chunk <= 0) {
+        // aim for >= ~4 CTAs per SM over 148 SMs, chunk between 8 and 64 lags
+        const int want_ctas = 148 * 4;
+        const int nch = std::max(1, (want_ctas + tiles - 1) / tiles);
+        chunk = (L + nch - 1) / nch;
+        chunk = std::max(8, std::min(chunk, 64));
+    }
+    chunk = std::min(chunk, L);
+    // shared-memory ceiling (K tile is chunk * D * D doubles)
+    while (chunk > 1 && (D == 6 || D == 12) && radiation_smem_bytes(D, chunk) > 160 * 1024) chunk /= 2;
+    rad_chunk = chunk;
+    rad_nchunk = (L + chunk - 1) / chunk;
+    d_rad_partial.alloc(size_t(rad_nchunk) * D * Bp);
+}
+
+void hc_ensemble::enqueue_kernels(const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events) {
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
+    PrestepArgs pa{};
+    pa.hdr = d_hdr.p; pa.vel = d_vel_in; pa.hist = d_hist.p; pa.times = d_times.p;
+    pa.rirf_t = d_rirf_t.p; pa.rirf_w = d_rirf_w.p;
+    pa.pr_new = d_pr_new.p; pa.pr_old = d_pr_old.p; pa.pr_wn = d_pr_wn.p; pa.pr_wo = d_pr_wo.p; pa.pr_wd = d_pr_wd.p;
+    pa.B = B; pa.Bp = Bp; pa.D = D; pa.L = L;
+    pa.ngroups = 0;
+    if (wave_mode == 2) {
+        pa.ngroups = int(groups.size());
+        for (size_t g = 0; g < groups.size(); ++g) {
+            pa.tau[g] = groups[g]->tau.p; pa.Le[g] = groups[g]->Le;
+            pa.pe_idx[g] = groups[g]->idx.p; pa.pe_w1[g] = groups[g]->w1.p; pa.pe_w2[g] = groups[g]->w2.p;
+        }
+        pa.eta_t = d_eta_t.p; pa.n_eta = n_eta; pa.eta_dt = ip.simulation_dt;
+    }
+    CUDA_CHECK(launch_prestep(pa, stream));
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PRE], stream));
+
+    RadiationArgs ra{};
+    ra.hdr = d_hdr.p; ra.K = d_K.p; ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
+    ra.times = d_times.p; ra.partial = d_rad_partial.p;
+    ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
+    CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
+
+    FinalizeGroups fg{};
+    if (wave_mode == 2) {
+        ExcitationArgs ea{};
+        ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
+        ea.eta_dt = ip.simulation_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            Group& G = *groups[g];
+            ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
+            CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, stream));
+            fg.dof0[g] = G.dof0; fg.nd[g] = G.nd; fg.chunk0[g] = G.chunk0; fg.nchunk[g] = G.nchunk;
+        }
+    }
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
+
+    FinalizeArgs fa{};
+    fa.hdr = d_hdr.p; fa.pose = d_pose_in; fa.rad_partial = d_rad_partial.p; fa.exc_partial = d_exc_partial.p;
+    fa.force = d_force_out; fa.comp = d_comp.p;
+    fa.reg_amp = d_reg_amp.p; fa.reg_omega = d_reg_omega.p; fa.reg_mag = d_reg_mag.p; fa.reg_phase = d_reg_phase.p;
+    fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
+    fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
+    CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_END], stream));
+}
+
+void hc_ensemble::collect_events() {
+    // called after a stream synchronisation
+    float ms[4] = {0, 0, 0, 0};
+    cudaEventElapsedTime(&ms[0], ev[EV_BEGIN], ev[EV_PRE]);
+    cudaEventElapsedTime(&ms[1], ev[EV_PRE], ev[EV_RAD]);
+    cudaEventElapsedTime(&ms[2], ev[EV_RAD], ev[EV_EXC]);
+    cudaEventElapsedTime(&ms[3], ev[EV_EXC], ev[EV_END]);
+    for (int i = 0; i < 4; ++i) acc_ms[i] += ms[i];
+    ms_steps++;
+    events_pending = false;
+    prof.radiation_seconds += 1e-3 * (ms[0] + ms[1]);
+    prof.waves_seconds += 1e-3 * ms[2];
+    prof.hydrostatics_seconds += 1e-3 * ms[3];
+    prof.step_seconds += 1e-3 * (ms[0] + ms[1] + ms[2] + ms[3]);
+}
+
+// One recompute (hydro_forces.cpp:746-760) for all instances.
+void hc_ensemble::run_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
+    // --- ComputeForceRadiationDampingConv's host-side bookkeeping ---
+    if (!times.empty() && t == times.front())
+        fail(HC_ERR_DUPLICATE_TIME, "Tried to compute the radiation damping convolution twice within the same time step!");
+    if (!times.empty() && t < times.front())
+        fail(HC_ERR_TIME_ORDER, "Radiation convolution: interpolation error; query_time not bracketed by history.");
+    if (wave_mode == 2) {
+        // ExcitationConvolution bounds (wave_types.cpp:800,833-840): every t - tau_j must lie inside the eta window
+        const double tmin = eta_t_h.front(), tmax = eta_t_h.back();
+        for (auto& G : groups) {
+            const double hi = t - G->tau_first, lo = t - G->tau_last;
+            if (!(tmin <= lo && hi <= tmax))
+                fail(HC_ERR_ETA_WINDOW,
+                     "Excitation convolution: trying to find free surface elevation at a time out of bounds from the "
+                     "precomputed free surface elevation (" + std::to_string(hi > tmax ? hi : lo) + "not in [" +
+                     std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.");
+        }
+    }
+    if (int(times.size()) >= cap) grow_ring();
+    times.push_front(t);
+    head = (head + 1) % cap;
+    const double t_min = t - T->rirf_t.back();                        // history_min_time (:552)
+    while (times.size() > 1 && times[times.size() - 2] < t_min) times.pop_back();   // PruneHistory (:327-340)
+
+    if (events_pending) {   // the profiling events are about to be re-recorded
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        collect_events();
+    }
+    // Pageable source: the runtime stages small copies at call time, so the stack header can be reused at once.
+    StepHeader hh{};
+    hh.t = t; hh.g[0] = g[0]; hh.g[1] = g[1]; hh.g[2] = g[2];
+    hh.snap = opts.bracket_snap; hh.head = head; hh.len = int(times.size()); hh.cap = cap; hh.flags = 0;
+    CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
+
+    const bool want_graph = opts.use_graph && !profiling;
+    if (want_graph) {
+        if (!graph_valid || graph_pose != d_pose_in || graph_vel != d_vel_in || graph_force != d_force_out) {
+            drop_graph();
+            CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_kernels(d_pose_in, d_vel_in, d_force_out, false);
+            } catch (...) {
+                cudaGraph_t tmp = nullptr;
+                cudaStreamEndCapture(stream, &tmp);
+                if (tmp) cudaGraphDestroy(tmp);
+                throw;
+            }
+            CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+            CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
+            graph_valid = true;
+            graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out;
+        }
+        CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
+    } else {
+        enqueue_kernels(d_pose_in, d_vel_in, d_force_out, profiling);
+        events_pending = profiling;
+    }
+    prof.kernel_launches += 3 + (wave_mode == 2 ? (long long)groups.size() : 0);
+    prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
+    prev_time = t;
+    force_valid = true;
+}
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+#define HC_GUARD_BEGIN try {
+#define HC_GUARD_END                                                                                 \
+    }                                                                                                \
+    catch (const hc::StatusError& e) { hc::set_last_error(e.msg); return e.code; }                   \
+    catch (const std::out_of_range& e) { hc::set_last_error(e.what()); return HC_ERR_OUT_OF_RANGE; } \
+    catch (const std::exception& e) { hc::set_last_error(e.what()); return HC_ERR_INVALID; }
+
+extern "C" {
+
+int hc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void hc_ensemble_default_opts(hc_ensemble_opts* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->device = 0; o->batch = 1; o->dt_hint = 0.0; o->bracket_snap = 0.0;
+    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->stream = nullptr;
+}
+
+hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, hc_ensemble** out) {
+    HC_GUARD_BEGIN
+    if (!t || !opts || !out) fail(HC_ERR_INVALID, "null argument");
+    if (opts->batch < 1) fail(HC_ERR_INVALID, "batch must be >= 1");
+    if (t->N > kMaxBodies) fail(HC_ERR_INVALID, "too many bodies (max " + std::to_string(kMaxBodies) + ")");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(HC_ERR_CUDA, "no CUDA device available: hydrochrono_b200 has no CPU fallback");
+    }
+    if (opts->device < 0 || opts->device >= ndev) fail(HC_ERR_INVALID, "bad device ordinal");
+    std::unique_ptr<hc_ensemble> e(new hc_ensemble());
+    e->T = t; e->opts = *opts; e->dev = opts->device;
+    e->use_device();
+    e->B = opts->batch; e->N = t->N; e->D = t->D; e->L = t->L;
+    const int lane_tile = 32 * kIPT;
+    e->Bp = ((e->B + lane_tile - 1) / lane_tile) * lane_tile;
+    if (opts->stream) { e->stream = static_cast<cudaStream_t>(opts->stream); }
+    else { CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+    for (auto& ev : e->ev) CUDA_CHECK(cudaEventCreate(&ev));
+
+    const int D = e->D, L = e->L;
+    // K staged as [lag][col][row]: one lag's D x D block is contiguous, rows fastest
+    std::vector<double> Kdev(size_t(L) * D * D);
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c)
+            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s];
+    e->d_K.upload(Kdev);
+    e->d_rirf_t.upload(t->rirf_t);
+    e->d_rirf_w.upload(t->rirf_w);
+    std::vector<double> A(size_t(D) * D);
+    for (int b = 0; b < t->N; ++b)
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < D; ++c) A[size_t(6 * b + r) * D + c] = t->body[b].ainf[size_t(r) * D + c];
+    e->d_ainf.upload(A);
+    e->hs.rho = t->rho;
+    for (int b = 0; b < t->N; ++b) {
+        std::copy(t->body[b].lin.begin(), t->body[b].lin.end(), e->hs.Kh[b]);
+        e->hs.disp_vol[b] = t->body[b].disp_vol;
+        for (int i = 0; i < 3; ++i) e->hs.cb_minus_cg[b][i] = t->cb_minus_cg[3 * b + i];
+        for (int i = 0; i < 6; ++i) e->hs.equilibrium[b][i] = t->equilibrium[6 * b + i];
+    }
+    // history ring: window / dt + slack
+    const double window = t->rirf_t.back() - t->rirf_t.front();
+    double dt = opts->dt_hint > 0.0 ? opts->dt_hint : (t->rirf_t[1] - t->rirf_t[0]);
+    int cap = int(std::ceil(window / dt)) + 8;
+    cap = std::max(cap, 16);
+    e->alloc_ring(cap);
+    e->d_pr_new.alloc(L); e->d_pr_old.alloc(L); e->d_pr_wn.alloc(L); e->d_pr_wo.alloc(L); e->d_pr_wd.alloc(L);
+    e->setup_radiation_chunks();
+    e->d_hdr.alloc(1);
+    const size_t bd = size_t(e->B) * D;
+    e->d_pose.alloc(bd); e->d_vel.alloc(bd); e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
+    e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    *out = e.release();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+void hc_ensemble_destroy(hc_ensemble* e) { delete e; }
+int hc_ensemble_batch(const hc_ensemble* e) { return e->B; }
+int hc_ensemble_dofs(const hc_ensemble* e) { return e->D; }
+int hc_ensemble_history_len(const hc_ensemble* e) { return int(e->times.size()); }
+
+hc_status hc_ensemble_reset(hc_ensemble* e) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->times.clear();
+    e->head = -1;
+    e->prev_time = -1.0;
+    e->force_valid = false;
+    CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
+    CUDA_CHECK(cudaMemsetAsync(e->d_comp.p, 0, e->d_comp.n * sizeof(double), e->stream));
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_ensemble_host_buffers(hc_ensemble* e, double** pose, double** vel, double** force) {
+    if (pose) *pose = static_cast<double*>(e->h_pose.p);
+    if (vel) *vel = static_cast<double*>(e->h_vel.p);
+    if (force) *force = static_cast<double*>(e->h_force.p);
+    return HC_OK;
+}
+
+// ---- waves ---------------------------------------------------------------------------
+hc_status hc_waves_none(hc_ensemble* e) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->wave_mode = 0;
+    e->drop_graph();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_waves_regular(hc_ensemble* e, int count, const double* amplitude, const double* omega, const double* phase) {
+    HC_GUARD_BEGIN
+    const hc_tables& T = *e->T;
+    if (!(count == 1 || count == e->B)) fail(HC_ERR_INVALID, "count must be 1 or the batch size");
+    if (!amplitude || !omega) fail(HC_ERR_INVALID, "null argument");
+    if (T.nw < 2) fail(HC_ERR_INVALID, "tables hold no excitation magnitude/phase data");
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const int D = e->D, Bp = e->Bp;
+    // RegularWave::AddH5Data (wave_types.cpp:278-299) per distinct wave
+    e->reg_count = count;
+    e->reg_mag_h.assign(size_t(count) * D, 0.0);
+    e->reg_phase_h.assign(size_t(count) * D, 0.0);
+    e->reg_k_h.assign(count, 0.0);
+    const double omega_max = T.w_list.back();
+    const double num_freqs = double(T.w_list.size());
+    const double domega = omega_max / num_freqs;                       // GetOmegaDelta (:329-333)
+    for (int i = 0; i < count; ++i) {
+        const double pos = (omega[i] / domega) - 1;                    // freq_index_des (:290)
+        const double fl = std::floor(pos);
+        const int i0 = int(fl);
+        if (i0 < 0 || i0 + 1 >= T.nw)
+            throw std::out_of_range("regular wave omega outside the excitation frequency table");
+        const double frac = pos - fl;
+        for (int b = 0; b < T.N; ++b)
+            for (int r = 0; r < 6; ++r) {
+                const double* m = &T.body[b].exc_mag[size_t(r) * T.nw];
+                const double* p = &T.body[b].exc_phase[size_t(r) * T.nw];
+                e->reg_mag_h[size_t(i) * D + 6 * b + r] = (frac * (m[i0 + 1] - m[i0])) + m[i0];
+                e->reg_phase_h[size_t(i) * D + 6 * b + r] = (frac * (p[i0 + 1] - p[i0])) + p[i0];
+            }
+        e->reg_k_h[i] = wave_number(omega[i], T.depth, T.g);           // RegularWave::Initialize (:274-276)
+    }
+    std::vector<double> amp(Bp, 0.0), om(Bp, 0.0), mag(size_t(D) * Bp, 0.0), ph(size_t(6) * Bp, 0.0);
+    for (int b = 0; b < e->B; ++b) {
+        const int i = count == 1 ? 0 : b;
+        amp[b] = amplitude[i]; om[b] = omega[i];
+        for (int d = 0; d < D; ++d) mag[size_t(d) * Bp + b] = e->reg_mag_h[size_t(i) * D + d];
+        for (int r = 0; r < 6; ++r) ph[size_t(r) * Bp + b] = e->reg_phase_h[size_t(i) * D + r];   // body 0 (quirk, :323)
+    }
+    (void)phase;  // regular_wave_phase_ is not used by the force (only by eta / kinematics)
+    e->d_reg_amp.upload(amp); e->d_reg_omega.upload(om); e->d_reg_mag.upload(mag); e->d_reg_phase.upload(ph);
+    e->wave_mode = 1;
+    e->drop_graph();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+void hc_irregular_default_params(hc_irregular_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->frequency_min = 0.001; p->frequency_max = 1.0; p->nfrequencies = 0;
+    p->peak_enhancement_factor = 1.0; p->is_normalized = 0; p->seed = 1;
+}
+
+hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const int* seeds, const double* Hs_arr,
+                             const double* Tp_arr) {
+    HC_GUARD_BEGIN
+    if (!p) fail(HC_ERR_INVALID, "null argument");
+    const hc_tables& T = *e->T;
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (p->simulation_dt <= 0.0) fail(HC_ERR_INVALID, "simulation_dt must be positive for irregular waves");
+    const int B = e->B, Bp = e->Bp, D = e->D;
+    e->ip = *p;
+    // --- InitializeIRFVectors / ResampleIRF (wave_types.cpp:432-449,572-606) ---
+    e->irf = resample_excitation_irf(T, p->simulation_dt);
+    // group bodies that share one IRF time grid bit-for-bit (the usual case: one BEMIO run)
+    e->groups.clear();
+    bool all_same = true;
+    for (int b = 1; b < T.N; ++b)
+        if (e->irf[b].t != e->irf[0].t) all_same = false;
+    const bool merged = all_same && (D == 6 || D == 12);
+    const int ngroups = merged ? 1 : T.N;
+    if (ngroups > kMaxBodies) fail(HC_ERR_INVALID, "too many excitation groups");
+    e->exc_ndmax = merged ? D : 6;
+    int max_Le = 0;
+    for (int g = 0; g < ngroups; ++g) max_Le = std::max(max_Le, int(e->irf[g].t.size()));
+    {
+        const int tiles = (Bp + kTileInst - 1) / kTileInst;
+        int chunk = e->opts.exc_chunk;
+        if (chunk <= 0) {
+            const int want = 148 * 4;
+            const int nch = std::max(1, (want + tiles * ngroups - 1) / (tiles * ngroups));
+            chunk = (max_Le + nch - 1) / nch;
+            chunk = std::max(32, std::min(chunk, 512));
+        }
+        e->exc_chunk = std::min(chunk, std::max(1, max_Le));
+    }
+    int chunk0 = 0;
+    for (int g = 0; g < ngroups; ++g) {
+        auto G = std::make_unique<hc_ensemble::Group>();
+        const ExcIrfBody& I0 = e->irf[g];
+        G->Le = int(I0.t.size());
+        G->dof0 = merged ? 0 : 6 * g;
+        G->nd = merged ? D : 6;
+        G->tau_first = I0.t.front(); G->tau_last = I0.t.back();
+        std::vector<double> fw(size_t(G->Le) * G->nd);
+        for (int d = 0; d < G->nd; ++d) {
+            const int body = (G->dof0 + d) / 6, r = (G->dof0 + d) % 6;
+            const ExcIrfBody& I = e->irf[body];
+            for (int j = 0; j < G->Le; ++j) fw[size_t(j) * G->nd + d] = I.f[size_t(r) * G->Le + j] * I.w[j];
+        }
+        G->tau.upload(I0.t); G->fw.upload(fw);
+        G->idx.alloc(G->Le); G->w1.alloc(G->Le); G->w2.alloc(G->Le);
+        G->chunk0 = chunk0;
+        G->nchunk = (G->Le + e->exc_chunk - 1) / e->exc_chunk;
+        chunk0 += G->nchunk;
+        e->groups.push_back(std::move(G));
+    }
+    e->exc_total_chunks = chunk0;
+    e->d_exc_partial.alloc(size_t(chunk0) * e->exc_ndmax * Bp);
+
+    e->n_eta = 0; e->nf = 0;
+    e->wave_mode = 2;
+    e->drop_graph();
+    const bool have_sea = (Hs_arr || p->wave_height != 0.0) && (Tp_arr || p->wave_period != 0.0);
+    // --- eta time grid (CreateFreeSurfaceElevation, wave_types.cpp:717-744) ---
+    double t_irf_min = 0.0, t_irf_max = 0.0;
+    for (const ExcIrfBody& I : e->irf) {
+        t_irf_min = std::min({t_irf_min, I.t.front(), I.t.back()});
+        t_irf_max = std::max({t_irf_max, I.t.front(), I.t.back()});
+    }
+    const double duration = p->simulation_duration + 2 * (t_irf_max - t_irf_min);
+    const int num_timesteps = static_cast<int>(std::ceil(duration / p->simulation_dt));
+    e->eta_t_h = linspaced(num_timesteps + 1, 0, num_timesteps * p->simulation_dt);
+    for (double& x : e->eta_t_h) x += -t_irf_max;
+    e->n_eta = int(e->eta_t_h.size());
+    e->d_eta_t.upload(e->eta_t_h);
+    e->d_eta.alloc(size_t(e->n_eta) * Bp);   // zero: wave_height == 0 leaves eta empty in the reference
+    if (!have_sea) return HC_OK;             // wave_types.cpp:454 (no spectrum, no elevation)
+
+    // --- CreateSpectrum (wave_types.cpp:643-676) ---
+    int nf;
+    if (p->nfrequencies == 0) {
+        const double df = 1.0 / p->simulation_duration;
+        nf = std::ceil((p->frequency_max - p->frequency_min) / df);
+    } else {
+        nf = p->nfrequencies;
+    }
+    if (nf < 1) fail(HC_ERR_INVALID, "no spectrum frequencies");
+    e->nf = nf;
+    e->freqs_h = linspaced(nf, p->frequency_min, p->frequency_max);
+    e->widths_h = trapezoid_widths(e->freqs_h);
+    e->wavenumbers_h.resize(nf);
+    std::vector<double> omega(nf);
+    for (int i = 0; i < nf; ++i) {
+        omega[i] = 2 * M_PI * e->freqs_h[i];
+        e->wavenumbers_h[i] = wave_number(omega[i], T.depth, T.g);
+    }
+    e->per_instance_spectrum = (Hs_arr != nullptr) || (Tp_arr != nullptr);
+    const int nS = e->per_instance_spectrum ? B : 1;
+    e->S_h.resize(size_t(nS) * nf);
+    std::vector<double> amp(e->per_instance_spectrum ? size_t(nf) * Bp : size_t(nf), 0.0);
+    for (int s = 0; s < nS; ++s) {
+        const double Hs = Hs_arr ? Hs_arr[s] : p->wave_height;
+        const double Tp = Tp_arr ? Tp_arr[s] : p->wave_period;
+        dvec S = jonswap(e->freqs_h, Hs, Tp, p->peak_enhancement_factor, p->is_normalized != 0);
+        std::copy(S.begin(), S.end(), e->S_h.begin() + size_t(s) * nf);
+        for (int i = 0; i < nf; ++i) {
+            const double a = std::sqrt(2 * S[i] * e->widths_h[i]);      // GetEtaIrregular (:39)
+            if (e->per_instance_spectrum) amp[size_t(i) * Bp + s] = a; else amp[i] = a;
+        }
+    }
+    e->phases_h.resize(size_t(B) * nf);
+    std::vector<double> ph(size_t(nf) * Bp, 0.0);
+    for (int b = 0; b < B; ++b) {
+        dvec v = random_phases(seeds ? seeds[b] : p->seed, nf);
+        std::copy(v.begin(), v.end(), e->phases_h.begin() + size_t(b) * nf);
+        for (int i = 0; i < nf; ++i) ph[size_t(i) * Bp + b] = v[i];
+    }
+    e->d_omega.upload(omega); e->d_amp.upload(amp); e->d_phase.upload(ph);
+
+    // --- eta synthesis on the device (wave_types.cpp:27-59,750-769) ---
+    EtaArgs ea{};
+    ea.eta_t = e->d_eta_t.p; ea.omega = e->d_omega.p; ea.amp = e->d_amp.p; ea.phase = e->d_phase.p; ea.eta = e->d_eta.p;
+    ea.ramp = p->ramp_duration; ea.n_eta = e->n_eta; ea.nf = nf; ea.Bp = Bp; ea.amp_per_instance = e->per_instance_spectrum;
+    CUDA_CHECK(cudaEventRecord(e->ev[EV_BEGIN], e->stream));
+    CUDA_CHECK(launch_eta(ea, e->stream));
+    CUDA_CHECK(cudaEventRecord(e->ev[EV_END], e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[EV_BEGIN], e->ev[EV_END]);
+    e->prof.eta_synthesis_seconds += 1e-3 * ms;
+    e->prof.kernel_launches += 1;
+    // phases/amplitudes are only needed for the synthesis; keep omega/amp small arrays, free the big ones
+    e->d_phase.release();
+    if (e->per_instance_spectrum) e->d_amp.release();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_waves_irregular_sizes(const hc_ensemble* e, int* nfreq, int* n_eta, int* exc_steps) {
+    if (e->wave_mode != 2) { set_last_error("ensemble has no irregular waves"); return HC_ERR_INVALID; }
+    if (nfreq) *nfreq = e->nf;
+    if (n_eta) *n_eta = e->n_eta;
+    if (exc_steps) for (int b = 0; b < e->N; ++b) exc_steps[b] = int(e->irf[b].t.size());
+    return HC_OK;
+}
+
+hc_status hc_waves_irregular_spectrum(const hc_ensemble* e, int inst, double* freqs, double* S, double* widths,
+                                      double* phases, double* wavenumbers) {
+    HC_GUARD_BEGIN
+    if (e->wave_mode != 2 || e->nf == 0)   // IrregularWaves::GetSpectrum (wave_types.cpp:461-467)
+        fail(HC_ERR_INVALID, "Spectrum has not been created. Initialize with wave height and period to create spectrum.");
+    if (inst < 0 || inst >= e->B) throw std::out_of_range("instance index out of range");
+    const int nf = e->nf;
+    if (freqs) std::copy(e->freqs_h.begin(), e->freqs_h.end(), freqs);
+    if (widths) std::copy(e->widths_h.begin(), e->widths_h.end(), widths);
+    if (wavenumbers) std::copy(e->wavenumbers_h.begin(), e->wavenumbers_h.end(), wavenumbers);
+    if (S) {
+        const size_t s = e->per_instance_spectrum ? inst : 0;
+        std::copy(e->S_h.begin() + s * nf, e->S_h.begin() + (s + 1) * nf, S);
+    }
+    if (phases) std::copy(e->phases_h.begin() + size_t(inst) * nf, e->phases_h.begin() + size_t(inst + 1) * nf, phases);
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_waves_irregular_eta(const hc_ensemble* e, int inst, double* eta_t, double* eta) {
+    HC_GUARD_BEGIN
+    if (e->wave_mode != 2) fail(HC_ERR_INVALID, "ensemble has no irregular waves");
+    if (inst < 0 || inst >= e->B) throw std::out_of_range("instance index out of range");
+    e->use_device();
+    if (eta_t) std::copy(e->eta_t_h.begin(), e->eta_t_h.end(), eta_t);
+    if (eta) {
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        CUDA_CHECK(cudaMemcpy2D(eta, sizeof(double), e->d_eta.p + inst, size_t(e->Bp) * sizeof(double), sizeof(double),
+                                e->n_eta, cudaMemcpyDeviceToHost));
+    }
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_waves_irregular_irf(const hc_ensemble* e, int body, double* t, double* width, double* f) {
+    HC_GUARD_BEGIN
+    if (e->wave_mode != 2) fail(HC_ERR_INVALID, "ensemble has no irregular waves");
+    if (body < 0 || body >= e->N) throw std::out_of_range("body index out of range");
+    const ExcIrfBody& I = e->irf[body];
+    if (t) std::copy(I.t.begin(), I.t.end(), t);
+    if (width) std::copy(I.w.begin(), I.w.end(), width);
+    if (f) std::copy(I.f.begin(), I.f.end(), f);
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_waves_regular_coeffs(const hc_ensemble* e, int inst, double* mag, double* phase, double* wavenumber) {
+    HC_GUARD_BEGIN
+    if (e->wave_mode != 1) fail(HC_ERR_INVALID, "ensemble has no regular waves");
+    if (inst < 0 || inst >= e->B) throw std::out_of_range("instance index out of range");
+    const int i = e->reg_count == 1 ? 0 : inst;
+    if (mag) std::copy(e->reg_mag_h.begin() + size_t(i) * e->D, e->reg_mag_h.begin() + size_t(i + 1) * e->D, mag);
+    if (phase) std::copy(e->reg_phase_h.begin() + size_t(i) * e->D, e->reg_phase_h.begin() + size_t(i + 1) * e->D, phase);
+    if (wavenumber) *wavenumber = e->reg_k_h[i];
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// ---- step ----------------------------------------------------------------------------
+hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, const double* d_vel, const double g[3],
+                         double* d_force, int* recomputed) {
+    HC_GUARD_BEGIN
+    if (!d_pose || !d_vel || !g || !d_force) fail(HC_ERR_INVALID, "null argument");
+    e->use_device();
+    const size_t bytes = size_t(e->B) * e->D * sizeof(double);
+    if (t == e->prev_time) {                                           // time-keyed cache (hydro_forces.cpp:742-744)
+        if (d_force != e->d_force.p)
+            CUDA_CHECK(cudaMemcpyAsync(d_force, e->d_force.p, bytes, cudaMemcpyDeviceToDevice, e->stream));
+        if (recomputed) *recomputed = 0;
+        return HC_OK;
+    }
+    e->run_step(t, g, d_pose, d_vel, e->d_force.p);
+    if (d_force != e->d_force.p)
+        CUDA_CHECK(cudaMemcpyAsync(d_force, e->d_force.p, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    if (recomputed) *recomputed = 1;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* vel, const double g[3], double* force,
+                  int* recomputed) {
+    HC_GUARD_BEGIN
+    if (!pose || !vel || !g || !force) fail(HC_ERR_INVALID, "null argument");
+    e->use_device();
+    const size_t bytes = size_t(e->B) * e->D * sizeof(double);
+    int re = 0;
+    if (t != e->prev_time) {
+        CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+        e->run_step(t, g, e->d_pose.p, e->d_vel.p, e->d_force.p);
+        re = 1;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->events_pending) e->collect_events();
+    if (recomputed) *recomputed = re;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_get_components(hc_ensemble* e, double* hs, double* rad, double* waves) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    const size_t n = size_t(e->B) * e->D;
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (hs) CUDA_CHECK(cudaMemcpy(hs, e->d_comp.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (rad) CUDA_CHECK(cudaMemcpy(rad, e->d_comp.p + n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (waves) CUDA_CHECK(cudaMemcpy(waves, e->d_comp.p + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_sync(hc_ensemble* e) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->events_pending) e->collect_events();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// ---- added mass ----------------------------------------------------------------------
+hc_status hc_added_mass_mv_device(hc_ensemble* e, int n_sys, double c, const double* d_w, double* d_R) {
+    HC_GUARD_BEGIN
+    if (n_sys < e->D) fail(HC_ERR_INVALID, "n_sys must be >= 6 * num_bodies");
+    e->use_device();
+    CUDA_CHECK(launch_added_mass_mv(e->d_ainf.p, n_sys, e->D, c, d_w, d_R, e->B, e->stream));
+    e->prof.kernel_launches += 1;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_added_mass_mv(hc_ensemble* e, int n_sys, double c, const double* w, double* R) {
+    HC_GUARD_BEGIN
+    if (n_sys < e->D) fail(HC_ERR_INVALID, "n_sys must be >= 6 * num_bodies");
+    e->use_device();
+    const size_t n = size_t(e->B) * n_sys;
+    DevBuf<double> dw, dR;
+    dw.alloc(n, false); dR.alloc(n, false);
+    CUDA_CHECK(cudaMemcpyAsync(dw.p, w, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dR.p, R, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(launch_added_mass_mv(e->d_ainf.p, n_sys, e->D, c, dw.p, dR.p, e->B, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(R, dR.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->prof.kernel_launches += 1;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// ---- profiling -----------------------------------------------------------------------
+hc_status hc_set_profiling(hc_ensemble* e, int enable) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->events_pending) e->collect_events();
+    e->profiling = enable != 0;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_get_profile(hc_ensemble* e, hc_profile_stats* out) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->events_pending) e->collect_events();
+    *out = e->prof;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_get_kernel_ms(hc_ensemble* e, double* pre, double* rad, double* exc, double* fin, int reset) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->events_pending) e->collect_events();
+    const double cnt = e->ms_steps > 0 ? double(e->ms_steps) : 1.0;
+    if (pre) *pre = e->acc_ms[0] / cnt;
+    if (rad) *rad = e->acc_ms[1] / cnt;
+    if (exc) *exc = e->acc_ms[2] / cnt;
+    if (fin) *fin = e->acc_ms[3] / cnt;
+    if (reset) { for (double& v : e->acc_ms) v = 0.0; e->ms_steps = 0; }
+    return HC_OK;
+    HC_GUARD_END
+}
+
+void* hc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void hc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

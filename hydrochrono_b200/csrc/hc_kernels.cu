@@ -1,0 +1,541 @@
+// CUDA kernels of the per-step hydrodynamic force path (sm_100a, FP64).
+//
+//   k_prestep     appends the step's velocities to the device-resident history ring and builds the
+//                 instance-independent interpolation plans (bracket + weights per lag) for the radiation
+//                 and excitation convolutions            src/hydro_forces.cpp:559-577,601-610,343-381
+//                                                        src/wave_types.cpp:796-829
+//   k_radiation   batched radiation-damping convolution over the velocity history
+//                                                        src/hydro_forces.cpp:586-647
+//   k_excitation  batched excitation-IRF convolution over the precomputed free-surface elevation
+//                                                        src/wave_types.cpp:552-570,776-844
+//   k_finalize    reduces the lag-chunk partials in fixed order, adds hydrostatics and regular-wave
+//                 excitation, forms total = hydrostatic - radiation + waves
+//                                                        src/hydro_forces.cpp:263-322,758-760; src/wave_types.cpp:315-327
+//   k_eta         free-surface elevation synthesis for every realisation
+//                                                        src/wave_types.cpp:14-59,717-769
+//   k_added_mass_mv  R += c * M * w, batched             src/chloadaddedmass.cpp:55-71
+//
+// Layout: lanes <-> instances.  History ring hist[slot][dof][instance] and eta[sample][instance] are
+// instance-innermost, so a warp reads one contiguous 512-byte segment per (row, dof).  Convolution kernels
+// (K / f*w tiles) are staged per CTA in shared memory with a TMA bulk copy and broadcast to all lanes.
+#include "hc_kernels.cuh"
+
+namespace hc {
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_prestep
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a) {
+    const StepHeader h = *a.hdr;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+
+    // (1) history append: hist[head][c][b] = vel[b][c]   (hydro_forces.cpp:560-574)
+    {
+        double* row = a.hist + (size_t)h.head * a.D * a.Bp;
+        const int n = a.D * a.Bp;
+        for (int i = tid; i < n; i += nth) {
+            const int c = i / a.Bp, b = i - c * a.Bp;
+            row[i] = (b < a.B) ? a.vel[(size_t)b * a.D + c] : 0.0;
+        }
+        if (tid == 0) a.times[h.head] = h.t;
+    }
+
+    // (2) radiation plan.  History index i (0 = newest) lives in ring slot (head - i) mod cap; entry 0 is this
+    //     step (time h.t, written above by another thread, so it is taken from the header).
+    auto hist_time = [&](int i) -> double {
+        if (i == 0) return h.t;
+        int s = h.head - i;
+        if (s < 0) s += h.cap;
+        return a.times[s];
+    };
+    for (int s = tid; s < a.L; s += nth) {
+        int slot_new = 0, slot_old = 0;
+        double wn = 0.0, wo = 0.0, wd = 0.0;
+        if (h.len > 1) {
+            const double q = h.t - a.rirf_t[s];                      // rirf_query_time, :601
+            // AdvanceToBracket (:374-381): smallest i with time(i+1) <= q, i+1 < len
+            if (hist_time(h.len - 1) <= q) {
+                int lo = 0, hi = h.len - 2;                          // answer in [lo, hi]
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (hist_time(mid + 1) <= q) hi = mid; else lo = mid + 1;
+                }
+                const double newer = hist_time(lo), older = hist_time(lo + 1);
+                // InterpolateVelocity6D (:343-371)
+                bool ok = true;
+                if (q == older) { wo = 1.0; wn = 0.0; }
+                else if (q == newer) { wn = 1.0; wo = 0.0; }
+                else if (q > older && q < newer) {
+                    const double delta = newer - older;
+                    wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
+                    wn = 1.0 - wo;
+                    if (h.snap > 0.0) {                              // optional near-exact-hit snapping
+                        if (wo <= h.snap) { wo = 0.0; wn = 1.0; }
+                        else if (wn <= h.snap) { wn = 0.0; wo = 1.0; }
+                    }
+                } else ok = false;                                   // cannot happen for monotone times
+                if (ok) {
+                    wd = a.rirf_w[s];                                // step_width == 0 -> skipped (:622-625)
+                    slot_new = h.head - lo; if (slot_new < 0) slot_new += h.cap;
+                    slot_old = h.head - lo - 1; if (slot_old < 0) slot_old += h.cap;
+                }
+            }
+        }
+        a.pr_new[s] = slot_new; a.pr_old[s] = slot_old;
+        a.pr_wn[s] = wn; a.pr_wo[s] = wo; a.pr_wd[s] = wd;
+    }
+
+    // (3) excitation plan (wave_types.cpp:796-829): largest i with eta_t[i] <= t - tau_j; exact hit or lerp.
+    for (int g = 0; g < a.ngroups; ++g) {
+        for (int j = tid; j < a.Le[g]; j += nth) {
+            const double tt = h.t - a.tau[g][j];
+            int i = (int)floor((tt - a.eta_t[0]) / a.eta_dt);
+            i = max(0, min(i, a.n_eta - 1));
+            while (i > 0 && a.eta_t[i] > tt) --i;
+            while (i + 1 < a.n_eta && a.eta_t[i + 1] <= tt) ++i;
+            double w1 = 1.0, w2 = 0.0;
+            const double t1 = a.eta_t[i];
+            if (tt != t1 && i + 1 < a.n_eta) {
+                const double t2 = a.eta_t[i + 1];
+                w1 = (t2 - tt) / (t2 - t1);
+                w2 = 1.0 - w1;
+            }
+            a.pe_idx[g][j] = i; a.pe_w1[g][j] = w1; a.pe_w2[g][j] = w2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_radiation<D>: one CTA = kTileInst instances x one lag chunk.  acc[ipt][row] over all D columns.
+// ------------------------------------------------------------------------------------------
+struct RadPlanPtrs { const int* nw; const int* od; const double* wn; const double* wo; const double* wd; };
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_radiation(const RadiationArgs a, const RadPlanPtrs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int s0 = blockIdx.y * a.chunk;
+    const int ns = min(a.chunk, a.L - s0);
+    double* Ks = reinterpret_cast<double*>(smem_raw);                    // [chunk][D(col)][D(row)]
+    double* s_wn = Ks + (size_t)a.chunk * D * D;
+    double* s_wo = s_wn + a.chunk;
+    double* s_wd = s_wo + a.chunk;
+    int* s_new = reinterpret_cast<int*>(s_wd + a.chunk);
+    int* s_old = s_new + a.chunk;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_old + a.chunk + (a.chunk & 1));
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)ns * D * D * sizeof(double);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(Ks, a.K + (size_t)s0 * D * D, bytes, bar);
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        s_wn[i] = p.wn[s0 + i]; s_wo[i] = p.wo[s0 + i]; s_wd[i] = p.wd[s0 + i];
+        s_new[i] = p.nw[s0 + i]; s_old[i] = p.od[s0 + i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int b0 = (blockIdx.x * kThreads + threadIdx.x) * kIPT;
+    double acc0[D], acc1[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) { acc0[r] = 0.0; acc1[r] = 0.0; }
+    const size_t row_stride = (size_t)D * a.Bp;
+
+    if (b0 < a.Bp) {
+        for (int s = 0; s < ns; ++s) {
+            const double wd = s_wd[s];
+            if (wd == 0.0) continue;
+            const double wn = s_wn[s], wo = s_wo[s];
+            const double* rn = a.hist + (size_t)s_new[s] * row_stride + b0;
+            const double* ro = a.hist + (size_t)s_old[s] * row_stride + b0;
+            double2 v[D];
+            if (wo == 0.0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) v[c] = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
+            } else if (wn == 0.0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) v[c] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+            } else {
+                double2 u[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    u[c] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+                    v[c] = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) {   // weight_older*older + weight_newer*newer, unfused as on the host
+                    v[c].x = __dadd_rn(__dmul_rn(wo, u[c].x), __dmul_rn(wn, v[c].x));
+                    v[c].y = __dadd_rn(__dmul_rn(wo, u[c].y), __dmul_rn(wn, v[c].y));
+                }
+            }
+            const double* kk = Ks + (size_t)s * D * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const double sx = __dmul_rn(v[c].x, wd), sy = __dmul_rn(v[c].y, wd);   // contribution_scale
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    const double k = kk[c * D + r];
+                    acc0[r] = fma(k, sx, acc0[r]);
+                    acc1[r] = fma(k, sy, acc1[r]);
+                }
+            }
+        }
+        double* out = a.partial + (size_t)blockIdx.y * row_stride + b0;
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+            *reinterpret_cast<double2*>(out + (size_t)r * a.Bp) = make_double2(acc0[r], acc1[r]);
+    }
+}
+
+// Generic fallback for large body counts: D at run time, 6 rows (one body) per z-slice, K read from global/L2.
+__global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationArgs a, const RadPlanPtrs p) {
+    const int s0 = blockIdx.y * a.chunk;
+    const int ns = min(a.chunk, a.L - s0);
+    const int r0 = blockIdx.z * 6;
+    const int D = a.D;
+    const int b0 = (blockIdx.x * kThreads + threadIdx.x) * kIPT;
+    if (b0 >= a.Bp) return;
+    double acc0[6] = {0, 0, 0, 0, 0, 0}, acc1[6] = {0, 0, 0, 0, 0, 0};
+    const size_t row_stride = (size_t)D * a.Bp;
+    for (int s = 0; s < ns; ++s) {
+        const double wd = p.wd[s0 + s];
+        if (wd == 0.0) continue;
+        const double wn = p.wn[s0 + s], wo = p.wo[s0 + s];
+        const double* rn = a.hist + (size_t)p.nw[s0 + s] * row_stride + b0;
+        const double* ro = a.hist + (size_t)p.od[s0 + s] * row_stride + b0;
+        const double* kk = a.K + (size_t)(s0 + s) * D * D;
+        for (int c = 0; c < D; ++c) {
+            double2 v;
+            if (wo == 0.0) v = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
+            else if (wn == 0.0) v = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+            else {
+                const double2 u = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+                v = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
+                v.x = __dadd_rn(__dmul_rn(wo, u.x), __dmul_rn(wn, v.x));
+                v.y = __dadd_rn(__dmul_rn(wo, u.y), __dmul_rn(wn, v.y));
+            }
+            const double sx = __dmul_rn(v.x, wd), sy = __dmul_rn(v.y, wd);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const double k = __ldg(kk + c * D + r0 + r);
+                acc0[r] = fma(k, sx, acc0[r]);
+                acc1[r] = fma(k, sy, acc1[r]);
+            }
+        }
+    }
+    double* out = a.partial + (size_t)blockIdx.y * row_stride + b0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+        *reinterpret_cast<double2*>(out + (size_t)(r0 + r) * a.Bp) = make_double2(acc0[r], acc1[r]);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_excitation<ND>: one CTA = kTileInst instances x one lag chunk of one IRF group.
+// ------------------------------------------------------------------------------------------
+struct ExcPlanPtrs { const int* idx; const double* w1; const double* w2; };
+
+template <int ND>
+__global__ void __launch_bounds__(kThreads) k_excitation(const ExcitationArgs a, const ExcGroup g, const ExcPlanPtrs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int j0 = blockIdx.y * a.chunk;
+    const int nj = min(a.chunk, g.Le - j0);
+    double* Fs = reinterpret_cast<double*>(smem_raw);                    // [chunk][ND]
+    double* s_w1 = Fs + (size_t)a.chunk * ND;
+    double* s_w2 = s_w1 + a.chunk;
+    int* s_idx = reinterpret_cast<int*>(s_w2 + a.chunk);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_idx + a.chunk + (a.chunk & 1));
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)nj * ND * sizeof(double);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(Fs, g.fw + (size_t)j0 * ND, bytes, bar);
+    }
+    for (int i = threadIdx.x; i < nj; i += blockDim.x) {
+        s_w1[i] = p.w1[j0 + i]; s_w2[i] = p.w2[j0 + i]; s_idx[i] = p.idx[j0 + i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int b0 = (blockIdx.x * kThreads + threadIdx.x) * kIPT;
+    if (b0 >= a.Bp) return;
+    double acc0[ND], acc1[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { acc0[d] = 0.0; acc1[d] = 0.0; }
+
+    int prev_idx = -2;
+    double2 prev_e = make_double2(0.0, 0.0);
+    for (int j = 0; j < nj; ++j) {
+        const int idx = s_idx[j];
+        const double w1 = s_w1[j], w2 = s_w2[j];
+        const double2 e1 = __ldg(reinterpret_cast<const double2*>(a.eta + (size_t)idx * a.Bp + b0));
+        double2 ev = e1;
+        if (w2 != 0.0) {
+            // eta row idx+1 is the row the previous lag interpolated from in the common case
+            const double2 e2 = (idx + 1 == prev_idx)
+                                   ? prev_e
+                                   : __ldg(reinterpret_cast<const double2*>(a.eta + (size_t)(idx + 1) * a.Bp + b0));
+            ev.x = __dadd_rn(__dmul_rn(w1, e1.x), __dmul_rn(w2, e2.x));      // w1*eta1 + w2*eta2 (:821-824)
+            ev.y = __dadd_rn(__dmul_rn(w1, e1.y), __dmul_rn(w2, e2.y));
+        }
+        prev_idx = idx; prev_e = e1;
+        const double* ff = Fs + (size_t)j * ND;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double f = ff[d];
+            acc0[d] = fma(f, ev.x, acc0[d]);
+            acc1[d] = fma(f, ev.y, acc1[d]);
+        }
+    }
+    double* out = a.partial + ((size_t)(g.chunk0 + blockIdx.y) * a.ndmax) * a.Bp + b0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) *reinterpret_cast<double2*>(out + (size_t)d * a.Bp) = make_double2(acc0[d], acc1[d]);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_finalize: one thread per instance.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_finalize(const FinalizeArgs a, const HydrostaticTables hs,
+                                                  const FinalizeGroups eg) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const StepHeader h = *a.hdr;
+    const int D = a.D;
+    const double gx = h.g[0], gy = h.g[1], gz = h.g[2];
+    // ChVector3::Length(): sqrt(x*x + y*y + z*z)
+    const double glen = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+    const double rho_g = __dmul_rn(hs.rho, glen);
+    const double* pose = a.pose + (size_t)b * D;
+    double* out = a.force + (size_t)b * D;
+    const size_t BD = (size_t)a.B * D;
+    for (int body = 0; body < a.N; ++body) {
+        // ---- hydrostatics (hydro_forces.cpp:263-322), arithmetic order kept, no FMA contraction ----
+        double disp[6], fh[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) disp[i] = __dsub_rn(pose[6 * body + i], hs.equilibrium[body][i]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s = __dadd_rn(s, __dmul_rn(hs.Kh[body][i * 6 + j], disp[j]));
+            fh[i] = __dmul_rn(-rho_g, s);
+        }
+        const double V = hs.disp_vol[body];
+        const double bx = __dmul_rn(__dmul_rn(hs.rho, -gx), V);
+        const double by = __dmul_rn(__dmul_rn(hs.rho, -gy), V);
+        const double bz = __dmul_rn(__dmul_rn(hs.rho, -gz), V);
+        fh[0] = __dadd_rn(fh[0], bx); fh[1] = __dadd_rn(fh[1], by); fh[2] = __dadd_rn(fh[2], bz);
+        const double rx = hs.cb_minus_cg[body][0], ry = hs.cb_minus_cg[body][1], rz = hs.cb_minus_cg[body][2];
+        fh[3] = __dadd_rn(fh[3], __dsub_rn(__dmul_rn(ry, bz), __dmul_rn(rz, by)));
+        fh[4] = __dadd_rn(fh[4], __dsub_rn(__dmul_rn(rz, bx), __dmul_rn(rx, bz)));
+        fh[5] = __dadd_rn(fh[5], __dsub_rn(__dmul_rn(rx, by), __dmul_rn(ry, bx)));
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int d = 6 * body + i;
+            // ---- radiation: fixed-order sum of lag-chunk partials ----
+            double fr = 0.0;
+            for (int ch = 0; ch < a.rad_nchunk; ++ch) fr += a.rad_partial[((size_t)ch * D + d) * a.Bp + b];
+            // ---- waves ----
+            double fw = 0.0;
+            if (a.wave_mode == 1) {
+                // mag * A * cos(omega t + phase[rowEx])  (wave_types.cpp:322-323; phase of body 0, reference quirk)
+                const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
+                fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
+            } else if (a.wave_mode == 2) {
+                for (int g = 0; g < a.exc_ngroups; ++g) {
+                    if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
+                    const int dl = d - eg.dof0[g];
+                    for (int ch = 0; ch < eg.nchunk[g]; ++ch)
+                        fw += a.exc_partial[((size_t)(eg.chunk0[g] + ch) * a.exc_ndmax + dl) * a.Bp + b];
+                }
+            }
+            out[d] = __dadd_rn(__dsub_rn(fh[i], fr), fw);            // hs - rad + waves (:758-760)
+            if (a.comp) {
+                a.comp[(size_t)b * D + d] = fh[i];
+                a.comp[BD + (size_t)b * D + d] = fr;
+                a.comp[2 * BD + (size_t)b * D + d] = fw;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eta: eta[k][b] = sum_i amp_i cos(k_i*0 - omega_i t_k + phase_{b,i}), ramped.  One thread = one instance
+// x KT consecutive samples; the sum runs over i in ascending order like the reference's loop.
+// ------------------------------------------------------------------------------------------
+constexpr int kEtaKT = 4;
+__global__ void __launch_bounds__(128) k_eta(const EtaArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = blockIdx.y * kEtaKT;
+    if (b >= a.Bp) return;
+    double tk[kEtaKT], acc[kEtaKT];
+#pragma unroll
+    for (int q = 0; q < kEtaKT; ++q) {
+        tk[q] = a.eta_t[min(k0 + q, a.n_eta - 1)];
+        acc[q] = 0.0;
+    }
+    for (int i = 0; i < a.nf; ++i) {
+        const double om = a.omega[i];
+        const double am = a.amp_per_instance ? a.amp[(size_t)i * a.Bp + b] : a.amp[i];
+        const double ph = a.phase[(size_t)i * a.Bp + b];
+#pragma unroll
+        for (int q = 0; q < kEtaKT; ++q) {
+            // wavenumber*x - omega*time + phase with x = 0  ->  (0 - omega*t) + phase, unfused
+            const double arg = __dadd_rn(__dsub_rn(0.0, __dmul_rn(om, tk[q])), ph);
+            acc[q] = __dadd_rn(acc[q], __dmul_rn(am, cos(arg)));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kEtaKT; ++q) {
+        if (k0 + q >= a.n_eta) break;
+        double e = acc[q];
+        if (a.ramp > 0.0 && tk[q] < a.ramp) {                            // wave_types.cpp:759-769
+            if (tk[q] <= 0.0) e = __dmul_rn(e, 0.0);
+            else e = __dmul_rn(e, __ddiv_rn(tk[q], a.ramp));
+        }
+        a.eta[(size_t)(k0 + q) * a.Bp + b] = e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_added_mass_mv: R[b][i] += sum_j (c*M[i][j]) * w[b][j];  M is the padded n_sys x n_sys matrix.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_added_mass_mv(const double* __restrict__ M, int n_sys, int D, double c,
+                                                       const double* __restrict__ w, double* __restrict__ R, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* wb = w + (size_t)b * n_sys;
+    double* Rb = R + (size_t)b * n_sys;
+    // rows/cols >= D of M_sys are zero (chloadaddedmass.cpp:35-44): adding c*0*w changes nothing
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < D; ++j) s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, M[(size_t)i * D + j]), wb[j]));
+        Rb[i] = __dadd_rn(Rb[i], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers (host)
+// ------------------------------------------------------------------------------------------
+size_t radiation_smem_bytes(int D, int chunk) {
+    return (size_t)chunk * D * D * 8 + (size_t)chunk * 3 * 8 + (size_t)(chunk + (chunk & 1)) * 2 * 4 + 16;
+}
+size_t excitation_smem_bytes(int nd, int chunk) {
+    return (size_t)chunk * nd * 8 + (size_t)chunk * 2 * 8 + (size_t)(chunk + (chunk & 1)) * 4 + 16;
+}
+
+template <int D>
+static cudaError_t launch_rad_t(const RadiationArgs& a, const RadPlanPtrs& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_radiation<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    k_radiation<D><<<grid, kThreads, smem, st>>>(a, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const int* pr_old, const double* pr_wn,
+                             const double* pr_wo, const double* pr_wd, cudaStream_t st) {
+    RadPlanPtrs p{pr_new, pr_old, pr_wn, pr_wo, pr_wd};
+    dim3 grid((a.Bp + kTileInst - 1) / kTileInst, a.nchunk, 1);
+    const size_t smem = radiation_smem_bytes(a.D, a.chunk);
+    switch (a.D) {
+        case 6: return launch_rad_t<6>(a, p, grid, smem, st);
+        case 12: return launch_rad_t<12>(a, p, grid, smem, st);
+        default:
+            grid.z = a.D / 6;
+            k_radiation_generic<<<grid, kThreads, 0, st>>>(a, p);
+            return cudaGetLastError();
+    }
+}
+
+template <int ND>
+static cudaError_t launch_exc_t(const ExcitationArgs& a, const ExcGroup& g, const ExcPlanPtrs& p, dim3 grid, size_t smem,
+                                cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_excitation<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    k_excitation<ND><<<grid, kThreads, smem, st>>>(a, g, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const int* idx, const double* w1,
+                              const double* w2, cudaStream_t st) {
+    ExcPlanPtrs p{idx, w1, w2};
+    dim3 grid((a.Bp + kTileInst - 1) / kTileInst, g.nchunk, 1);
+    const size_t smem = excitation_smem_bytes(g.nd, a.chunk);
+    switch (g.nd) {
+        case 6: return launch_exc_t<6>(a, g, p, grid, smem, st);
+        case 12: return launch_exc_t<12>(a, g, p, grid, smem, st);
+        default: return cudaErrorInvalidValue;   // groups are formed with nd in {6, 12} only
+    }
+}
+
+cudaError_t launch_prestep(const PrestepArgs& a, cudaStream_t st) {
+    const int work = max(a.D * a.Bp, a.L);
+    int blocks = (work + 255) / 256;
+    blocks = max(1, min(blocks, 148 * 8));
+    k_prestep<<<blocks, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                            cudaStream_t st) {
+    k_finalize<<<(a.B + 127) / 128, 128, 0, st>>>(a, hs, eg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st) {
+    dim3 grid((a.Bp + 127) / 128, (a.n_eta + kEtaKT - 1) / kEtaKT);
+    k_eta<<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_added_mass_mv(const double* M, int n_sys, int D, double c, const double* w, double* R, int B,
+                                 cudaStream_t st) {
+    k_added_mass_mv<<<(B + 127) / 128, 128, 0, st>>>(M, n_sys, D, c, w, R, B);
+    return cudaGetLastError();
+}
+
+}  // namespace hc

@@ -1,0 +1,132 @@
+// Device-side data structures and kernel launch wrappers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hc {
+
+constexpr int kMaxBodies = 8;        // static hydrostatics tables live in kernel-parameter space
+constexpr int kThreads = 256;        // CTA size of the convolution kernels
+constexpr int kIPT = 2;              // instances per thread (one 16-byte load per history value pair)
+constexpr int kTileInst = kThreads * kIPT;
+
+// Written by the host for every step (pinned -> device copy), read by every kernel of the step so that the
+// captured CUDA graph is static.
+struct StepHeader {
+    double t;
+    double g[3];
+    double snap;       // bracket snap tolerance (0 = faithful)
+    int head;          // ring slot of the newest history entry
+    int len;           // history entries after pruning (newest first)
+    int cap;           // ring capacity
+    int flags;
+};
+
+struct HydrostaticTables {
+    double rho;
+    double Kh[kMaxBodies][36];
+    double disp_vol[kMaxBodies];
+    double cb_minus_cg[kMaxBodies][3];
+    double equilibrium[kMaxBodies][6];
+};
+
+struct RadiationArgs {
+    const StepHeader* hdr;
+    const double* K;          // [RT][L][D][DR]
+    const double* rirf_t;     // [L]
+    const double* rirf_w;     // [L]
+    const double* hist;       // [cap][D][Bp]
+    const double* times;      // [cap]
+    double* partial;          // [nchunk][D][Bp]
+    int L, D, Bp, chunk, nchunk;
+};
+
+struct ExcGroup {             // bodies sharing one excitation-IRF time grid
+    const double* tau;        // [Le]
+    const double* fw;         // [Le][nd]   f * width, dof fastest
+    int Le, nd, dof0;         // dofs [dof0, dof0+nd) of the 6N vector
+    int chunk0;               // first partial chunk index of this group
+    int nchunk;
+};
+
+struct ExcitationArgs {
+    const StepHeader* hdr;
+    const double* eta;        // [n_eta][Bp]
+    const double* eta_t;      // [n_eta]
+    double* partial;          // [total chunks][ndmax][Bp]
+    double eta_dt;            // nominal grid spacing (index guess only)
+    int n_eta, Bp, chunk, ndmax;
+};
+
+struct FinalizeArgs {
+    const StepHeader* hdr;
+    const double* pose;       // [B][D]
+    const double* rad_partial;
+    const double* exc_partial;
+    double* force;            // [B][D]
+    double* comp;             // [3][B][D] hydrostatic, radiation, waves
+    // regular waves (SoA over instances)
+    const double* reg_amp;    // [Bp]
+    const double* reg_omega;  // [Bp]
+    const double* reg_mag;    // [D][Bp]
+    const double* reg_phase;  // [6][Bp]  (body 0's phases, reference quirk wave_types.cpp:323)
+    int B, Bp, D, N;
+    int rad_nchunk;
+    int wave_mode;            // 0 none, 1 regular, 2 irregular
+    int exc_ngroups;
+    int exc_ndmax;
+};
+
+struct EtaArgs {
+    const double* eta_t;      // [n_eta]
+    const double* omega;      // [nf]    2*pi*f
+    const double* amp;        // [nf] shared, or [nf][Bp] per instance
+    const double* phase;      // [nf][Bp]
+    double* eta;              // [n_eta][Bp]
+    double ramp;
+    int n_eta, nf, Bp, amp_per_instance;
+};
+
+struct PrestepArgs {
+    const StepHeader* hdr;
+    const double* vel;     // [B][D]
+    double* hist;          // [cap][D][Bp]
+    double* times;         // [cap]
+    const double* rirf_t;  // [L]
+    const double* rirf_w;  // [L]
+    int* pr_new;           // [L] ring slot of the newer bracket sample
+    int* pr_old;           // [L]
+    double* pr_wn;         // [L] weight of the newer sample
+    double* pr_wo;         // [L] weight of the older sample
+    double* pr_wd;         // [L] trapezoid width (0 = lag skipped)
+    int B, Bp, D, L;
+    // excitation
+    int ngroups;
+    const double* tau[kMaxBodies];
+    int Le[kMaxBodies];
+    int* pe_idx[kMaxBodies];
+    double* pe_w1[kMaxBodies];
+    double* pe_w2[kMaxBodies];
+    const double* eta_t;
+    int n_eta;
+    double eta_dt;
+};
+
+struct FinalizeGroups {
+    int dof0[kMaxBodies], nd[kMaxBodies], chunk0[kMaxBodies], nchunk[kMaxBodies];
+};
+
+size_t radiation_smem_bytes(int D, int chunk);
+size_t excitation_smem_bytes(int nd, int chunk);
+cudaError_t launch_prestep(const PrestepArgs& a, cudaStream_t st);
+cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const int* pr_old, const double* pr_wn,
+                             const double* pr_wo, const double* pr_wd, cudaStream_t st);
+cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const int* idx, const double* w1,
+                              const double* w2, cudaStream_t st);
+cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                            cudaStream_t st);
+cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st);
+cudaError_t launch_added_mass_mv(const double* M, int n_sys, int D, double c, const double* w, double* R, int B,
+                                 cudaStream_t st);
+
+}  // namespace hc

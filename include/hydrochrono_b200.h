@@ -1,0 +1,260 @@
+/* =====================================================================================
+ * hydrochrono_b200.h -- C ABI of the B200-native hydrodynamic force path.
+ *
+ * Drop-in boundary for HydroChrono's per-timestep force computation (reference paths are
+ * relative to the HydroChrono source tree):
+ *
+ *   hc_tables_*        replaces  H5FileInfo::ReadH5Data / HydroData          src/h5fileinfo.cpp:27-91,309-343
+ *                                + TestHydro ctor tables (widths, equilibrium) src/hydro_forces.cpp:170-216
+ *                                + TestHydro::EnsureProcessedRIRF             src/hydro_forces.cpp:385-535
+ *   hc_ensemble_*      replaces  TestHydro state (velocity history, cache)    include/hydroc/hydro_forces.h:286-340
+ *   hc_waves_*         replaces  NoWave / RegularWave / IrregularWaves setup  src/wave_types.cpp:257-352,432-459,
+ *                                                                             572-774
+ *   hc_step*           replaces  TestHydro::CoordinateFuncForBody recompute:  src/hydro_forces.cpp:727-767
+ *                                ComputeForceHydrostatics (:263-322), ComputeForceRadiationDampingConv (:537-691),
+ *                                ComputeForceWaves (:713-725) -> WaveBase::GetForceAtTime
+ *                                (src/wave_types.cpp:257-264,315-327,552-570,776-844)
+ *   hc_added_mass*     replaces  ChLoadAddedMass ctor / ComputeJacobian / LoadIntLoadResidual_Mv
+ *                                                                             src/chloadaddedmass.cpp:12-71
+ *   hc_get_profile     replaces  TestHydro::GetProfileStats                   include/hydroc/hydro_forces.h:153-160,284
+ *
+ * One ensemble = B independent copies ("instances") of one TestHydro: same hydro tables, own body
+ * state, own velocity history, own wave realisation.  B = 1 is the reference's single system.
+ * All instances are stepped in lockstep (same t).  Everything is FP64.
+ *
+ * Conventions: plain pointers and sizes only.  Every function returns an hc_status (0 = ok);
+ * hc_last_error() gives the thread-local message.  Exceptions the reference would throw map to
+ * status codes (see each function).  Handles are not thread-safe: one host thread per handle.
+ * There is NO CPU fallback: every compute entry point requires a CUDA device and fails with
+ * HC_ERR_CUDA otherwise.
+ * ===================================================================================== */
+#ifndef HYDROCHRONO_B200_H
+#define HYDROCHRONO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_API __attribute__((visibility("default")))
+
+typedef enum hc_status {
+    HC_OK = 0,
+    HC_ERR_INVALID = 1,       /* bad argument / bad table shape                     (std::runtime_error)   */
+    HC_ERR_OUT_OF_RANGE = 2,  /* index / frequency outside tables                   (std::out_of_range)    */
+    HC_ERR_CUDA = 3,          /* CUDA runtime failure or no device                                          */
+    HC_ERR_DUPLICATE_TIME = 4,/* radiation convolution evaluated twice at one time  hydro_forces.cpp:555-557*/
+    HC_ERR_ETA_WINDOW = 5,    /* t - tau outside the precomputed eta window         wave_types.cpp:833-840  */
+    HC_ERR_IO = 6,            /* cannot open / parse HDF5 file                      h5fileinfo.cpp:172-181  */
+    HC_ERR_TIME_ORDER = 7,    /* time went backwards (history no longer bracketed)  hydro_forces.cpp:370    */
+    HC_ERR_CAPACITY = 8       /* velocity-history ring too small for this dt                               */
+} hc_status;
+
+typedef struct hc_tables hc_tables;
+typedef struct hc_ensemble hc_ensemble;
+
+HC_API const char* hc_last_error(void);
+HC_API const char* hc_version(void);
+HC_API int hc_device_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Hydro tables (HydroData).  Arrays are the RAW values of the BEMIO .h5 datasets, row-major:
+ *   rirf_t [N][L], rirf_K [N][6][6N][L], lin_matrix [N][6][6], inf_added_mass [N][6][6N],
+ *   disp_vol [N], cg/cb [N][3], w [nw], exc_mag/exc_phase [N][6][nw] (wave direction 0),
+ *   exc_irf_t [N][Le0], exc_irf_f [N][6][Le0].
+ * Scalings (x rho, x rho*g) are applied inside exactly where the reference applies them.
+ * nw or Le0 may be 0 (no regular / irregular wave data).
+ * ------------------------------------------------------------------------------------- */
+typedef struct hc_tables_desc {
+    int num_bodies;
+    int rirf_steps;          /* L   */
+    int num_freqs;           /* nw  */
+    int exc_irf_steps;       /* Le0 */
+    double rho, g, water_depth;   /* water_depth may be +inf ("infinite" in the file) */
+    const double* rirf_t;
+    const double* rirf_K;
+    const double* lin_matrix;
+    const double* inf_added_mass;
+    const double* disp_vol;
+    const double* cg;
+    const double* cb;
+    const double* w;
+    const double* exc_mag;
+    const double* exc_phase;
+    const double* exc_irf_t;
+    const double* exc_irf_f;
+} hc_tables_desc;
+
+HC_API hc_status hc_tables_create(const hc_tables_desc* desc, hc_tables** out);
+/* H5FileInfo(file, num_bodies).ReadH5Data(): built-in classic-HDF5 reader, no libhdf5. */
+HC_API hc_status hc_tables_load_h5(const char* path, int num_bodies, hc_tables** out);
+HC_API void hc_tables_destroy(hc_tables* t);
+
+/* HydroData getters (include/hydroc/h5fileinfo.h:102-225) */
+HC_API int hc_tables_num_bodies(const hc_tables* t);
+HC_API int hc_tables_rirf_steps(const hc_tables* t);                 /* GetRIRFDims(2) */
+HC_API int hc_tables_num_freqs(const hc_tables* t);
+HC_API int hc_tables_exc_irf_steps(const hc_tables* t);
+HC_API double hc_tables_rho(const hc_tables* t);                     /* GetRhoVal */
+HC_API double hc_tables_g(const hc_tables* t);
+HC_API double hc_tables_water_depth(const hc_tables* t);
+HC_API hc_status hc_tables_rirf_time(const hc_tables* t, double* out /*[L]*/);       /* GetRIRFTimeVector */
+HC_API hc_status hc_tables_rirf_width(const hc_tables* t, double* out /*[L]*/);      /* hydro_forces.cpp:181-190 */
+/* TestHydro::GetRIRFval(row, col, st): rho-scaled (or TaperedDirect-processed) kernel value */
+HC_API hc_status hc_tables_rirf_val(const hc_tables* t, int row, int col, int st, double* out);
+HC_API hc_status hc_tables_rirf_all(const hc_tables* t, double* out /*[6N][6N][L]*/);
+HC_API hc_status hc_tables_lin_matrix(const hc_tables* t, int body, double* out /*[36]*/);   /* GetLinMatrix */
+HC_API hc_status hc_tables_hydrostatic_stiffness(const hc_tables* t, int body, int i, int j, double* out);
+HC_API hc_status hc_tables_inf_added_mass(const hc_tables* t, int body, double* out /*[6][6N], x rho*/);
+HC_API hc_status hc_tables_disp_vol(const hc_tables* t, int body, double* out);
+HC_API hc_status hc_tables_cg(const hc_tables* t, int body, double* out /*[3]*/);
+HC_API hc_status hc_tables_cb(const hc_tables* t, int body, double* out /*[3]*/);
+
+/* TestHydro::SetRadiationConvolutionMode + SetTaperedDirectOptions (hydro_forces.h:233-265).
+ * mode 0 = Baseline, 1 = TaperedDirect.  smoothing: "moving_average" selects the moving average, anything else
+ * the 5-point Savitzky-Golay branch (hydro_forces.cpp:433-457).  Must be called before ensembles are created. */
+typedef struct hc_tapered_opts {
+    const char* smoothing;
+    int window_length;
+    double rirf_end_time;
+    double taper_start_percent;
+    double taper_end_percent;
+    double taper_final_amplitude;
+} hc_tapered_opts;
+HC_API hc_status hc_tables_set_convolution_mode(hc_tables* t, int mode, const hc_tapered_opts* opts);
+
+/* ChLoadAddedMass (src/chloadaddedmass.cpp:12-52): the 6N x 6N infinite-frequency added-mass matrix,
+ * zero-padded to n_sys x n_sys with the block at (0,0).  n_sys >= 6N.  Host table op. */
+HC_API hc_status hc_added_mass(const hc_tables* t, int n_sys, double* M_out /*[n_sys][n_sys]*/);
+
+/* ---------------------------------------------------------------------------------------
+ * Ensemble
+ * ------------------------------------------------------------------------------------- */
+typedef struct hc_ensemble_opts {
+    int device;               /* CUDA device ordinal */
+    int batch;                /* B, number of instances on this device */
+    double dt_hint;           /* expected step size; sizes the velocity-history ring (rirf window / dt + slack).
+                                 <= 0: ring sized for rirf_t spacing. The ring grows on demand.          */
+    double bracket_snap;      /* 0 = bit-faithful bracketing (==, as the reference).  > 0: a convolution query
+                                 time within snap*(t_newer - t_older) of a history sample is treated as an exact
+                                 hit (skips reading the second, ~zero-weight row).  See DESIGN.md.      */
+    int rad_chunk;            /* radiation lags per CTA (0 = auto)   */
+    int exc_chunk;            /* excitation lags per CTA (0 = auto)  */
+    int use_graph;            /* 1: capture the per-step kernel sequence in a CUDA graph (default 1) */
+    void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
+} hc_ensemble_opts;
+
+HC_API void hc_ensemble_default_opts(hc_ensemble_opts* o);
+HC_API hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, hc_ensemble** out);
+HC_API void hc_ensemble_destroy(hc_ensemble* e);
+HC_API int hc_ensemble_batch(const hc_ensemble* e);
+HC_API int hc_ensemble_dofs(const hc_ensemble* e);      /* 6N */
+/* Drops the velocity history and the time cache (a fresh TestHydro), keeps the waves. */
+HC_API hc_status hc_ensemble_reset(hc_ensemble* e);
+/* Pinned host staging owned by the ensemble ([B][6N] each).  Filling/reading these in place makes hc_step
+ * copy-free on the host side. */
+HC_API hc_status hc_ensemble_host_buffers(hc_ensemble* e, double** pose, double** vel, double** force);
+
+/* ---- waves (TestHydro::AddWaves, src/hydro_forces.cpp:244-261) ---- */
+HC_API hc_status hc_waves_none(hc_ensemble* e);                               /* NoWave */
+/* RegularWave (src/wave_types.cpp:266-352).  Arrays have length B, or stride 0 semantics when count == 1
+ * (one wave shared by all instances). */
+HC_API hc_status hc_waves_regular(hc_ensemble* e, int count, const double* amplitude, const double* omega,
+                                  const double* phase /* may be NULL -> 0 */);
+/* IrregularWaves(IrregularWaveParams) (include/hydroc/wave_types.h:277-292, src/wave_types.cpp:430-459). */
+typedef struct hc_irregular_params {
+    double simulation_dt;
+    double simulation_duration;
+    double ramp_duration;
+    double wave_height;              /* Hs */
+    double wave_period;              /* Tp */
+    double frequency_min;            /* default 0.001 */
+    double frequency_max;            /* default 1.0   */
+    double nfrequencies;             /* 0 = ceil((fmax-fmin)*duration) */
+    double peak_enhancement_factor;  /* gamma, default 1.0 */
+    int is_normalized;
+    int seed;                        /* default 1; ignored when per-instance seeds are given */
+} hc_irregular_params;
+HC_API void hc_irregular_default_params(hc_irregular_params* p);
+/* seeds: NULL (every instance uses p->seed) or [B] (instance b uses std::mt19937(seeds[b])).
+ * wave_height / wave_period: NULL (shared p->...) or [B] per-instance sea states.
+ * Synthesises eta for every instance on the device (src/wave_types.cpp:27-59,717-774). */
+HC_API hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const int* seeds,
+                                    const double* wave_height, const double* wave_period);
+/* Introspection of the irregular-wave setup (IrregularWaves::GetSpectrum / GetFreeSurfaceElevation /
+ * GetFreeSurfaceTime / GetFrequenciesHz, wave_types.h:300-309). */
+HC_API hc_status hc_waves_irregular_sizes(const hc_ensemble* e, int* nfreq, int* n_eta, int* exc_steps /*[N]*/);
+HC_API hc_status hc_waves_irregular_spectrum(const hc_ensemble* e, int instance, double* freqs_hz, double* S,
+                                             double* widths, double* phases, double* wavenumbers); /* any NULL */
+HC_API hc_status hc_waves_irregular_eta(const hc_ensemble* e, int instance, double* eta_t, double* eta); /* D2H */
+HC_API hc_status hc_waves_irregular_irf(const hc_ensemble* e, int body, double* t, double* width,
+                                        double* f /*[6][Le]*/);
+HC_API hc_status hc_waves_regular_coeffs(const hc_ensemble* e, int instance, double* mag /*[6N]*/,
+                                         double* phase /*[6N]*/, double* wavenumber);
+
+/* ---- per-step force (TestHydro::CoordinateFuncForBody, src/hydro_forces.cpp:727-767) ----
+ * pose  [B][6N]: per body (x, y, z, Cardan-XYZ roll, pitch, yaw)   -- GetPos(), GetRot().GetCardanAnglesXYZ()
+ * vel   [B][6N]: per body (GetPosDt(), GetAngVelParent())
+ * g_vec [3]    : system gravitational acceleration vector
+ * force [B][6N]: total = hydrostatic - radiation + waves
+ * Calling twice with the same t returns the cached forces (status HC_OK, *recomputed = 0), like the reference's
+ * time-keyed cache; a new t appends (t, vel) to the history and recomputes.
+ * Host-pointer version: H2D, kernels, D2H, synchronous at return. */
+HC_API hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* vel, const double g_vec[3],
+                         double* force, int* recomputed /* may be NULL */);
+/* Device-pointer version: pointers are device memory on the ensemble's device; asynchronous on the
+ * ensemble's stream (use hc_sync or the caller's own stream ordering). */
+HC_API hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, const double* d_vel,
+                                const double g_vec[3], double* d_force, int* recomputed);
+/* Components of the last evaluation (ComputeForceHydrostatics / RadiationDampingConv / Waves), host [B][6N]
+ * each; any may be NULL. */
+HC_API hc_status hc_get_components(hc_ensemble* e, double* hydrostatic, double* radiation, double* waves);
+HC_API hc_status hc_sync(hc_ensemble* e);
+HC_API int hc_ensemble_history_len(const hc_ensemble* e);
+
+/* ChLoadAddedMass::LoadIntLoadResidual_Mv (src/chloadaddedmass.cpp:55-71), batched: R[b] += c * M_sys * w[b]
+ * for every instance.  w, R host [B][n_sys]. */
+HC_API hc_status hc_added_mass_mv(hc_ensemble* e, int n_sys, double c, const double* w, double* R);
+HC_API hc_status hc_added_mass_mv_device(hc_ensemble* e, int n_sys, double c, const double* d_w, double* d_R);
+
+/* HydroProfileStats (include/hydroc/hydro_forces.h:153-160), fed by CUDA events. */
+typedef struct hc_profile_stats {
+    double hydrostatics_seconds;
+    double radiation_seconds;
+    double waves_seconds;
+    int hydrostatics_calls;
+    int radiation_calls;
+    int waves_calls;
+    double eta_synthesis_seconds;   /* one-off, hc_waves_irregular */
+    double step_seconds;            /* whole per-step kernel sequence */
+    long long kernel_launches;      /* kernels of this library launched so far */
+} hc_profile_stats;
+/* enable = 1 inserts CUDA events around each kernel group (adds sync cost at read time only). */
+HC_API hc_status hc_set_profiling(hc_ensemble* e, int enable);
+HC_API hc_status hc_get_profile(hc_ensemble* e, hc_profile_stats* out);
+/* Average device time (ms) of the radiation / excitation / finalize kernels since the last call (needs profiling). */
+HC_API hc_status hc_get_kernel_ms(hc_ensemble* e, double* prestep_ms, double* radiation_ms, double* excitation_ms,
+                                  double* finalize_ms, int reset);
+
+/* Pinned host memory helpers for callers that keep their own buffers. */
+HC_API void* hc_host_alloc(size_t bytes);
+HC_API void hc_host_free(void* p);
+
+/* ---- stand-alone wave helpers on the reference's public surface (host, setup-time) ---- */
+HC_API hc_status hc_pierson_moskowitz_spectrum_hz(int n, const double* f, double Hs, double Tp, double* S);
+HC_API hc_status hc_jonswap_spectrum_hz(int n, const double* f, double Hs, double Tp, double gamma,
+                                        int is_normalized, double* S);
+HC_API hc_status hc_compute_wave_number(double omega, double water_depth, double g, double* k);
+/* IrregularWaves::ResampleIRF + CalculateWidthIRF (src/wave_types.cpp:572-628) for one body: excitation IRF resampled
+ * to ceil((t1-t0)/dt) points with Eigen's cubic B-spline fit.  Call with t_out == NULL to query *n_out. */
+HC_API hc_status hc_resample_excitation_irf(const hc_tables* t, double dt, int body, int* n_out, double* t_out,
+                                            double* width_out, double* f_out /*[6][n]*/);
+/* Random phases of CreateSpectrum (src/wave_types.cpp:663-669): std::mt19937(seed), uniform_real(0, 2 pi). */
+HC_API hc_status hc_random_phases(int seed, int n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROCHRONO_B200_H */

@@ -486,7 +486,9 @@ static void CreateFreeSurfaceElevation(Waves& W) {
     W.eta_t = LinSpaced(num_timesteps + 1, 0, num_timesteps * p.simulation_dt);
     for (size_t ii = 0; ii < W.eta_t.size(); ii++) W.eta_t[ii] += -t_irf_max;
     W.eta.resize(W.eta_t.size());
-    for (size_t j = 0; j < W.eta_t.size(); ++j) W.eta[j] = EtaIrregular(0.0, W.eta_t[j], W);
+    // (samples are independent; the OpenMP loop only speeds up test set-up, each sample's sum order is unchanged)
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < (long)W.eta_t.size(); ++j) W.eta[j] = EtaIrregular(0.0, W.eta_t[j], W);
     if (p.ramp_duration > 0.0) {
         for (size_t i = 0; i < W.eta_t.size(); ++i) {
             if (W.eta_t[i] < p.ramp_duration) {

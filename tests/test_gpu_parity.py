@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north star): every force component at every step within 1e-9 relative of the reference computation,
+with an absolute floor of 1e-9 * 1e-3 * max_t|F component| for components that cross zero
+(common.force_tol).  Trajectories: within the reference's regression gates against its golden files.
+"""
+import numpy as np
+import pytest
+
+import common
+import stepper
+import hydrochrono_b200 as hc
+from hydrochrono_b200 import synth
+from oracle import hc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+G981 = (0.0, 0.0, -9.81)
+
+
+def _motion(D, B, t, seed=3):
+    amp, om = synth.prescribed_motion(D, seed)
+    ph = 0.37 * np.arange(B)[:, None] + 0.11 * np.arange(D)[None, :]
+    pose = amp * np.sin(om * t + ph)
+    vel = amp * om * np.cos(om * t + ph)
+    return pose, vel
+
+
+def _assert_parity(got, ref, what, rel=1e-9):
+    got, ref = np.asarray(got), np.asarray(ref)
+    tol = common.force_tol(ref, rel=rel)
+    err = np.abs(got - ref)
+    worst = np.unravel_index(np.argmax(err / tol), err.shape)
+    assert np.all(err <= tol), "%s: worst at %s: got %r ref %r (err/tol %.3g)" % (
+        what, worst, got[worst], ref[worst], (err / tol)[worst])
+    return float((err / np.maximum(np.abs(ref), 1e-300)).max())
+
+
+def _run_pair(ens, insts, times, D, gvec=G981, seed=3):
+    """Steps the GPU ensemble and the oracle instances through the same prescribed motion."""
+    B = len(insts)
+    tot, hs, rad, wv = [np.empty((len(times), B, D)) for _ in range(4)]
+    rtot, rhs, rrad, rwv = [np.empty((len(times), B, D)) for _ in range(4)]
+    for n, t in enumerate(times):
+        pose, vel = _motion(D, B, t, seed)
+        tot[n] = ens.step(t, pose, vel, gvec)
+        hs[n], rad[n], wv[n] = ens.components()
+        for b, inst in enumerate(insts):
+            rtot[n, b], rhs[n, b], rrad[n, b], rwv[n, b] = inst.force(t, pose[b], vel[b], gvec, components=True)
+    return (tot, hs, rad, wv), (rtot, rhs, rrad, rwv)
+
+
+def _acc_times(n, dt):
+    """t_{k+1} = t_k + dt, as Chrono advances ChTime."""
+    t = np.empty(n)
+    x = 0.0
+    for i in range(n):
+        t[i] = x
+        x += dt
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# sphere (real BEMIO tables)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def sphere():
+    raw = common.sphere_raw()
+    return hc.Tables.from_raw(raw), orc.Tables(raw)
+
+
+def test_sphere_decay_trajectory_and_forces(sphere):
+    """BASELINE config 0: sphere heave decay through the GPU path, single instance (B = 1)."""
+    T, O = sphere
+    ens = hc.Ensemble(T, batch=1, dt_hint=common.SPHERE_DT)
+    inst = orc.Instance(O)
+    gold = common.sphere_goldens()["decay_um"] * 1e-6
+    pose0 = np.zeros(6)
+    pose0[2] = -1.0
+    rec_g, rec_o = [], []
+
+    def f_gpu(t, x, v):
+        F = ens.step(t, x[None, :], v[None, :], G981)[0].copy()
+        rec_g.append(F)
+        rec_o.append(inst.force(t, x, v, G981))
+        return F
+
+    t, x = stepper.run(f_gpu, T.added_mass(), [common.SPHERE_MASS], [[1.0, 1.0, 1.0]], pose0, common.SPHERE_DT, gold.size)
+    n1, n2 = common.traj_norms(x[:, 2], gold)
+    assert n1 <= 1e-4 and n2 <= 0.02 and n2 <= 1e-6, (n1, n2)
+    _assert_parity(np.array(rec_g), np.array(rec_o), "sphere decay total force")
+    assert ens.history_len() == inst.history_len()
+
+
+def test_sphere_regular_and_hydrostatics_bitwise(sphere):
+    T, O = sphere
+    B = 5
+    ens = hc.Ensemble(T, batch=B, dt_hint=common.SPHERE_DT)
+    amps = np.array(common.TASK10_AMPS[:B])
+    oms = np.array(common.TASK10_OMEGAS[:B])
+    ens.set_waves_regular(amps, oms)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_regular(amps[b], oms[b])
+        insts.append(i)
+        mag, ph, k = ens.regular_coeffs(b)
+        rmag, rph, rk = i.regular()
+        np.testing.assert_array_equal(mag, rmag)
+        np.testing.assert_array_equal(ph, rph)
+        assert k == rk
+    times = _acc_times(1300, common.SPHERE_DT)        # beyond the 1001-lag window: pruning active
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 6)
+    np.testing.assert_array_equal(hs, rhs)            # same arithmetic order, no FMA contraction
+    _assert_parity(rad, rrad, "radiation")
+    _assert_parity(wv, rwv, "regular-wave excitation")
+    _assert_parity(tot, rtot, "total")
+    assert ens.history_len() == insts[0].history_len()
+
+
+def test_sphere_irregular_eta_and_forces(sphere):
+    T, O = sphere
+    B = 3
+    seeds = [1, 2, 77]
+    ens = hc.Ensemble(T, batch=B, dt_hint=common.SPHERE_DT)
+    kw = dict(dt=common.SPHERE_DT, duration=40.0, ramp=10.0, Hs=2.0, Tp=12.0, fmin=0.001, fmax=1.0, nfreq=500,
+              gamma=1.0)
+    ens.set_waves_irregular(seeds=seeds, **kw)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular(seed=seeds[b], share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+        g, r = ens.irregular(b), i.irregular()
+        for k in ("freqs", "S", "widths", "phases", "wavenumbers", "eta_t"):
+            np.testing.assert_array_equal(g[k], r[k], err_msg=k)
+        # eta: identical operation order; device cos vs libm cos differ by <= 2 ulp per term
+        assert np.abs(g["eta"] - r["eta"]).max() <= 1e-12 * np.abs(r["eta"]).max()
+        assert g["eta"][g["eta_t"] <= 0].max() == 0.0 and np.abs(g["eta"]).max() > 0.1
+    times = _acc_times(600, common.SPHERE_DT)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 6)
+    _assert_parity(wv, rwv, "irregular excitation")
+    _assert_parity(rad, rrad, "radiation")
+    _assert_parity(tot, rtot, "total")
+
+
+def test_sphere_irregular_golden_trajectory(sphere):
+    """The reference's irregular-wave regression case end to end through the GPU path (first 100 s)."""
+    T, O = sphere
+    ens = hc.Ensemble(T, batch=1, dt_hint=common.SPHERE_DT)
+    ens.set_waves_irregular(dt=common.SPHERE_DT, duration=600.0, ramp=60.0, Hs=2.0, Tp=12.0, nfreq=1000, gamma=1.0,
+                            seed=1)
+    assert ens.irregular_sizes() == (1000, 56668, [8334])
+    nsteps = 6700
+    gold = common.sphere_goldens()["irreg_um"][:nsteps] * 1e-6
+    pose0 = np.zeros(6)
+    pose0[2] = -2.0
+    free = np.zeros(6, bool)
+    free[2] = True
+    t, x = stepper.run(lambda t, p, v: ens.step(t, p[None, :], v[None, :], G981)[0], T.added_mass(),
+                       [common.SPHERE_MASS], [[1.0, 1.0, 1.0]], pose0, common.SPHERE_DT, nsteps, free=free)
+    n1, n2 = common.traj_norms(x[:, 2], gold)
+    assert n1 <= 1e-4 and n2 <= 0.02 and n2 <= 2e-4, (n1, n2)
+
+
+# ---------------------------------------------------------------------------------------------
+# RM3-shaped two-body system (synthetic tables), the headline workload's design
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rm3():
+    raw = synth.rm3_like()
+    return hc.Tables.from_raw(raw), orc.Tables(raw)
+
+
+IRR = dict(dt=0.01, duration=20.0, ramp=5.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.0, nfreq=200, gamma=3.3)
+
+
+@pytest.mark.parametrize("snap", [0.0, 1e-9])
+def test_rm3_irregular_ensemble(rm3, snap):
+    """12-DoF coupled radiation + two-body excitation; B = 7 is ragged against the 64-instance lane tile.
+    snap = 0 is the bit-faithful bracket test; snap = 1e-9 is the configuration bench.py measures."""
+    T, O = rm3
+    B = 7
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap)
+    seeds = list(range(1, B + 1))
+    ens.set_waves_irregular(seeds=seeds, **IRR)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular(seed=seeds[b], share_irf_from=insts[0] if insts else None, **IRR)
+        insts.append(i)
+    times = _acc_times(700, 0.01)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
+    np.testing.assert_array_equal(hs, rhs)
+    worst = _assert_parity(rad, rrad, "radiation")
+    _assert_parity(wv, rwv, "irregular excitation")
+    _assert_parity(tot, rtot, "total")
+    assert worst < 1e-9
+
+
+def test_rm3_long_run_window_full(rm3):
+    """History longer than the RIRF window (6000 steps at dt = 0.01): pruning, ring wrap-around, steady state."""
+    T, O = rm3
+    B = 2
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01)
+    insts = [orc.Instance(O) for _ in range(B)]
+    times = _acc_times(6300, 0.01)
+    check = set(range(0, 6300, 450)) | set(range(5990, 6300, 7))
+    D = 12
+    for n, t in enumerate(times):
+        pose, vel = _motion(D, B, t)
+        F = ens.step(t, pose, vel, G981)
+        if n in check:
+            ref = np.array([i.force(t, pose[b], vel[b], G981) for b, i in enumerate(insts)])
+            _assert_parity(F[None], ref[None], "step %d" % n, rel=1e-9)
+        else:
+            for b, i in enumerate(insts):
+                i.force(t, pose[b], vel[b], G981)
+    assert ens.history_len() == insts[0].history_len()
+    assert 6000 <= ens.history_len() <= 6003
+
+
+def test_regular_waves_two_bodies_phase_quirk(rm3):
+    """RegularWave uses body 0's interpolated phases for every body (wave_types.cpp:323) -- preserved."""
+    T, O = rm3
+    ens = hc.Ensemble(T, batch=2, dt_hint=0.01)
+    ens.set_waves_regular([1.0], [2.10])           # demos/rm3/demo_rm3_reg_waves.cpp: A = 1.0, omega = 2.10
+    insts = [orc.Instance(O), orc.Instance(O)]
+    for i in insts:
+        i.set_regular(1.0, 2.10)
+    times = _acc_times(150, 0.01)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
+    _assert_parity(wv, rwv, "regular excitation")
+    _assert_parity(tot, rtot, "total")
+    with pytest.raises(IndexError):
+        ens.set_waves_regular([1.0], [50.0])       # omega beyond the frequency table
+
+
+def test_tapered_direct_mode(rm3):
+    raw = synth.rm3_like()
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    T.set_convolution_mode("TaperedDirect", taper_start_percent=0.5, taper_end_percent=0.9)
+    O.set_tapered(start=0.5, end=0.9)
+    ens = hc.Ensemble(T, batch=2, dt_hint=0.01)
+    insts = [orc.Instance(O), orc.Instance(O)]
+    times = _acc_times(400, 0.01)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
+    _assert_parity(rad, rrad, "tapered radiation")
+
+
+# ---------------------------------------------------------------------------------------------
+# semantics of the reference's TestHydro preserved at the boundary
+# ---------------------------------------------------------------------------------------------
+def test_time_cache_duplicate_and_window_errors(sphere):
+    T, O = sphere
+    ens = hc.Ensemble(T, batch=2, dt_hint=common.SPHERE_DT)
+    pose, vel = _motion(6, 2, 0.0)
+    F0 = ens.step(0.0, pose, vel).copy()
+    assert ens.last_recomputed
+    # same time value again: cached totals, whatever the state passed in (hydro_forces.cpp:742-744)
+    F1 = ens.step(0.0, pose * 3.0, vel * -2.0)
+    assert not ens.last_recomputed
+    np.testing.assert_array_equal(F0, F1)
+    assert ens.history_len() == 1
+    ens.step(0.015, pose, vel)
+    with pytest.raises(hc.HydroError):             # time went backwards: history no longer brackets the query
+        ens.step(0.010, pose, vel)
+    # first evaluation with one history entry: radiation is zero (hydro_forces.cpp:580-584)
+    ens.reset()
+    ens.step(5.0, pose, vel)
+    hs, rad, wv = ens.components()
+    assert np.all(rad == 0.0) and np.all(wv == 0.0)
+    # excitation outside the precomputed eta window throws in the reference (wave_types.cpp:833-840)
+    ens.set_waves_irregular(dt=common.SPHERE_DT, duration=5.0, Hs=1.0, Tp=8.0, nfreq=50)
+    ens.reset()
+    ens.step(0.0, pose, vel)
+    with pytest.raises(hc.EtaWindowError):
+        ens.step(500.0, pose, vel)
+
+
+def test_irregular_dt_and_ring_growth(sphere):
+    """Step size smaller than the hint: the history ring has to grow; irregular step sizes exercise the lerp."""
+    T, O = sphere
+    ens = hc.Ensemble(T, batch=3, dt_hint=0.05)    # ring sized for ~300 entries
+    insts = [orc.Instance(O) for _ in range(3)]
+    rng = np.random.default_rng(5)
+    times = np.cumsum(rng.uniform(0.004, 0.011, size=2500))
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 6)
+    _assert_parity(rad, rrad, "radiation, irregular dt")
+    assert ens.history_len() == insts[0].history_len() > 300
+
+
+def test_gravity_vector_and_body_count_generic_path():
+    """3-body system (D = 18) runs the run-time-D radiation kernel; tilted gravity exercises the buoyancy cross term."""
+    raw = synth.make_tables(num_bodies=3, rirf_steps=301, rirf_duration=15.0, exc_irf_steps=201, exc_half_window=10.0)
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    B = 4
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.05)
+    kw = dict(dt=0.05, duration=10.0, ramp=0.0, Hs=1.5, Tp=7.0, nfreq=64, gamma=2.0)
+    ens.set_waves_irregular(seed=9, **kw)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular(seed=9, share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    times = _acc_times(420, 0.05)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 18, gvec=(0.3, -0.2, -9.7))
+    np.testing.assert_array_equal(hs, rhs)
+    _assert_parity(rad, rrad, "radiation D=18")
+    _assert_parity(wv, rwv, "excitation D=18")
+    _assert_parity(tot, rtot, "total D=18")
+
+
+def test_added_mass_mv(rm3):
+    T, O = rm3
+    B, n_sys = 9, 18                               # one extra non-hydro body in the system
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01)
+    rng = np.random.default_rng(2)
+    w = rng.standard_normal((B, n_sys))
+    R = rng.standard_normal((B, n_sys))
+    out = ens.added_mass_mv(0.37, w, R)
+    ref = np.array([O.added_mass_mv(0.37, w[b], R[b]) for b in range(B)])
+    np.testing.assert_array_equal(out, ref)
+    np.testing.assert_array_equal(out[:, 12:], R[:, 12:])
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size ensemble: size-independent properties (the oracle cannot follow 16384 instances)
+# ---------------------------------------------------------------------------------------------
+def test_large_ensemble_properties(rm3):
+    import torch
+    T, O = rm3
+    B, D = 16384, 12
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.05, bracket_snap=1e-9)
+    kw = dict(dt=0.05, duration=12.0, ramp=2.0, Hs=2.5, Tp=8.0, nfreq=32, gamma=3.3)
+    # instances b and b + B/2 share a seed: identical realisations must give identical forces
+    seeds = np.concatenate([np.arange(1, B // 2 + 1), np.arange(1, B // 2 + 1)]).astype(np.int32)
+    ens.set_waves_irregular(seeds=seeds, **kw)
+    amp, om = synth.prescribed_motion(D)
+    half = B // 2
+    ph = (0.01 * np.arange(half))[:, None]
+    sample = [0, 1, 63, 64, 511, 512, half - 1]
+    insts = []
+    for b in sample:
+        i = orc.Instance(O)
+        i.set_irregular(seed=int(seeds[b]), share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    times = _acc_times(230, 0.05)
+    dev = torch.device("cuda", 0)
+    d_pose = torch.empty((B, D), dtype=torch.float64, device=dev)
+    d_vel = torch.empty_like(d_pose)
+    d_force = torch.empty_like(d_pose)
+    for n, t in enumerate(times):
+        p = amp * np.sin(om * t + ph)
+        v = amp * om * np.cos(om * t + ph)
+        pose = np.concatenate([p, p])
+        vel = np.concatenate([v, v])
+        d_pose.copy_(torch.from_numpy(pose))
+        d_vel.copy_(torch.from_numpy(vel))
+        torch.cuda.synchronize()
+        ens.step_device(t, d_pose, d_vel, d_force)          # device-resident inputs/outputs
+        ens.sync()
+        F = d_force.cpu().numpy()
+        assert np.array_equal(F[:half], F[half:])           # replicas agree bit for bit
+        if n % 23 == 0 or n > 220:
+            ref = np.array([i.force(t, pose[b], vel[b], G981) for b, i in zip(sample, insts)])
+            _assert_parity(F[sample][None], ref[None], "sampled instances, step %d" % n)
+        else:
+            for b, i in zip(sample, insts):
+                i.force(t, pose[b], vel[b], G981)
+    # linearity of the radiation term in the velocity history: F_rad(2v) == 2 F_rad(v) (exact in binary)
+    e1 = hc.Ensemble(T, batch=64, dt_hint=0.05)
+    e2 = hc.Ensemble(T, batch=64, dt_hint=0.05)
+    for t in _acc_times(40, 0.05):
+        pose, vel = _motion(D, 64, t)
+        e1.step(t, pose, vel)
+        e2.step(t, pose, 2.0 * vel)
+    r1, r2 = e1.components()[1], e2.components()[1]
+    np.testing.assert_array_equal(2.0 * r1, r2)
