@@ -145,13 +145,13 @@ __global__ void __launch_bounds__(kThreads) k_radiation(const RadiationArgs a, c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int s0 = blockIdx.y * a.chunk;
     const int ns = min(a.chunk, a.L - s0);
-    double* Ks = reinterpret_cast<double*>(smem_raw);                    // [chunk][D(col)][D(row)]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);               // 16 bytes reserved
+    double* Ks = reinterpret_cast<double*>(smem_raw + 16);               // [chunk][D(col)][D(row)]
     double* s_wn = Ks + (size_t)a.chunk * D * D;
     double* s_wo = s_wn + a.chunk;
     double* s_wd = s_wo + a.chunk;
     int* s_new = reinterpret_cast<int*>(s_wd + a.chunk);
     int* s_old = s_new + a.chunk;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_old + a.chunk + (a.chunk & 1));
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(kThreads) k_excitation(const ExcitationArgs a,
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int j0 = blockIdx.y * a.chunk;
     const int nj = min(a.chunk, g.Le - j0);
-    double* Fs = reinterpret_cast<double*>(smem_raw);                    // [chunk][ND]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);               // 16 bytes reserved
+    double* Fs = reinterpret_cast<double*>(smem_raw + 16);               // [chunk][ND]
     double* s_w1 = Fs + (size_t)a.chunk * ND;
     double* s_w2 = s_w1 + a.chunk;
     int* s_idx = reinterpret_cast<int*>(s_w2 + a.chunk);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_idx + a.chunk + (a.chunk & 1));
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -450,10 +450,10 @@ __global__ void __launch_bounds__(128) k_added_mass_mv(const double* __restrict_
 // launch wrappers (host)
 // ------------------------------------------------------------------------------------------
 size_t radiation_smem_bytes(int D, int chunk) {
-    return (size_t)chunk * D * D * 8 + (size_t)chunk * 3 * 8 + (size_t)(chunk + (chunk & 1)) * 2 * 4 + 16;
+    return 16 + (size_t)chunk * D * D * 8 + (size_t)chunk * 3 * 8 + (size_t)chunk * 2 * 4 + 16;
 }
 size_t excitation_smem_bytes(int nd, int chunk) {
-    return (size_t)chunk * nd * 8 + (size_t)chunk * 2 * 8 + (size_t)(chunk + (chunk & 1)) * 4 + 16;
+    return 16 + (size_t)chunk * nd * 8 + (size_t)chunk * 2 * 8 + (size_t)chunk * 4 + 16;
 }
 
 template <int D>

@@ -30,10 +30,11 @@ def _assert_parity(got, ref, what, rel=1e-9):
     got, ref = np.asarray(got), np.asarray(ref)
     tol = common.force_tol(ref, rel=rel)
     err = np.abs(got - ref)
-    worst = np.unravel_index(np.argmax(err / tol), err.shape)
+    ratio = np.where(tol > 0, err / np.where(tol > 0, tol, 1.0), np.where(err > 0, np.inf, 0.0))
+    worst = np.unravel_index(np.argmax(ratio), err.shape)
     assert np.all(err <= tol), "%s: worst at %s: got %r ref %r (err/tol %.3g)" % (
-        what, worst, got[worst], ref[worst], (err / tol)[worst])
-    return float((err / np.maximum(np.abs(ref), 1e-300)).max())
+        what, worst, got[worst], ref[worst], ratio[worst])
+    return float(ratio.max()) * rel       # worst error in units of max(|F_ref|, floor)
 
 
 def _run_pair(ens, insts, times, D, gvec=G981, seed=3):
@@ -195,7 +196,8 @@ def test_rm3_irregular_ensemble(rm3, snap):
     worst = _assert_parity(rad, rrad, "radiation")
     _assert_parity(wv, rwv, "irregular excitation")
     _assert_parity(tot, rtot, "total")
-    assert worst < 1e-9
+    # bit-faithful bracketing differs from the oracle only by summation order / FMA contraction
+    assert worst < (1e-12 if snap == 0.0 else 1e-9), worst
 
 
 def test_rm3_long_run_window_full(rm3):
