@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a) {
 struct RadPlanPtrs { const int* nw; const int* od; const double* wn; const double* wo; const double* wd; };
 
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_radiation(const RadiationArgs a, const RadPlanPtrs p) {
+__global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const RadiationArgs a, const RadPlanPtrs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int s0 = blockIdx.y * a.chunk;
     const int ns = min(a.chunk, a.L - s0);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationA
 struct ExcPlanPtrs { const int* idx; const double* w1; const double* w2; };
 
 template <int ND>
-__global__ void __launch_bounds__(kThreads) k_excitation(const ExcitationArgs a, const ExcGroup g, const ExcPlanPtrs p) {
+__global__ void __launch_bounds__(kThreads, 2) k_excitation(const ExcitationArgs a, const ExcGroup g, const ExcPlanPtrs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int j0 = blockIdx.y * a.chunk;
     const int nj = min(a.chunk, g.Le - j0);
@@ -296,17 +296,52 @@ __global__ void __launch_bounds__(kThreads) k_excitation(const ExcitationArgs a,
 
     int prev_idx = -2;
     double2 prev_e = make_double2(0.0, 0.0);
-    for (int j = 0; j < nj; ++j) {
+    const double* eta_b = a.eta + b0;
+    // One lag = one eta row (16 B per thread).  kExcUnroll independent row loads are issued before the first
+    // dependent FMA so that every warp keeps several 512-byte requests in flight (the kernel is latency-bound
+    // otherwise: one request per warp at a time).
+    constexpr int U = 8;
+    int j = 0;
+    for (; j + U <= nj; j += U) {
+        int idx[U];
+        double2 e1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            idx[u] = s_idx[j + u];
+            e1[u] = __ldg(reinterpret_cast<const double2*>(eta_b + (size_t)idx[u] * a.Bp));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double w1 = s_w1[j + u], w2 = s_w2[j + u];
+            double2 ev = e1[u];
+            if (w2 != 0.0) {
+                // eta row idx+1 is the row the previous lag interpolated from in the common case
+                const double2 e2 = (idx[u] + 1 == prev_idx)
+                                       ? prev_e
+                                       : __ldg(reinterpret_cast<const double2*>(eta_b + (size_t)(idx[u] + 1) * a.Bp));
+                ev.x = __dadd_rn(__dmul_rn(w1, e1[u].x), __dmul_rn(w2, e2.x));   // w1*eta1 + w2*eta2 (:821-824)
+                ev.y = __dadd_rn(__dmul_rn(w1, e1[u].y), __dmul_rn(w2, e2.y));
+            }
+            prev_idx = idx[u]; prev_e = e1[u];
+            const double* ff = Fs + (size_t)(j + u) * ND;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double f = ff[d];
+                acc0[d] = fma(f, ev.x, acc0[d]);
+                acc1[d] = fma(f, ev.y, acc1[d]);
+            }
+        }
+    }
+    for (; j < nj; ++j) {
         const int idx = s_idx[j];
         const double w1 = s_w1[j], w2 = s_w2[j];
-        const double2 e1 = __ldg(reinterpret_cast<const double2*>(a.eta + (size_t)idx * a.Bp + b0));
+        const double2 e1 = __ldg(reinterpret_cast<const double2*>(eta_b + (size_t)idx * a.Bp));
         double2 ev = e1;
         if (w2 != 0.0) {
-            // eta row idx+1 is the row the previous lag interpolated from in the common case
             const double2 e2 = (idx + 1 == prev_idx)
                                    ? prev_e
-                                   : __ldg(reinterpret_cast<const double2*>(a.eta + (size_t)(idx + 1) * a.Bp + b0));
-            ev.x = __dadd_rn(__dmul_rn(w1, e1.x), __dmul_rn(w2, e2.x));      // w1*eta1 + w2*eta2 (:821-824)
+                                   : __ldg(reinterpret_cast<const double2*>(eta_b + (size_t)(idx + 1) * a.Bp));
+            ev.x = __dadd_rn(__dmul_rn(w1, e1.x), __dmul_rn(w2, e2.x));
             ev.y = __dadd_rn(__dmul_rn(w1, e1.y), __dmul_rn(w2, e2.y));
         }
         prev_idx = idx; prev_e = e1;
@@ -327,67 +362,83 @@ __global__ void __launch_bounds__(kThreads) k_excitation(const ExcitationArgs a,
 // k_finalize: one thread per instance.
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_finalize(const FinalizeArgs a, const HydrostaticTables hs,
+__global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const HydrostaticTables hs,
                                                   const FinalizeGroups eg) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    // one thread per (dof, instance); instances fastest so the partial reads are coalesced
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = tid / a.Bp;
+    const int b = tid - d * a.Bp;
+    if (d >= a.D || b >= a.B) return;
     const StepHeader h = *a.hdr;
     const int D = a.D;
+    const int body = d / 6, i = d - 6 * body;
     const double gx = h.g[0], gy = h.g[1], gz = h.g[2];
+    // ---- hydrostatics (hydro_forces.cpp:263-322), arithmetic order kept, no FMA contraction ----
     // ChVector3::Length(): sqrt(x*x + y*y + z*z)
     const double glen = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
     const double rho_g = __dmul_rn(hs.rho, glen);
-    const double* pose = a.pose + (size_t)b * D;
-    double* out = a.force + (size_t)b * D;
-    const size_t BD = (size_t)a.B * D;
-    for (int body = 0; body < a.N; ++body) {
-        // ---- hydrostatics (hydro_forces.cpp:263-322), arithmetic order kept, no FMA contraction ----
-        double disp[6], fh[6];
+    const double* pose = a.pose + (size_t)b * D + 6 * body;
+    double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) disp[i] = __dsub_rn(pose[6 * body + i], hs.equilibrium[body][i]);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) s = __dadd_rn(s, __dmul_rn(hs.Kh[body][i * 6 + j], disp[j]));
-            fh[i] = __dmul_rn(-rho_g, s);
+    for (int j = 0; j < 6; ++j)
+        s = __dadd_rn(s, __dmul_rn(hs.Kh[body][i * 6 + j], __dsub_rn(pose[j], hs.equilibrium[body][j])));
+    double fh = __dmul_rn(-rho_g, s);
+    const double V = hs.disp_vol[body];
+    const double bx = __dmul_rn(__dmul_rn(hs.rho, -gx), V);
+    const double by = __dmul_rn(__dmul_rn(hs.rho, -gy), V);
+    const double bz = __dmul_rn(__dmul_rn(hs.rho, -gz), V);
+    const double rx = hs.cb_minus_cg[body][0], ry = hs.cb_minus_cg[body][1], rz = hs.cb_minus_cg[body][2];
+    double add;
+    switch (i) {
+        case 0: add = bx; break;
+        case 1: add = by; break;
+        case 2: add = bz; break;
+        case 3: add = __dsub_rn(__dmul_rn(ry, bz), __dmul_rn(rz, by)); break;
+        case 4: add = __dsub_rn(__dmul_rn(rz, bx), __dmul_rn(rx, bz)); break;
+        default: add = __dsub_rn(__dmul_rn(rx, by), __dmul_rn(ry, bx)); break;
+    }
+    fh = __dadd_rn(fh, add);
+    // ---- radiation: fixed-order sum of lag-chunk partials ----
+    double fr = 0.0;
+    {
+        const double* p = a.rad_partial + (size_t)d * a.Bp + b;
+        const size_t stride = (size_t)D * a.Bp;
+        int ch = 0;
+        for (; ch + 4 <= a.rad_nchunk; ch += 4) {
+            const double p0 = p[(size_t)ch * stride], p1 = p[(size_t)(ch + 1) * stride];
+            const double p2 = p[(size_t)(ch + 2) * stride], p3 = p[(size_t)(ch + 3) * stride];
+            fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
         }
-        const double V = hs.disp_vol[body];
-        const double bx = __dmul_rn(__dmul_rn(hs.rho, -gx), V);
-        const double by = __dmul_rn(__dmul_rn(hs.rho, -gy), V);
-        const double bz = __dmul_rn(__dmul_rn(hs.rho, -gz), V);
-        fh[0] = __dadd_rn(fh[0], bx); fh[1] = __dadd_rn(fh[1], by); fh[2] = __dadd_rn(fh[2], bz);
-        const double rx = hs.cb_minus_cg[body][0], ry = hs.cb_minus_cg[body][1], rz = hs.cb_minus_cg[body][2];
-        fh[3] = __dadd_rn(fh[3], __dsub_rn(__dmul_rn(ry, bz), __dmul_rn(rz, by)));
-        fh[4] = __dadd_rn(fh[4], __dsub_rn(__dmul_rn(rz, bx), __dmul_rn(rx, bz)));
-        fh[5] = __dadd_rn(fh[5], __dsub_rn(__dmul_rn(rx, by), __dmul_rn(ry, bx)));
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int d = 6 * body + i;
-            // ---- radiation: fixed-order sum of lag-chunk partials ----
-            double fr = 0.0;
-            for (int ch = 0; ch < a.rad_nchunk; ++ch) fr += a.rad_partial[((size_t)ch * D + d) * a.Bp + b];
-            // ---- waves ----
-            double fw = 0.0;
-            if (a.wave_mode == 1) {
-                // mag * A * cos(omega t + phase[rowEx])  (wave_types.cpp:322-323; phase of body 0, reference quirk)
-                const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
-                fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
-            } else if (a.wave_mode == 2) {
-                for (int g = 0; g < a.exc_ngroups; ++g) {
-                    if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
-                    const int dl = d - eg.dof0[g];
-                    for (int ch = 0; ch < eg.nchunk[g]; ++ch)
-                        fw += a.exc_partial[((size_t)(eg.chunk0[g] + ch) * a.exc_ndmax + dl) * a.Bp + b];
-                }
+        for (; ch < a.rad_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
+    }
+    // ---- waves ----
+    double fw = 0.0;
+    if (a.wave_mode == 1) {
+        // mag * A * cos(omega t + phase[rowEx])  (wave_types.cpp:322-323; phase of body 0, reference quirk)
+        const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
+        fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
+    } else if (a.wave_mode == 2) {
+        for (int g = 0; g < a.exc_ngroups; ++g) {
+            if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
+            const int dl = d - eg.dof0[g];
+            const double* p = a.exc_partial + ((size_t)eg.chunk0[g] * a.exc_ndmax + dl) * a.Bp + b;
+            const size_t stride = (size_t)a.exc_ndmax * a.Bp;
+            int ch = 0;
+            for (; ch + 4 <= eg.nchunk[g]; ch += 4) {
+                const double p0 = p[(size_t)ch * stride], p1 = p[(size_t)(ch + 1) * stride];
+                const double p2 = p[(size_t)(ch + 2) * stride], p3 = p[(size_t)(ch + 3) * stride];
+                fw = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fw, p0), p1), p2), p3);
             }
-            out[d] = __dadd_rn(__dsub_rn(fh[i], fr), fw);            // hs - rad + waves (:758-760)
-            if (a.comp) {
-                a.comp[(size_t)b * D + d] = fh[i];
-                a.comp[BD + (size_t)b * D + d] = fr;
-                a.comp[2 * BD + (size_t)b * D + d] = fw;
-            }
+            for (; ch < eg.nchunk[g]; ++ch) fw = __dadd_rn(fw, p[(size_t)ch * stride]);
         }
+    }
+    const size_t o = (size_t)b * D + d;
+    a.force[o] = __dadd_rn(__dsub_rn(fh, fr), fw);                   // hs - rad + waves (:758-760)
+    if (a.comp) {
+        const size_t BD = (size_t)a.B * D;
+        a.comp[o] = fh;
+        a.comp[BD + o] = fr;
+        a.comp[2 * BD + o] = fw;
     }
 }
 
@@ -522,7 +573,7 @@ cudaError_t launch_prestep(const PrestepArgs& a, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    k_finalize<<<(a.B + 127) / 128, 128, 0, st>>>(a, hs, eg);
+    k_finalize<<<(a.D * a.Bp + 255) / 256, 256, 0, st>>>(a, hs, eg);
     return cudaGetLastError();
 }
 
