@@ -59,7 +59,7 @@ struct PinBuf {
     }
 };
 
-enum { EV_BEGIN = 0, EV_PRE, EV_RAD, EV_EXC, EV_END, EV_COUNT };
+enum { EV_BEGIN = 0, EV_PLAN, EV_EXC, EV_APPEND, EV_RAD, EV_END, EV_COUNT };
 
 }  // namespace hc
 
@@ -68,7 +68,7 @@ using namespace hc;
 struct hc_ensemble {
     const hc_tables* T = nullptr;
     hc_ensemble_opts opts{};
-    int dev = 0, B = 0, Bp = 0, D = 0, N = 0, L = 0;
+    int dev = 0, B = 0, Bp = 0, D = 0, N = 0, L = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
 
@@ -112,9 +112,11 @@ struct hc_ensemble {
     int n_eta = 0, nf = 0;
 
     // graph + profiling
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    bool graph_valid = false;
+    cudaGraph_t graph = nullptr, graph1 = nullptr;          // phase 2 / phase 1
+    cudaGraphExec_t graph_exec = nullptr, graph1_exec = nullptr;
+    bool graph_valid = false, graph1_valid = false;
+    cudaStream_t copy_stream = nullptr;                     // H2D of pose/vel overlaps phase 1
+    cudaEvent_t ev_inputs = nullptr;
     const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
     cudaEvent_t ev[EV_COUNT] = {};
@@ -128,19 +130,26 @@ struct hc_ensemble {
         drop_graph();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_inputs) cudaEventDestroy(ev_inputs);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        if (graph1_exec) cudaGraphExecDestroy(graph1_exec);
+        if (graph1) cudaGraphDestroy(graph1);
         graph_exec = nullptr; graph = nullptr; graph_valid = false;
+        graph1_exec = nullptr; graph1 = nullptr; graph1_valid = false;
     }
     void use_device() const { CUDA_CHECK(cudaSetDevice(dev)); }
 
     void alloc_ring(int new_cap);
     void grow_ring();
     void setup_radiation_chunks();
-    void enqueue_kernels(const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
-    void run_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
+    void enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
+    void launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
+    void begin_step(double t, const double* g);
+    void finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void collect_events();
 };
 
@@ -177,26 +186,42 @@ void hc_ensemble::grow_ring() {
     drop_graph();
 }
 
+// Lag-chunk size such that the grid (instance tiles x chunks) fills an integer number of waves of resident CTAs:
+// the smallest wave count whose chunk fits the shared-memory budget for `occ_target` CTAs per SM.
+static int pick_chunk(int n_lags, int tiles, int sm_count, int occ_target, size_t smem_budget,
+                      size_t (*smem_of)(int, int), int width, int min_chunk) {
+    const int slots = sm_count * occ_target;
+    for (int waves = 1; waves <= 64; ++waves) {
+        const int n = (waves * slots) / tiles;
+        if (n < 1) continue;
+        int chunk = (n_lags + n - 1) / n;
+        if (chunk < min_chunk) return std::min(min_chunk, n_lags);
+        if (smem_of(width, chunk) <= smem_budget) return chunk;
+    }
+    return std::min(std::max(min_chunk, 8), n_lags);
+}
+
 void hc_ensemble::setup_radiation_chunks() {
     const int tiles = (Bp + kTileInst - 1) / kTileInst;
     int chunk = opts.rad_chunk;
     if (chunk <= 0) {
-        // aim for >= ~4 CTAs per SM over 148 SMs, chunk between 8 and 64 lags
-        const int want_ctas = 148 * 4;
-        const int nch = std::max(1, (want_ctas + tiles - 1) / tiles);
-        chunk = (L + nch - 1) / nch;
-        chunk = std::max(8, std::min(chunk, 64));
+        const bool templated = (D == 6 || D == 12);
+        const int occ = templated ? 2 : 4;
+        auto smem_of = templated ? radiation_smem_bytes : +[](int, int) -> size_t { return 0; };
+        chunk = pick_chunk(L, tiles * (templated ? 1 : D / 6), sm_count, occ, size_t(110) * 1024, smem_of, D, 4);
     }
-    chunk = std::min(chunk, L);
-    // shared-memory ceiling (K tile is chunk * D * D doubles)
-    while (chunk > 1 && (D == 6 || D == 12) && radiation_smem_bytes(D, chunk) > 160 * 1024) chunk /= 2;
+    chunk = std::max(1, std::min(chunk, L));
+    while (chunk > 1 && (D == 6 || D == 12) && radiation_smem_bytes(D, chunk) > 200 * 1024) chunk /= 2;
     rad_chunk = chunk;
     rad_nchunk = (L + chunk - 1) / chunk;
     d_rad_partial.alloc(size_t(rad_nchunk) * D * Bp);
 }
 
-void hc_ensemble::enqueue_kernels(const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events) {
-    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
+// The per-step kernel sequence in two phases.  Phase 1 needs only the step header (time): interpolation plans +
+// excitation convolution.  Phase 2 needs the step's state: history append, radiation convolution, finalize.
+// hc_step overlaps the pose/velocity H2D copy with phase 1.
+void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out,
+                                bool with_events) {
     PrestepArgs pa{};
     pa.hdr = d_hdr.p; pa.vel = d_vel_in; pa.hist = d_hist.p; pa.times = d_times.p;
     pa.rirf_t = d_rirf_t.p; pa.rirf_w = d_rirf_w.p;
@@ -211,8 +236,25 @@ void hc_ensemble::enqueue_kernels(const double* d_pose_in, const double* d_vel_i
         }
         pa.eta_t = d_eta_t.p; pa.n_eta = n_eta; pa.eta_dt = ip.simulation_dt;
     }
-    CUDA_CHECK(launch_prestep(pa, stream));
-    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PRE], stream));
+    if (phase == 1) {
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
+        CUDA_CHECK(launch_prestep(pa, 2, stream));
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
+        if (wave_mode == 2) {
+            ExcitationArgs ea{};
+            ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
+            ea.eta_dt = ip.simulation_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
+            for (size_t g = 0; g < groups.size(); ++g) {
+                Group& G = *groups[g];
+                ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
+                CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, stream));
+            }
+        }
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
+        return;
+    }
+    CUDA_CHECK(launch_prestep(pa, 1, stream));
+    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
 
     RadiationArgs ra{};
     ra.hdr = d_hdr.p; ra.K = d_K.p; ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
@@ -222,19 +264,11 @@ void hc_ensemble::enqueue_kernels(const double* d_pose_in, const double* d_vel_i
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
 
     FinalizeGroups fg{};
-    if (wave_mode == 2) {
-        ExcitationArgs ea{};
-        ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
-        ea.eta_dt = ip.simulation_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
+    if (wave_mode == 2)
         for (size_t g = 0; g < groups.size(); ++g) {
             Group& G = *groups[g];
-            ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
-            CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, stream));
             fg.dof0[g] = G.dof0; fg.nd[g] = G.nd; fg.chunk0[g] = G.chunk0; fg.nchunk[g] = G.nchunk;
         }
-    }
-    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
-
     FinalizeArgs fa{};
     fa.hdr = d_hdr.p; fa.pose = d_pose_in; fa.rad_partial = d_rad_partial.p; fa.exc_partial = d_exc_partial.p;
     fa.force = d_force_out; fa.comp = d_comp.p;
@@ -247,22 +281,55 @@ void hc_ensemble::enqueue_kernels(const double* d_pose_in, const double* d_vel_i
 
 void hc_ensemble::collect_events() {
     // called after a stream synchronisation
-    float ms[4] = {0, 0, 0, 0};
-    cudaEventElapsedTime(&ms[0], ev[EV_BEGIN], ev[EV_PRE]);
-    cudaEventElapsedTime(&ms[1], ev[EV_PRE], ev[EV_RAD]);
-    cudaEventElapsedTime(&ms[2], ev[EV_RAD], ev[EV_EXC]);
-    cudaEventElapsedTime(&ms[3], ev[EV_EXC], ev[EV_END]);
-    for (int i = 0; i < 4; ++i) acc_ms[i] += ms[i];
+    float plan = 0, exc = 0, app = 0, rad = 0, fin = 0;
+    cudaEventElapsedTime(&plan, ev[EV_BEGIN], ev[EV_PLAN]);
+    cudaEventElapsedTime(&exc, ev[EV_PLAN], ev[EV_EXC]);
+    cudaEventElapsedTime(&app, ev[EV_EXC], ev[EV_APPEND]);
+    cudaEventElapsedTime(&rad, ev[EV_APPEND], ev[EV_RAD]);
+    cudaEventElapsedTime(&fin, ev[EV_RAD], ev[EV_END]);
+    acc_ms[0] += plan + app; acc_ms[1] += rad; acc_ms[2] += exc; acc_ms[3] += fin;
     ms_steps++;
     events_pending = false;
-    prof.radiation_seconds += 1e-3 * (ms[0] + ms[1]);
-    prof.waves_seconds += 1e-3 * ms[2];
-    prof.hydrostatics_seconds += 1e-3 * ms[3];
-    prof.step_seconds += 1e-3 * (ms[0] + ms[1] + ms[2] + ms[3]);
+    prof.radiation_seconds += 1e-3 * (plan + app + rad);
+    prof.waves_seconds += 1e-3 * exc;
+    prof.hydrostatics_seconds += 1e-3 * fin;
+    prof.step_seconds += 1e-3 * (plan + app + rad + exc + fin);
 }
 
-// One recompute (hydro_forces.cpp:746-760) for all instances.
-void hc_ensemble::run_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
+void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
+    const bool want_graph = opts.use_graph && !profiling;
+    if (!want_graph) {
+        enqueue_phase(phase, d_pose_in, d_vel_in, d_force_out, profiling);
+        if (phase == 2) events_pending = profiling;
+        return;
+    }
+    cudaGraph_t& g = phase == 1 ? graph1 : graph;
+    cudaGraphExec_t& ge = phase == 1 ? graph1_exec : graph_exec;
+    bool valid = phase == 1 ? graph1_valid
+                            : (graph_valid && graph_pose == d_pose_in && graph_vel == d_vel_in && graph_force == d_force_out);
+    if (!valid) {
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
+        ge = nullptr; g = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_phase(phase, d_pose_in, d_vel_in, d_force_out, false);
+        } catch (...) {
+            cudaGraph_t tmp = nullptr;
+            cudaStreamEndCapture(stream, &tmp);
+            if (tmp) cudaGraphDestroy(tmp);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+        CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+        if (phase == 1) graph1_valid = true;
+        else { graph_valid = true; graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out; }
+    }
+    CUDA_CHECK(cudaGraphLaunch(ge, stream));
+}
+
+// Host-side bookkeeping of one recompute (hydro_forces.cpp:746-760) + phase 1 launch.
+void hc_ensemble::begin_step(double t, const double* g) {
     // --- ComputeForceRadiationDampingConv's host-side bookkeeping ---
     if (!times.empty() && t == times.front())
         fail(HC_ERR_DUPLICATE_TIME, "Tried to compute the radiation damping convolution twice within the same time step!");
@@ -295,31 +362,12 @@ void hc_ensemble::run_step(double t, const double* g, const double* d_pose_in, c
     hh.t = t; hh.g[0] = g[0]; hh.g[1] = g[1]; hh.g[2] = g[2];
     hh.snap = opts.bracket_snap; hh.head = head; hh.len = int(times.size()); hh.cap = cap; hh.flags = 0;
     CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
+    launch_phase(1, nullptr, nullptr, nullptr);
+}
 
-    const bool want_graph = opts.use_graph && !profiling;
-    if (want_graph) {
-        if (!graph_valid || graph_pose != d_pose_in || graph_vel != d_vel_in || graph_force != d_force_out) {
-            drop_graph();
-            CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            try {
-                enqueue_kernels(d_pose_in, d_vel_in, d_force_out, false);
-            } catch (...) {
-                cudaGraph_t tmp = nullptr;
-                cudaStreamEndCapture(stream, &tmp);
-                if (tmp) cudaGraphDestroy(tmp);
-                throw;
-            }
-            CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
-            CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
-            graph_valid = true;
-            graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out;
-        }
-        CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
-    } else {
-        enqueue_kernels(d_pose_in, d_vel_in, d_force_out, profiling);
-        events_pending = profiling;
-    }
-    prof.kernel_launches += 3 + (wave_mode == 2 ? (long long)groups.size() : 0);
+void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
+    launch_phase(2, d_pose_in, d_vel_in, d_force_out);
+    prof.kernel_launches += 4 + (wave_mode == 2 ? (long long)groups.size() : 0);
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
     force_valid = true;
@@ -364,11 +412,14 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     e->T = t; e->opts = *opts; e->dev = opts->device;
     e->use_device();
     e->B = opts->batch; e->N = t->N; e->D = t->D; e->L = t->L;
+    CUDA_CHECK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->dev));
     const int lane_tile = 32 * kIPT;
     e->Bp = ((e->B + lane_tile - 1) / lane_tile) * lane_tile;
     if (opts->stream) { e->stream = static_cast<cudaStream_t>(opts->stream); }
     else { CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
     for (auto& ev : e->ev) CUDA_CHECK(cudaEventCreate(&ev));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_inputs, cudaEventDisableTiming));
 
     const int D = e->D, L = e->L;
     // K staged as [lag][col][row]: one lag's D x D block is contiguous, rows fastest
@@ -526,12 +577,9 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
     {
         const int tiles = (Bp + kTileInst - 1) / kTileInst;
         int chunk = e->opts.exc_chunk;
-        if (chunk <= 0) {
-            const int want = 148 * 4;
-            const int nch = std::max(1, (want + tiles * ngroups - 1) / (tiles * ngroups));
-            chunk = (max_Le + nch - 1) / nch;
-            chunk = std::max(32, std::min(chunk, 512));
-        }
+        if (chunk <= 0)
+            chunk = pick_chunk(max_Le, tiles * ngroups, e->sm_count, 2, size_t(110) * 1024, excitation_smem_bytes,
+                               e->exc_ndmax, 16);
         e->exc_chunk = std::min(chunk, std::max(1, max_Le));
     }
     int chunk0 = 0;
@@ -716,7 +764,8 @@ hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, const d
         if (recomputed) *recomputed = 0;
         return HC_OK;
     }
-    e->run_step(t, g, d_pose, d_vel, e->d_force.p);
+    e->begin_step(t, g);
+    e->finish_step(t, d_pose, d_vel, e->d_force.p);
     if (d_force != e->d_force.p)
         CUDA_CHECK(cudaMemcpyAsync(d_force, e->d_force.p, bytes, cudaMemcpyDeviceToDevice, e->stream));
     if (recomputed) *recomputed = 1;
@@ -732,9 +781,18 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
     const size_t bytes = size_t(e->B) * e->D * sizeof(double);
     int re = 0;
     if (t != e->prev_time) {
-        CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, e->stream));
-        CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, e->stream));
-        e->run_step(t, g, e->d_pose.p, e->d_vel.p, e->d_force.p);
+        // state upload on the copy stream, overlapped with the state-independent phase 1 on the main stream
+        CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CUDA_CHECK(cudaEventRecord(e->ev_inputs, e->copy_stream));
+        try {
+            e->begin_step(t, g);
+        } catch (...) {
+            cudaStreamSynchronize(e->copy_stream);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_inputs, 0));
+        e->finish_step(t, e->d_pose.p, e->d_vel.p, e->d_force.p);
         re = 1;
     }
     CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));

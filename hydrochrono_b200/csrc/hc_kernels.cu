@@ -54,13 +54,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // k_prestep
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a) {
+// mode bit 0: history append (needs the step's velocities); bit 1: interpolation plans (need the header only).
+__global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int mode) {
     const StepHeader h = *a.hdr;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
 
     // (1) history append: hist[head][c][b] = vel[b][c]   (hydro_forces.cpp:560-574)
-    {
+    if (mode & 1) {
         double* row = a.hist + (size_t)h.head * a.D * a.Bp;
         const int n = a.D * a.Bp;
         for (int i = tid; i < n; i += nth) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a) {
         if (s < 0) s += h.cap;
         return a.times[s];
     };
+    if (!(mode & 2)) return;
     for (int s = tid; s < a.L; s += nth) {
         int slot_new = 0, slot_old = 0;
         double wn = 0.0, wo = 0.0, wd = 0.0;
@@ -563,11 +565,47 @@ cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const 
     }
 }
 
-cudaError_t launch_prestep(const PrestepArgs& a, cudaStream_t st) {
-    const int work = max(a.D * a.Bp, a.L);
+int radiation_ctas_per_sm(int D, int chunk) {
+    int n = 0;
+    const size_t smem = radiation_smem_bytes(D, chunk);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (D == 6) {
+        cudaFuncSetAttribute(k_radiation<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radiation<6>, kThreads, smem);
+    } else if (D == 12) {
+        cudaFuncSetAttribute(k_radiation<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radiation<12>, kThreads, smem);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_radiation_generic, kThreads, 0);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+    return n > 0 ? n : 1;
+}
+int excitation_ctas_per_sm(int nd, int chunk) {
+    int n = 0;
+    const size_t smem = excitation_smem_bytes(nd, chunk);
+    cudaError_t e;
+    if (nd == 6) {
+        cudaFuncSetAttribute(k_excitation<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_excitation<6>, kThreads, smem);
+    } else {
+        cudaFuncSetAttribute(k_excitation<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_excitation<12>, kThreads, smem);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+    return n > 0 ? n : 1;
+}
+
+cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
+    int work = 1;
+    if (mode & 1) work = max(work, a.D * a.Bp);
+    if (mode & 2) {
+        work = max(work, a.L);
+        for (int g = 0; g < a.ngroups; ++g) work = max(work, a.Le[g]);
+    }
     int blocks = (work + 255) / 256;
     blocks = max(1, min(blocks, 148 * 8));
-    k_prestep<<<blocks, 256, 0, st>>>(a);
+    k_prestep<<<blocks, 256, 0, st>>>(a, mode);
     return cudaGetLastError();
 }
 

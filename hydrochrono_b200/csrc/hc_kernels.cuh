@@ -118,7 +118,9 @@ struct FinalizeGroups {
 
 size_t radiation_smem_bytes(int D, int chunk);
 size_t excitation_smem_bytes(int nd, int chunk);
-cudaError_t launch_prestep(const PrestepArgs& a, cudaStream_t st);
+cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st);
+int radiation_ctas_per_sm(int D, int chunk);
+int excitation_ctas_per_sm(int nd, int chunk);
 cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const int* pr_old, const double* pr_wn,
                              const double* pr_wo, const double* pr_wd, cudaStream_t st);
 cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const int* idx, const double* w1,

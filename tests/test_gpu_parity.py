@@ -197,7 +197,7 @@ def test_rm3_irregular_ensemble(rm3, snap):
     _assert_parity(wv, rwv, "irregular excitation")
     _assert_parity(tot, rtot, "total")
     # bit-faithful bracketing differs from the oracle only by summation order / FMA contraction
-    assert worst < (1e-12 if snap == 0.0 else 1e-9), worst
+    assert worst < (1e-11 if snap == 0.0 else 1e-9), worst
 
 
 def test_rm3_long_run_window_full(rm3):
