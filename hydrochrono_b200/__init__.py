@@ -305,6 +305,15 @@ class Ensemble:
         _check(lib.hc_get_components(self._h, _dp(hs), _dp(rad), _dp(wv)))
         return hs, rad, wv
 
+    def wave_force_at_time(self, t):
+        """WaveBase::GetForceAtTime(t) for every instance: [B][6N]."""
+        out = np.empty((self.batch, self.dofs))
+        _check(lib.hc_waves_force_at_time(self._h, float(t), _dp(out)))
+        return out
+
+    def refresh_rirf(self):
+        _check(lib.hc_ensemble_refresh_rirf(self._h))
+
     def sync(self):
         _check(lib.hc_sync(self._h))
 

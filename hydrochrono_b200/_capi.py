@@ -81,6 +81,10 @@ SIGNATURES = {
     "hc_tables_disp_vol": (C.c_int, [vp, C.c_int, dp]),
     "hc_tables_cg": (C.c_int, [vp, C.c_int, dp]),
     "hc_tables_cb": (C.c_int, [vp, C.c_int, dp]),
+    "hc_tables_freq_list": (C.c_int, [vp, dp]),
+    "hc_tables_excitation_mag": (C.c_int, [vp, C.c_int, dp]),
+    "hc_tables_excitation_phase": (C.c_int, [vp, C.c_int, dp]),
+    "hc_tables_excitation_irf": (C.c_int, [vp, C.c_int, dp, dp]),
     "hc_tables_set_convolution_mode": (C.c_int, [vp, C.c_int, C.POINTER(TaperedOpts)]),
     "hc_added_mass": (C.c_int, [vp, C.c_int, dp]),
     "hc_ensemble_default_opts": (None, [C.POINTER(EnsembleOpts)]),
@@ -102,6 +106,8 @@ SIGNATURES = {
     "hc_step": (C.c_int, [vp, C.c_double, vp, vp, dp, vp, ip]),
     "hc_step_device": (C.c_int, [vp, C.c_double, vp, vp, dp, vp, ip]),
     "hc_get_components": (C.c_int, [vp, dp, dp, dp]),
+    "hc_waves_force_at_time": (C.c_int, [vp, C.c_double, dp]),
+    "hc_ensemble_refresh_rirf": (C.c_int, [vp]),
     "hc_sync": (C.c_int, [vp]),
     "hc_ensemble_history_len": (C.c_int, [vp]),
     "hc_added_mass_mv": (C.c_int, [vp, C.c_int, C.c_double, vp, vp]),
@@ -116,6 +122,17 @@ SIGNATURES = {
     "hc_compute_wave_number": (C.c_int, [C.c_double, C.c_double, C.c_double, dp]),
     "hc_resample_excitation_irf": (C.c_int, [vp, C.c_double, C.c_int, ip, dp, dp, dp]),
     "hc_random_phases": (C.c_int, [C.c_int, C.c_int, dp]),
+    "hc_h5_writer_create": (C.c_int, [C.POINTER(vp)]),
+    "hc_h5_writer_destroy": (None, [vp]),
+    "hc_h5_writer_put_group": (C.c_int, [vp, C.c_char_p]),
+    "hc_h5_writer_put_f64": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), dp]),
+    "hc_h5_writer_put_string": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
+    "hc_h5_writer_attr_string": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "hc_h5_writer_attr_f64": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_double]),
+    "hc_h5_writer_save": (C.c_int, [vp, C.c_char_p]),
+    "hc_h5_read_f64": (C.c_int, [C.c_char_p, C.c_char_p, ip, C.POINTER(C.c_uint64), dp, C.c_size_t]),
+    "hc_h5_read_string": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "hc_h5_list": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

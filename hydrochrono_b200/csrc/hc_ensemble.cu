@@ -90,7 +90,7 @@ struct hc_ensemble {
 
     // step I/O
     DevBuf<StepHeader> d_hdr;
-    DevBuf<double> d_pose, d_vel, d_force, d_comp;
+    DevBuf<double> d_pose, d_vel, d_force, d_comp, d_wave_tmp;
     PinBuf h_pose, h_vel, h_force;
 
     // waves
@@ -799,6 +799,66 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     if (e->events_pending) e->collect_events();
     if (recomputed) *recomputed = re;
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// WaveBase::GetForceAtTime(t) for every instance (src/wave_types.cpp:257-264,315-327,552-570): state-independent,
+// does not touch the velocity history or the force cache.
+hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
+    HC_GUARD_BEGIN
+    if (!out) fail(HC_ERR_INVALID, "null argument");
+    e->use_device();
+    const size_t n = size_t(e->B) * e->D;
+    if (e->wave_mode == 0) { std::fill(out, out + n, 0.0); return HC_OK; }
+    if (e->wave_mode == 2) {
+        const double tmin = e->eta_t_h.front(), tmax = e->eta_t_h.back();
+        for (auto& G : e->groups) {
+            const double hi = t - G->tau_first, lo = t - G->tau_last;
+            if (!(tmin <= lo && hi <= tmax))
+                fail(HC_ERR_ETA_WINDOW,
+                     "Excitation convolution: trying to find free surface elevation at a time out of bounds from the "
+                     "precomputed free surface elevation (" + std::to_string(hi > tmax ? hi : lo) + "not in [" +
+                     std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.");
+        }
+    }
+    if (e->events_pending) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); e->collect_events(); }
+    StepHeader hh{};
+    hh.t = t; hh.snap = e->opts.bracket_snap; hh.head = e->head < 0 ? 0 : e->head; hh.len = 0; hh.cap = e->cap;
+    CUDA_CHECK(cudaMemcpyAsync(e->d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, e->stream));
+    e->enqueue_phase(1, nullptr, nullptr, nullptr, false);
+    if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
+    FinalizeGroups fg{};
+    if (e->wave_mode == 2)
+        for (size_t g = 0; g < e->groups.size(); ++g) {
+            auto& G = *e->groups[g];
+            fg.dof0[g] = G.dof0; fg.nd[g] = G.nd; fg.chunk0[g] = G.chunk0; fg.nchunk[g] = G.nchunk;
+        }
+    FinalizeArgs fa{};
+    fa.hdr = e->d_hdr.p; fa.exc_partial = e->d_exc_partial.p; fa.force = e->d_wave_tmp.p; fa.comp = nullptr;
+    fa.reg_amp = e->d_reg_amp.p; fa.reg_omega = e->d_reg_omega.p; fa.reg_mag = e->d_reg_mag.p; fa.reg_phase = e->d_reg_phase.p;
+    fa.B = e->B; fa.Bp = e->Bp; fa.D = e->D; fa.N = e->N; fa.rad_nchunk = 0; fa.wave_mode = e->wave_mode;
+    fa.exc_ngroups = (e->wave_mode == 2) ? int(e->groups.size()) : 0; fa.exc_ndmax = e->exc_ndmax; fa.waves_only = 1;
+    CUDA_CHECK(launch_finalize(fa, e->hs, fg, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, e->d_wave_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->prof.kernel_launches += 2 + (e->wave_mode == 2 ? (long long)e->groups.size() : 0);
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// Re-stages the radiation kernel after hc_tables_set_convolution_mode was called on the ensemble's tables.
+hc_status hc_ensemble_refresh_rirf(hc_ensemble* e) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const hc_tables* t = e->T;
+    const int D = e->D, L = e->L;
+    std::vector<double> Kdev(size_t(L) * D * D);
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c)
+            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s];
+    CUDA_CHECK(cudaMemcpy(e->d_K.p, Kdev.data(), Kdev.size() * sizeof(double), cudaMemcpyHostToDevice));
     return HC_OK;
     HC_GUARD_END
 }

@@ -14,7 +14,6 @@
 #include "hc_internal.h"
 
 namespace hc {
-namespace {
 
 struct H5File {
     std::vector<uint8_t> buf;
@@ -191,8 +190,6 @@ struct H5File {
     }
 };
 
-}  // namespace
-
 hc_tables* load_bemio_h5(const char* path, int num_bodies) {
     if (num_bodies < 1) fail(HC_ERR_INVALID, "num_bodies must be >= 1");
     H5File f(path);
@@ -262,3 +259,51 @@ hc_tables* load_bemio_h5(const char* path, int num_bodies) {
 }
 
 }  // namespace hc
+
+// ---- generic dataset access (results files, fixtures) ----------------------------------------------
+extern "C" {
+
+hc_status hc_h5_read_f64(const char* file, const char* dataset, int* rank, uint64_t* dims, double* out, size_t capacity) {
+    try {
+        hc::H5File f(file);
+        std::vector<uint64_t> d;
+        hc::dvec v = f.numbers(dataset, &d);
+        if (rank) *rank = int(d.size());
+        if (dims) for (size_t i = 0; i < d.size() && i < 8; ++i) dims[i] = d[i];
+        if (out) {
+            if (capacity < v.size()) hc::fail(HC_ERR_INVALID, "hc_h5_read_f64: output buffer too small");
+            std::copy(v.begin(), v.end(), out);
+        }
+        return HC_OK;
+    } catch (const hc::StatusError& e) { hc::set_last_error(e.msg); return e.code; }
+      catch (const std::exception& e) { hc::set_last_error(e.what()); return HC_ERR_IO; }
+}
+
+hc_status hc_h5_read_string(const char* file, const char* dataset, char* out, size_t capacity) {
+    try {
+        hc::H5File f(file);
+        auto d = f.dataset(dataset);
+        if (d.type_class != 3) hc::fail(HC_ERR_INVALID, "hc_h5_read_string: not a fixed-length string dataset");
+        std::string s(reinterpret_cast<const char*>(&f.buf[d.data_off]), size_t(d.data_size));
+        s = s.substr(0, s.find('\0'));
+        if (capacity < s.size() + 1) hc::fail(HC_ERR_INVALID, "hc_h5_read_string: output buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+        return HC_OK;
+    } catch (const hc::StatusError& e) { hc::set_last_error(e.msg); return e.code; }
+      catch (const std::exception& e) { hc::set_last_error(e.what()); return HC_ERR_IO; }
+}
+
+// children of a group, '\n'-separated, sorted
+hc_status hc_h5_list(const char* file, const char* group, char* out, size_t capacity) {
+    try {
+        hc::H5File f(file);
+        std::string s;
+        for (auto& kv : f.children(f.resolve(group))) { if (!s.empty()) s += "\n"; s += kv.first; }
+        if (capacity < s.size() + 1) hc::fail(HC_ERR_INVALID, "hc_h5_list: output buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+        return HC_OK;
+    } catch (const hc::StatusError& e) { hc::set_last_error(e.msg); return e.code; }
+      catch (const std::exception& e) { hc::set_last_error(e.what()); return HC_ERR_IO; }
+}
+
+}  // extern "C"

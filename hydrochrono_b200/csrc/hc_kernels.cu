@@ -379,12 +379,14 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
     // ChVector3::Length(): sqrt(x*x + y*y + z*z)
     const double glen = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
     const double rho_g = __dmul_rn(hs.rho, glen);
+    double fh = 0.0;
+    if (!a.waves_only) {
     const double* pose = a.pose + (size_t)b * D + 6 * body;
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 6; ++j)
         s = __dadd_rn(s, __dmul_rn(hs.Kh[body][i * 6 + j], __dsub_rn(pose[j], hs.equilibrium[body][j])));
-    double fh = __dmul_rn(-rho_g, s);
+    fh = __dmul_rn(-rho_g, s);
     const double V = hs.disp_vol[body];
     const double bx = __dmul_rn(__dmul_rn(hs.rho, -gx), V);
     const double by = __dmul_rn(__dmul_rn(hs.rho, -gy), V);
@@ -400,9 +402,10 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         default: add = __dsub_rn(__dmul_rn(rx, by), __dmul_rn(ry, bx)); break;
     }
     fh = __dadd_rn(fh, add);
+    }
     // ---- radiation: fixed-order sum of lag-chunk partials ----
     double fr = 0.0;
-    {
+    if (!a.waves_only) {
         const double* p = a.rad_partial + (size_t)d * a.Bp + b;
         const size_t stride = (size_t)D * a.Bp;
         int ch = 0;
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         }
     }
     const size_t o = (size_t)b * D + d;
+    if (a.waves_only) { a.force[o] = fw; return; }
     a.force[o] = __dadd_rn(__dsub_rn(fh, fr), fw);                   // hs - rad + waves (:758-760)
     if (a.comp) {
         const size_t BD = (size_t)a.B * D;

@@ -75,6 +75,7 @@ struct FinalizeArgs {
     int wave_mode;            // 0 none, 1 regular, 2 irregular
     int exc_ngroups;
     int exc_ndmax;
+    int waves_only;           // 1: write only the wave force (WaveBase::GetForceAtTime), no state needed
 };
 
 struct EtaArgs {

@@ -246,6 +246,27 @@ hc_status hc_tables_cb(const hc_tables* t, int b, double* out) {
     return HC_OK;
 }
 
+hc_status hc_tables_freq_list(const hc_tables* t, double* out) {
+    std::copy(t->w_list.begin(), t->w_list.end(), out);
+    return HC_OK;
+}
+hc_status hc_tables_excitation_mag(const hc_tables* t, int b, double* out) {
+    if (hc_status s = check_body(t, b)) return s;
+    std::copy(t->body[b].exc_mag.begin(), t->body[b].exc_mag.end(), out);
+    return HC_OK;
+}
+hc_status hc_tables_excitation_phase(const hc_tables* t, int b, double* out) {
+    if (hc_status s = check_body(t, b)) return s;
+    std::copy(t->body[b].exc_phase.begin(), t->body[b].exc_phase.end(), out);
+    return HC_OK;
+}
+hc_status hc_tables_excitation_irf(const hc_tables* t, int b, double* time, double* f) {
+    if (hc_status s = check_body(t, b)) return s;
+    if (time) std::copy(t->body[b].exc_irf_t.begin(), t->body[b].exc_irf_t.end(), time);
+    if (f) std::copy(t->body[b].exc_irf_f.begin(), t->body[b].exc_irf_f.end(), f);
+    return HC_OK;
+}
+
 hc_status hc_tables_set_convolution_mode(hc_tables* t, int mode, const hc_tapered_opts* o) {
     HC_GUARD_BEGIN
     if (mode == 0) {

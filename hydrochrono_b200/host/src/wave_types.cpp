@@ -1,0 +1,275 @@
+// WaveBase family (reference src/wave_types.cpp).  Force evaluation is delegated to the device ensemble the wave
+// is bound to; wave kinematics (Airy theory, off the per-step path) are evaluated here on the host.
+#include <hydroc/wave_types.h>
+
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <stdexcept>
+
+#include "hc_check.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// spectra (src/wave_types.cpp:679-715)
+// ---------------------------------------------------------------------------------------------
+Eigen::VectorXd PiersonMoskowitzSpectrumHz(Eigen::VectorXd& f, double Hs, double Tp) {
+    Eigen::VectorXd S(f.size());
+    hc_throw_on_error(hc_pierson_moskowitz_spectrum_hz(int(f.size()), f.data(), Hs, Tp, S.data()));
+    return S;
+}
+Eigen::VectorXd JONSWAPSpectrumHz(Eigen::VectorXd& f, double Hs, double Tp, double gamma, bool is_normalized) {
+    Eigen::VectorXd S(f.size());
+    hc_throw_on_error(hc_jonswap_spectrum_hz(int(f.size()), f.data(), Hs, Tp, gamma, is_normalized ? 1 : 0, S.data()));
+    return S;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Airy kinematics of one component (src/wave_types.cpp:14-25,61-122); waves travel along global +x
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Component { double omega, amplitude, phase, k; };
+
+double eta_of(const Component& c, double x, double t) { return c.amplitude * std::cos(c.k * x - c.omega * t + c.phase); }
+
+bool deep(const Component& c, double depth) { return 2 * M_PI / c.k > depth || c.k * depth > 500.0; }
+
+Eigen::Vector3d velocity_of(const Component& c, const Eigen::Vector3d& p, double t, double depth, double mwl) {
+    const double z = p.z() - mwl, th = c.k * p.x() - c.omega * t + c.phase;
+    Eigen::Vector3d v(0.0, 0.0, 0.0);
+    if (deep(c, depth)) {
+        v[0] = c.omega * c.amplitude * std::exp(c.k * z) * std::cos(th);
+        v[2] = c.omega * c.amplitude * std::exp(c.k * z) * std::sin(th);
+    } else {
+        v[0] = c.omega * c.amplitude * std::cosh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::cos(th);
+        v[2] = c.omega * c.amplitude * std::sinh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::sin(th);
+    }
+    return v;
+}
+
+Eigen::Vector3d acceleration_of(const Component& c, const Eigen::Vector3d& p, double t, double depth, double mwl) {
+    const double z = p.z() - mwl, th = c.k * p.x() - c.omega * t + c.phase;
+    Eigen::Vector3d a(0.0, 0.0, 0.0);
+    if (deep(c, depth)) {
+        a[0] = c.omega * c.omega * c.amplitude * std::exp(c.k * z) * std::sin(th);
+        a[2] = -c.omega * c.omega * c.amplitude * std::exp(c.k * z) * std::cos(th);
+    } else {
+        a[0] = c.omega * c.omega * c.amplitude * std::cosh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::sin(th);
+        a[2] = -c.omega * c.omega * c.amplitude * std::sinh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::cos(th);
+    }
+    return a;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// WaveBase
+// ---------------------------------------------------------------------------------------------
+void WaveBase::Bind(hc_ensemble* ens, const HydroData::SimulationParameters& sim, unsigned int num_bodies) {
+    ens_ = ens;
+    bound_bodies_ = num_bodies;
+    water_depth_ = sim.water_depth;
+    g_ = sim.g;
+}
+
+Eigen::VectorXd WaveBase::DeviceForce(double t) const {
+    if (!ens_)
+        throw std::runtime_error("wave object is not attached to a TestHydro (no device ensemble to evaluate the force)");
+    Eigen::VectorXd f(6 * bound_bodies_);
+    hc_throw_on_error(hc_waves_force_at_time(ens_, t, f.data()));
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NoWave (src/wave_types.cpp:257-264)
+// ---------------------------------------------------------------------------------------------
+void NoWave::Bind(hc_ensemble* ens, const HydroData::SimulationParameters& sim, unsigned int num_bodies) {
+    WaveBase::Bind(ens, sim, num_bodies);
+    hc_throw_on_error(hc_waves_none(ens));
+}
+Eigen::VectorXd NoWave::GetForceAtTime(double) {
+    Eigen::VectorXd f(6 * num_bodies_);
+    f.setZero();
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RegularWave (src/wave_types.cpp:266-352)
+// ---------------------------------------------------------------------------------------------
+RegularWave::RegularWave() { num_bodies_ = 1; }
+RegularWave::RegularWave(unsigned int num_b) { num_bodies_ = num_b; }
+
+void RegularWave::AddH5Data(std::vector<HydroData::RegularWaveInfo>&, HydroData::SimulationParameters& sim_data) {
+    // the excitation tables already live in the device tables; only the scalars are kept here
+    water_depth_ = sim_data.water_depth;
+    g_ = sim_data.g;
+}
+
+void RegularWave::Bind(hc_ensemble* ens, const HydroData::SimulationParameters& sim, unsigned int num_bodies) {
+    WaveBase::Bind(ens, sim, num_bodies);
+    hc_throw_on_error(hc_waves_regular(ens, 1, &regular_wave_amplitude_, &regular_wave_omega_, &regular_wave_phase_));
+}
+
+void RegularWave::Initialize() {
+    hc_throw_on_error(hc_compute_wave_number(regular_wave_omega_, water_depth_, g_, &wavenumber_));
+}
+
+Eigen::VectorXd RegularWave::GetForceAtTime(double t) { return DeviceForce(t); }
+
+Eigen::VectorXd RegularWave::GetExcitationMag() const {
+    Eigen::VectorXd m(6 * bound_bodies_);
+    hc_throw_on_error(hc_waves_regular_coeffs(ens_, 0, m.data(), nullptr, nullptr));
+    return m;
+}
+Eigen::VectorXd RegularWave::GetExcitationPhase() const {
+    Eigen::VectorXd p(6 * bound_bodies_);
+    hc_throw_on_error(hc_waves_regular_coeffs(ens_, 0, nullptr, p.data(), nullptr));
+    return p;
+}
+
+double RegularWave::GetElevation(const Eigen::Vector3d& position, double time) {
+    return eta_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position.x(), time);
+}
+Eigen::Vector3d RegularWave::GetVelocity(const Eigen::Vector3d& position, double time) {
+    return velocity_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position, time,
+                       water_depth_, mwl_);
+}
+Eigen::Vector3d RegularWave::GetAcceleration(const Eigen::Vector3d& position, double time) {
+    return acceleration_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position, time,
+                           water_depth_, mwl_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IrregularWaves (src/wave_types.cpp:430-570,717-774)
+// ---------------------------------------------------------------------------------------------
+IrregularWaves::IrregularWaves(const IrregularWaveParams& params) : params_(params) {}
+
+void IrregularWaves::AddH5Data(std::vector<HydroData::IrregularWaveInfo>&, HydroData::SimulationParameters& sim_data) {
+    water_depth_ = sim_data.water_depth;
+    g_ = sim_data.g;
+}
+
+void IrregularWaves::Bind(hc_ensemble* ens, const HydroData::SimulationParameters& sim, unsigned int num_bodies) {
+    WaveBase::Bind(ens, sim, num_bodies);
+    if (!params_.eta_file_path_.empty())
+        // reference: IrregularWaves::ReadEtaFromFile fills no time grid in this snapshot: unsupported
+        throw std::runtime_error("Unable to open file at: " + params_.eta_file_path_ + ". (eta import is not supported)");
+    hc_irregular_params q;
+    hc_irregular_default_params(&q);
+    q.simulation_dt = params_.simulation_dt_;
+    q.simulation_duration = params_.simulation_duration_;
+    q.ramp_duration = params_.ramp_duration_;
+    q.wave_height = params_.wave_height_;
+    q.wave_period = params_.wave_period_;
+    q.frequency_min = params_.frequency_min_;
+    q.frequency_max = params_.frequency_max_;
+    q.nfrequencies = params_.nfrequencies_;
+    q.peak_enhancement_factor = params_.peak_enhancement_factor_;
+    q.is_normalized = params_.is_normalized_ ? 1 : 0;
+    q.seed = params_.seed_;
+    hc_throw_on_error(hc_waves_irregular(ens, &q, nullptr, nullptr, nullptr));
+    spectrum_fetched_ = false;
+}
+
+void IrregularWaves::FetchSpectrum() const {
+    if (spectrum_fetched_) return;
+    if (!ens_) throw std::runtime_error("Spectrum has not been created. Initialize with wave height and period to create spectrum.");
+    int nf = 0, ne = 0;
+    hc_throw_on_error(hc_waves_irregular_sizes(ens_, &nf, &ne, nullptr));
+    if (nf == 0) throw std::runtime_error("Spectrum has not been created. Initialize with wave height and period to create spectrum.");
+    freqs_.resize(nf); S_.resize(nf); widths_.resize(nf); phases_.resize(nf); wavenumbers_.resize(nf);
+    hc_throw_on_error(hc_waves_irregular_spectrum(ens_, 0, freqs_.data(), S_.data(), widths_.data(), phases_.data(),
+                                                  wavenumbers_.data()));
+    spectrum_fetched_ = true;
+}
+
+std::vector<double> IrregularWaves::GetSpectrum() { FetchSpectrum(); return S_; }
+std::vector<double> IrregularWaves::GetFrequenciesHz() const { FetchSpectrum(); return freqs_; }
+
+std::vector<double> IrregularWaves::GetFreeSurfaceElevation() {
+    int nf = 0, ne = 0;
+    if (!ens_) return {};
+    hc_throw_on_error(hc_waves_irregular_sizes(ens_, &nf, &ne, nullptr));
+    std::vector<double> eta(ne);
+    hc_throw_on_error(hc_waves_irregular_eta(ens_, 0, nullptr, eta.data()));
+    return eta;
+}
+std::vector<double> IrregularWaves::GetFreeSurfaceTime() const {
+    int nf = 0, ne = 0;
+    if (!ens_) return {};
+    hc_throw_on_error(hc_waves_irregular_sizes(ens_, &nf, &ne, nullptr));
+    std::vector<double> t(ne);
+    hc_throw_on_error(hc_waves_irregular_eta(ens_, 0, t.data(), nullptr));
+    return t;
+}
+
+Eigen::VectorXd IrregularWaves::GetForceAtTime(double t) { return DeviceForce(t); }
+
+double IrregularWaves::GetElevation(const Eigen::Vector3d& position, double time) {
+    FetchSpectrum();
+    double eta = 0.0;
+    for (size_t i = 0; i < freqs_.size(); ++i) {
+        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
+        eta += eta_of(c, position.x(), time);
+    }
+    return eta;
+}
+
+Eigen::Vector3d IrregularWaves::GetVelocity(const Eigen::Vector3d& position, double time) {
+    FetchSpectrum();
+    Eigen::Vector3d p = position;
+    if (params_.wave_stretching_) {   // Wheeler stretching (:516-525)
+        const double eta = GetElevation(position, time);
+        const double z = position.z() - mwl_;
+        p[2] = water_depth_ * (z - eta) / (water_depth_ + eta);
+    }
+    Eigen::Vector3d v(0.0, 0.0, 0.0);
+    for (size_t i = 0; i < freqs_.size(); ++i) {
+        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
+        v += velocity_of(c, p, time, water_depth_, mwl_);
+    }
+    return v;
+}
+
+Eigen::Vector3d IrregularWaves::GetAcceleration(const Eigen::Vector3d& position, double time) {
+    FetchSpectrum();
+    Eigen::Vector3d p = position;
+    if (params_.wave_stretching_) {
+        const double eta = GetElevation(position, time);
+        const double z = position.z() - mwl_;
+        p[2] = water_depth_ * (z - eta) / (water_depth_ + eta);
+    }
+    Eigen::Vector3d a(0.0, 0.0, 0.0);
+    for (size_t i = 0; i < freqs_.size(); ++i) {
+        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
+        a += acceleration_of(c, p, time, water_depth_, mwl_);
+    }
+    return a;
+}
+
+// Free-surface strip mesh for visualisation: two vertices per elevation sample, two triangles per quad.
+void IrregularWaves::SetUpWaveMesh(std::string filename) {
+    mesh_file_name_ = filename;
+    const std::vector<double> eta = GetFreeSurfaceElevation();
+    const int n = static_cast<int>(std::ceil(params_.simulation_duration_ / params_.simulation_dt_)) + 1;
+    std::ofstream out(filename);
+    if (!out) { std::cerr << "Failed to open " << filename << std::endl; return; }
+    out << "# Wavefront OBJ file exported by hydrochrono_b200\n";
+    out << std::fixed << std::setprecision(6);
+    const int count = std::min<int>(n, int(eta.size()));
+    for (int i = 0; i < count; ++i) {
+        const double x = -1.0 * (i * params_.simulation_dt_);
+        out << "v " << std::setw(14) << x << ' ' << std::setw(14) << -10.0 << ' ' << std::setw(14) << eta[i] << "\n";
+        out << "v " << std::setw(14) << x << ' ' << std::setw(14) << 10.0 << ' ' << std::setw(14) << eta[i] << "\n";
+    }
+    for (int i = 0; i + 1 < count; ++i) {
+        out << "f " << 2 * i + 1 << ' ' << 2 * i + 2 << ' ' << 2 * i + 4 << "\n";
+        out << "f " << 2 * i + 1 << ' ' << 2 * i + 4 << ' ' << 2 * i + 3 << "\n";
+    }
+}
+std::string IrregularWaves::GetMeshFile() { return mesh_file_name_; }
+Eigen::Vector3<double> IrregularWaves::GetWaveMeshVelocity() { return Eigen::Vector3d(1.0, 0, 0); }

@@ -111,6 +111,12 @@ HC_API hc_status hc_tables_inf_added_mass(const hc_tables* t, int body, double* 
 HC_API hc_status hc_tables_disp_vol(const hc_tables* t, int body, double* out);
 HC_API hc_status hc_tables_cg(const hc_tables* t, int body, double* out /*[3]*/);
 HC_API hc_status hc_tables_cb(const hc_tables* t, int body, double* out /*[3]*/);
+/* HydroData::RegularWaveInfo / IrregularWaveInfo (include/hydroc/h5fileinfo.h:60-72), scaled as the reference
+ * scales them at load time (mag x rho*g, IRF x rho*g). */
+HC_API hc_status hc_tables_freq_list(const hc_tables* t, double* out /*[nw]*/);
+HC_API hc_status hc_tables_excitation_mag(const hc_tables* t, int body, double* out /*[6][nw]*/);
+HC_API hc_status hc_tables_excitation_phase(const hc_tables* t, int body, double* out /*[6][nw]*/);
+HC_API hc_status hc_tables_excitation_irf(const hc_tables* t, int body, double* time /*[Le0]*/, double* f /*[6][Le0]*/);
 
 /* TestHydro::SetRadiationConvolutionMode + SetTaperedDirectOptions (hydro_forces.h:233-265).
  * mode 0 = Baseline, 1 = TaperedDirect.  smoothing: "moving_average" selects the moving average, anything else
@@ -211,6 +217,11 @@ HC_API hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, 
 /* Components of the last evaluation (ComputeForceHydrostatics / RadiationDampingConv / Waves), host [B][6N]
  * each; any may be NULL. */
 HC_API hc_status hc_get_components(hc_ensemble* e, double* hydrostatic, double* radiation, double* waves);
+/* WaveBase::GetForceAtTime(t) (src/wave_types.cpp:257-264,315-327,552-570) for every instance, host [B][6N]:
+ * the wave excitation force alone at an arbitrary time; does not touch the velocity history or the force cache. */
+HC_API hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* waves);
+/* Re-stage the radiation kernel after hc_tables_set_convolution_mode() changed the ensemble's tables. */
+HC_API hc_status hc_ensemble_refresh_rirf(hc_ensemble* e);
 HC_API hc_status hc_sync(hc_ensemble* e);
 HC_API int hc_ensemble_history_len(const hc_ensemble* e);
 
@@ -253,6 +264,28 @@ HC_API hc_status hc_resample_excitation_irf(const hc_tables* t, double dt, int b
                                             double* width_out, double* f_out /*[6][n]*/);
 /* Random phases of CreateSpectrum (src/wave_types.cpp:663-669): std::mt19937(seed), uniform_real(0, 2 pi). */
 HC_API hc_status hc_random_phases(int seed, int n, double* out);
+
+/* ---------------------------------------------------------------------------------------
+ * HDF5 output / generic input without libhdf5 (classic format: superblock v0, old-style groups, contiguous
+ * little-endian float64 datasets, fixed-length strings, scalar attributes).  Replaces the HDF5 C++ calls of
+ * H5Writer (src/h5_writer.cpp) used by SimulationExporter (src/simulation_exporter.cpp:181-199,373-391).
+ * Paths are '/'-separated; intermediate groups are created on demand.  Nothing touches the disk before save.
+ * ------------------------------------------------------------------------------------- */
+typedef struct hc_h5_writer hc_h5_writer;
+HC_API hc_status hc_h5_writer_create(hc_h5_writer** out);
+HC_API void hc_h5_writer_destroy(hc_h5_writer* w);
+HC_API hc_status hc_h5_writer_put_group(hc_h5_writer* w, const char* path);
+HC_API hc_status hc_h5_writer_put_f64(hc_h5_writer* w, const char* path, int rank, const uint64_t* dims,
+                                      const double* data);
+HC_API hc_status hc_h5_writer_put_string(hc_h5_writer* w, const char* path, const char* value);
+HC_API hc_status hc_h5_writer_attr_string(hc_h5_writer* w, const char* path, const char* name, const char* value);
+HC_API hc_status hc_h5_writer_attr_f64(hc_h5_writer* w, const char* path, const char* name, double value);
+HC_API hc_status hc_h5_writer_save(hc_h5_writer* w, const char* file);
+/* Reads: out may be NULL to query rank/dims (dims has room for 8 entries). */
+HC_API hc_status hc_h5_read_f64(const char* file, const char* dataset, int* rank, uint64_t* dims, double* out,
+                                size_t capacity);
+HC_API hc_status hc_h5_read_string(const char* file, const char* dataset, char* out, size_t capacity);
+HC_API hc_status hc_h5_list(const char* file, const char* group, char* out /* '\n'-separated */, size_t capacity);
 
 #ifdef __cplusplus
 }

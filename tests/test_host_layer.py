@@ -1,0 +1,102 @@
+"""C++ host layer (hydrochrono_b200/host): HydroChrono's own class surface -- TestHydro, ForceFunc6d, ComponentFunc,
+ChLoadAddedMass, H5FileInfo/HydroData, NoWave/RegularWave/IrregularWaves, ReadHydroYAML, SetupHydroFromYAML -- over
+the C ABI.  The demo mains mirror the reference's regression mains (tests/regression/sphere/**) call for call and
+their trajectories are held against the reference's golden files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from hydrochrono_b200 import h5io, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "hydrochrono_b200", "host")
+BUILD = os.path.join(HOST, "build")
+
+
+@pytest.fixture(scope="module")
+def host_build():
+    subprocess.check_call(["make", "-C", HOST, "-j8"], stdout=subprocess.DEVNULL)
+    return BUILD
+
+
+@pytest.fixture(scope="module")
+def sphere_h5(tmp_path_factory):
+    f = tmp_path_factory.mktemp("h5") / "sphere.h5"
+    h5io.write_bemio(f, common.sphere_raw())
+    return str(f)
+
+
+def _read_traj(path):
+    a = np.loadtxt(path, skiprows=1)
+    return a[:, 0], a[:, 1]
+
+
+def test_yaml_parser(host_build):
+    out = subprocess.run([os.path.join(host_build, "test_hydro_yaml_parser"), os.path.join(HOST, "tests", "data")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "All hydro YAML parser tests passed" in out.stdout
+
+
+def test_host_layer_fails_loudly_without_gpu(host_build, sphere_h5, tmp_path):
+    import hydrochrono_b200 as hc
+    if hc.device_count() > 0:
+        pytest.skip("CUDA device present")
+    out = subprocess.run([os.path.join(host_build, "demo_sphere_decay"), sphere_h5, str(tmp_path / "o.txt")],
+                         capture_output=True, text=True)
+    assert out.returncode == 1
+    assert "no CPU fallback" in out.stderr
+
+
+@pytest.mark.gpu
+def test_demo_sphere_decay_golden(host_build, sphere_h5, tmp_path):
+    o = tmp_path / "decay.txt"
+    out = subprocess.run([os.path.join(host_build, "demo_sphere_decay"), sphere_h5, str(o)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    t, z = _read_traj(o)
+    gold = common.sphere_goldens()["decay_um"] * 1e-6
+    assert z.size == gold.size
+    n1, n2 = common.traj_norms(z, gold)
+    assert n1 <= 1e-4 and n2 <= 0.02 and n2 <= 1.0e-6, (n1, n2)   # reference gate, then print precision
+    assert "radiation_calls %d" % gold.size in out.stdout           # exactly one device evaluation per time value
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wave_num", [1, 7])
+def test_demo_sphere_regular_waves_golden(host_build, sphere_h5, tmp_path, wave_num):
+    o = tmp_path / "reg.txt"
+    duration = 90.0
+    out = subprocess.run([os.path.join(host_build, "demo_sphere_waves"), sphere_h5, str(o), "regular", str(wave_num),
+                          str(duration)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    t, z = _read_traj(o)
+    gold = common.sphere_goldens()["reg%d_um" % wave_num][:z.size] * 1e-6
+    n1, n2 = common.traj_norms(z, gold)
+    assert n1 <= 1e-4 and n2 <= 0.02 and n2 <= 2.0e-6, (n1, n2)
+
+
+@pytest.mark.gpu
+def test_demo_sphere_irregular_waves_golden(host_build, sphere_h5, tmp_path):
+    o = tmp_path / "irr.txt"
+    out = subprocess.run([os.path.join(host_build, "demo_sphere_waves"), sphere_h5, str(o), "irregular", "75.0"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    t, z = _read_traj(o)
+    gold = common.sphere_goldens()["irreg_um"][:z.size] * 1e-6
+    n1, n2 = common.traj_norms(z, gold)
+    assert n1 <= 1e-4 and n2 <= 0.02 and n2 <= 2e-4, (n1, n2)
+
+
+@pytest.mark.gpu
+def test_api_surface_two_bodies(host_build, tmp_path):
+    h5 = tmp_path / "rm3_like.h5"
+    h5io.write_bemio(h5, synth.rm3_like(rirf_steps=201, rirf_duration=10.0, exc_irf_steps=201, exc_half_window=5.0))
+    y = tmp_path / "rm3.hydro.yaml"
+    y.write_text("hydrodynamics:\n  bodies:\n    - name: body1\n      h5_file: rm3_like.h5\n    - name: body2\n"
+                 "      h5_file: rm3_like.h5\n  waves:\n    type: irregular\n    height: 2.5\n    period: 8.0\n    seed: 5\n")
+    out = subprocess.run([os.path.join(host_build, "test_api_surface"), str(h5), str(y)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "API surface test passed" in out.stdout
