@@ -240,7 +240,10 @@ def main():
     stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
                       exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream)
-    seeds = (1 + rank * B + np.arange(B)).astype(np.int32)
+    from hydrochrono_b200 import shard
+    # weak scaling: every rank owns a contiguous block of B instances of the (world * B)-instance ensemble
+    lo, hi = shard.shard_range(world * B, world, rank)
+    seeds = shard.instance_seeds(lo, hi)
     t_setup = time.time()
     ens.set_waves_irregular(dt=DT, duration=total_steps * DT, ramp=SEA["ramp"], Hs=SEA["Hs"], Tp=SEA["Tp"],
                             fmin=SEA["fmin"], fmax=SEA["fmax"], nfreq=SEA["nfreq"], gamma=SEA["gamma"], seeds=seeds)
