@@ -198,6 +198,7 @@ class ChBody : public ChLoadable {
     const ChQuaterniond& GetRot() const { return rot_; }
     void SetPosDt(const ChVector3d& v) { vel_ = v; }
     const ChVector3d& GetPosDt() const { return vel_; }
+    const ChVector3d& GetPosDt2() const { return acc_; }
     void SetAngVelParent(const ChVector3d& w) { wvel_ = w; }
     const ChVector3d& GetAngVelParent() const { return wvel_; }
     void AddForce(std::shared_ptr<ChForce> f) { forces_.push_back(std::move(f)); }
@@ -214,7 +215,7 @@ class ChBody : public ChLoadable {
     bool fixed_ = false;
     double mass_ = 1.0;
     ChVector3d inertia_{1, 1, 1};
-    ChVector3d pos_, vel_, wvel_;
+    ChVector3d pos_, vel_, wvel_, acc_;
     ChQuaterniond rot_;
     std::vector<std::shared_ptr<ChForce>> forces_;
     ChSystem* system_ = nullptr;

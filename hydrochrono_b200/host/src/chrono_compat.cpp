@@ -106,6 +106,7 @@ int ChSystem::DoStepDynamics(double dt) {
             v[k] = b->free_dof[k] ? v[k] + dt * acc[6 * i + k] : 0.0;
             w[k] = b->free_dof[3 + k] ? w[k] + dt * acc[6 * i + 3 + k] : 0.0;
         }
+        b->acc_ = ChVector3d(acc[6 * i], acc[6 * i + 1], acc[6 * i + 2]);
         b->SetPosDt(v);
         b->SetAngVelParent(w);
         b->SetPos(b->GetPos() + v * dt);

@@ -44,3 +44,12 @@ def force_tol(ref_series, rel=1e-9, floor_frac=1e-3):
     ref_series = np.asarray(ref_series)
     comp_max = np.abs(ref_series).reshape(-1, ref_series.shape[-1]).max(axis=0)
     return rel * np.maximum(np.abs(ref_series), floor_frac * comp_max)
+
+
+def rms_relative_error(ref, pred):
+    """Gate of the reference's CLI regression harness (tests/regression/run_hydrochrono/compare_results.py:103-107)."""
+    ref, pred = np.asarray(ref), np.asarray(pred)
+    ref_rms = float(np.sqrt(np.mean(np.square(ref))))
+    if ref_rms == 0.0:
+        return float(np.sqrt(np.mean(np.square(pred))))
+    return float(np.sqrt(np.mean(np.square(pred - ref))) / ref_rms)

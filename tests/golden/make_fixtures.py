@@ -6,7 +6,8 @@ Run HERE (the container that has /root/reference); the GPU box only sees the gen
                        (src/h5fileinfo.cpp:27-91), raw/unscaled, via tests/h5lite.py
   sphere_goldens.npz   the reference's golden heave trajectories for the sphere
                        (tests/regression/reference_data/sphere/**), stored as int32 micro-metres
-                       (the files print 6 decimals) + the step count.
+                       (the files print 6 decimals) + the step count; plus time / heave of
+                       tests/regression/run_hydrochrono/iea_sphere/decay/expected/results.still.h5.
 """
 import os
 import sys
@@ -51,6 +52,11 @@ def goldens():
         out["reg%d_um" % i] = np.round(a[:, 1] * 1e6).astype(np.int32)
     a = _traj(os.path.join(rd, "irreg_waves/hc_ref_sphere_irreg_waves.txt"), 2)
     out["irreg_um"] = np.round(a[:, 1] * 1e6).astype(np.int32)
+    # CLI regression golden (HHT integrator, g = 9.8, dt = 0.01): heave of body1 + time, float64
+    from h5lite import H5Lite
+    h = H5Lite(os.path.join(REF, "tests/regression/run_hydrochrono/iea_sphere/decay/expected/results.still.h5"))
+    out["iea_decay_t"] = h.read("results/time/time")
+    out["iea_decay_z"] = h.read("results/model/bodies/body1/position")[:, 2].copy()
     np.savez_compressed(os.path.join(HERE, "sphere_goldens.npz"), **out)
     for k, v in out.items():
         print(k, v.shape)
