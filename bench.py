@@ -35,14 +35,14 @@ DOFS = 12
 RIRF_STEPS = 1001
 EXC_STEPS = 6000
 SEA = dict(Hs=2.5, Tp=8.0, gamma=3.3, fmin=0.001, fmax=1.0, nfreq=1000, ramp=20.0)
-SNAP = 1e-9
+SNAP = 1e-8
 GVEC = (0.0, 0.0, -9.81)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="instances per GPU")
@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
     return ap.parse_args()
 
 
@@ -239,7 +240,8 @@ def main():
     T = hc.Tables.from_raw(raw)
     stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
-                      exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream)
+                      exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream,
+                      exc_lookahead=1 if args.no_lookahead else 0)
     from hydrochrono_b200 import shard
     # weak scaling: every rank owns a contiguous block of B instances of the (world * B)-instance ensemble
     lo, hi = shard.shard_range(world * B, world, rank)
@@ -266,16 +268,19 @@ def main():
     torch.cuda.synchronize()
 
     step_no = [0]
+    t_now = [0.0]     # advanced as Chrono advances ChTime: t += dt
 
     def dev_step():
         n = step_no[0]
-        ens.step_device(n * DT, d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC)
+        ens.step_device(t_now[0], d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC)
         step_no[0] = n + 1
+        t_now[0] += DT
 
     def host_step():
         n = step_no[0]
-        ens.step(n * DT, h_pose[n % NBUF].numpy(), h_vel[n % NBUF].numpy(), GVEC, out=h_force.numpy())
+        ens.step(t_now[0], h_pose[n % NBUF].numpy(), h_vel[n % NBUF].numpy(), GVEC, out=h_force.numpy())
         step_no[0] = n + 1
+        t_now[0] += DT
 
     # ---- untimed: fill the radiation history window -----------------------------------------------
     for _ in range(prefill):
@@ -335,6 +340,7 @@ def main():
     kms = ens.kernel_ms(reset=True)
     ens.set_profiling(False)
 
+    fp64_peak = hc.measure_fp64_peak(local_rank) if rank == 0 else None
     if rank == 0:
         peak, peak_src = hbm_peak()
         rows = RIRF_STEPS if snap > 0 else 2 * RIRF_STEPS      # distinct history rows touched per step
@@ -342,6 +348,10 @@ def main():
         exc_bytes = B * 8 * (EXC_STEPS + 1) + 8 * (DOFS + 2) * EXC_STEPS
         ach = rad_bytes / (kms["radiation"] * 1e-3) / 1e9
         ach_exc = exc_bytes / (kms["excitation"] * 1e-3) / 1e9 if kms["excitation"] > 0 else None
+        exc_flops = 2.0 * DOFS * EXC_STEPS * B                      # per step: 2 * D * Le per instance
+        rad_flops = 2.0 * DOFS * DOFS * RIRF_STEPS * B
+        exc_tf = exc_flops / (kms["excitation"] * 1e-3) / 1e12 if kms["excitation"] > 0 else None
+        rad_tf = rad_flops / (kms["radiation"] * 1e-3) / 1e12
         traffic = ncu_traffic()
         value = world * B * K / t_dev
         e2e = world * B * K / t_e2e
@@ -353,6 +363,7 @@ def main():
                        "dofs": DOFS, "rirf_steps": RIRF_STEPS, "exc_irf_steps": EXC_STEPS, "dt": DT,
                        "spectrum_components": nf, "eta_samples": n_eta, "sea_state": SEA,
                        "bracket_snap": snap, "history_prefill_steps": prefill, "cuda_graph": not args.no_graph,
+                       "excitation_lookahead_steps": 1 if args.no_lookahead else 8,
                        "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
                              % (8e-9 * DOFS * B * 6002, 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
                        "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s); "
@@ -366,10 +377,19 @@ def main():
                          "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
                          "kernel_ms": kms["radiation"],
-                         "excitation": {"kernel": "k_excitation<12>", "achieved": ach_exc,
-                                        "frac": (ach_exc / peak) if ach_exc else None,
-                                        "algorithmic_bytes_per_launch": exc_bytes, "kernel_ms": kms["excitation"],
-                                        "traffic": (traffic or {}).get("excitation_dram_bytes_per_launch")}},
+                         "fp64_tflops": rad_tf, "fp64_peak_tflops": fp64_peak,
+                         "fp64_frac": rad_tf / fp64_peak if fp64_peak else None,
+                         "excitation": ({"kernel": "k_exc_block<12> (look-ahead, 8 steps per eta pass)", "bound": "fp64",
+                                         "achieved": exc_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                         "frac": exc_tf / fp64_peak if (exc_tf and fp64_peak) else None,
+                                         "peak_source": "measured in this run (hc_measure_fp64_peak, DFMA loop)",
+                                         "flops_per_step": exc_flops, "kernel_ms_per_step": kms["excitation"],
+                                         "hbm_gbs_per_step_equiv": ach_exc / 8 if ach_exc else None}
+                                        if not args.no_lookahead else
+                                        {"kernel": "k_excitation<12>", "bound": "hbm", "achieved": ach_exc, "peak": peak,
+                                         "unit": "GB/s", "frac": (ach_exc / peak) if ach_exc else None,
+                                         "algorithmic_bytes_per_launch": exc_bytes, "kernel_ms": kms["excitation"],
+                                         "traffic": (traffic or {}).get("excitation_dram_bytes_per_launch")})},
             "kernel_ms": kms,
             "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},
             "checksum": checksum,

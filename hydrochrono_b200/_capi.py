@@ -40,7 +40,8 @@ class TaperedOpts(C.Structure):
 
 class EnsembleOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("batch", C.c_int), ("dt_hint", C.c_double), ("bracket_snap", C.c_double),
-                ("rad_chunk", C.c_int), ("exc_chunk", C.c_int), ("use_graph", C.c_int), ("stream", vp)]
+                ("rad_chunk", C.c_int), ("exc_chunk", C.c_int), ("use_graph", C.c_int), ("exc_lookahead", C.c_int),
+                ("stream", vp)]
 
 
 class IrregularParams(C.Structure):
@@ -115,6 +116,7 @@ SIGNATURES = {
     "hc_set_profiling": (C.c_int, [vp, C.c_int]),
     "hc_get_profile": (C.c_int, [vp, C.POINTER(ProfileStats)]),
     "hc_get_kernel_ms": (C.c_int, [vp, dp, dp, dp, dp, C.c_int]),
+    "hc_measure_fp64_peak": (C.c_int, [C.c_int, dp]),
     "hc_host_alloc": (vp, [C.c_size_t]),
     "hc_host_free": (None, [vp]),
     "hc_pierson_moskowitz_spectrum_hz": (C.c_int, [C.c_int, dp, C.c_double, C.c_double, dp]),

@@ -101,7 +101,16 @@ struct hc_ensemble {
     // irregular
     hc_irregular_params ip{};
     std::vector<ExcIrfBody> irf;      // per body, host
-    struct Group { int dof0, nd, Le, chunk0, nchunk; DevBuf<double> tau, fw, w1, w2; DevBuf<int> idx; double tau_first, tau_last; };
+    struct Group {
+        int dof0, nd, Le, chunk0, nchunk;
+        DevBuf<double> tau, fw, w1, w2;
+        DevBuf<int> idx;
+        double tau_first, tau_last;
+        // look-ahead block: per-(time, lag) brackets and per-row taps
+        DevBuf<int> la_idx;
+        DevBuf<double> la_w1, la_w2, la_taps;
+        int la_rows_cap = 0;
+    };
     std::vector<std::unique_ptr<Group>> groups;
     int exc_chunk = 0, exc_total_chunks = 0, exc_ndmax = 0;
     DevBuf<double> d_exc_partial, d_eta, d_eta_t, d_omega, d_amp, d_phase;
@@ -110,6 +119,15 @@ struct hc_ensemble {
     std::vector<double> phases_h;     // [B][nf]
     bool per_instance_spectrum = false;
     int n_eta = 0, nf = 0;
+    // excitation look-ahead (state-independent wave force evaluated kLaT predicted steps at a time)
+    bool la_enabled = false;
+    double la_dt = 0.0;
+    std::vector<double> la_times;     // predicted times of the current block
+    int la_len = 0, la_pos = 0;       // valid slots / next slot expected
+    int la_builds = 0, la_hits_this_block = 0, la_poor_blocks = 0;
+    DevBuf<double> d_la_cache, d_la_times;
+    cudaEvent_t ev_la[2] = {nullptr, nullptr};
+    bool la_events_pending = false;
 
     // graph + profiling
     cudaGraph_t graph = nullptr, graph1 = nullptr;          // phase 2 / phase 1
@@ -119,6 +137,8 @@ struct hc_ensemble {
     cudaEvent_t ev_inputs = nullptr;
     const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
+    bool phase_uses_lookahead = false;    // set per step: phase 1 skips the per-step excitation kernels
+    bool graph1_la = false;               // what the captured phase-1 graph contains
     cudaEvent_t ev[EV_COUNT] = {};
     hc_profile_stats prof{};
     double acc_ms[4] = {0, 0, 0, 0};
@@ -132,6 +152,7 @@ struct hc_ensemble {
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_inputs) cudaEventDestroy(ev_inputs);
+        for (auto& x : ev_la) if (x) cudaEventDestroy(x);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -149,6 +170,9 @@ struct hc_ensemble {
     void enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
     void launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void begin_step(double t, const double* g);
+    void setup_lookahead();
+    int lookahead_slot(double t);
+    void build_lookahead_block(double t);
     void finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void collect_events();
 };
@@ -228,7 +252,8 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     pa.pr_new = d_pr_new.p; pa.pr_old = d_pr_old.p; pa.pr_wn = d_pr_wn.p; pa.pr_wo = d_pr_wo.p; pa.pr_wd = d_pr_wd.p;
     pa.B = B; pa.Bp = Bp; pa.D = D; pa.L = L;
     pa.ngroups = 0;
-    if (wave_mode == 2) {
+    const bool per_step_exc = (wave_mode == 2) && !(la_enabled && phase_uses_lookahead);
+    if (per_step_exc) {
         pa.ngroups = int(groups.size());
         for (size_t g = 0; g < groups.size(); ++g) {
             pa.tau[g] = groups[g]->tau.p; pa.Le[g] = groups[g]->Le;
@@ -240,7 +265,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
         CUDA_CHECK(launch_prestep(pa, 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
-        if (wave_mode == 2) {
+        if (per_step_exc) {
             ExcitationArgs ea{};
             ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
             ea.eta_dt = ip.simulation_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
@@ -275,6 +300,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.reg_amp = d_reg_amp.p; fa.reg_omega = d_reg_omega.p; fa.reg_mag = d_reg_mag.p; fa.reg_phase = d_reg_phase.p;
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
+    fa.exc_cache = d_la_cache.p;
     CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_END], stream));
 }
@@ -287,6 +313,12 @@ void hc_ensemble::collect_events() {
     cudaEventElapsedTime(&app, ev[EV_EXC], ev[EV_APPEND]);
     cudaEventElapsedTime(&rad, ev[EV_APPEND], ev[EV_RAD]);
     cudaEventElapsedTime(&fin, ev[EV_RAD], ev[EV_END]);
+    if (la_events_pending) {
+        float la = 0;
+        cudaEventElapsedTime(&la, ev_la[0], ev_la[1]);
+        exc += la;
+        la_events_pending = false;
+    }
     acc_ms[0] += plan + app; acc_ms[1] += rad; acc_ms[2] += exc; acc_ms[3] += fin;
     ms_steps++;
     events_pending = false;
@@ -305,7 +337,7 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
     }
     cudaGraph_t& g = phase == 1 ? graph1 : graph;
     cudaGraphExec_t& ge = phase == 1 ? graph1_exec : graph_exec;
-    bool valid = phase == 1 ? graph1_valid
+    bool valid = phase == 1 ? (graph1_valid && graph1_la == phase_uses_lookahead)
                             : (graph_valid && graph_pose == d_pose_in && graph_vel == d_vel_in && graph_force == d_force_out);
     if (!valid) {
         if (ge) cudaGraphExecDestroy(ge);
@@ -322,7 +354,7 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
         }
         CUDA_CHECK(cudaStreamEndCapture(stream, &g));
         CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
-        if (phase == 1) graph1_valid = true;
+        if (phase == 1) { graph1_valid = true; graph1_la = phase_uses_lookahead; }
         else { graph_valid = true; graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out; }
     }
     CUDA_CHECK(cudaGraphLaunch(ge, stream));
@@ -361,13 +393,100 @@ void hc_ensemble::begin_step(double t, const double* g) {
     StepHeader hh{};
     hh.t = t; hh.g[0] = g[0]; hh.g[1] = g[1]; hh.g[2] = g[2];
     hh.snap = opts.bracket_snap; hh.head = head; hh.len = int(times.size()); hh.cap = cap; hh.flags = 0;
+    phase_uses_lookahead = false;
+    if (wave_mode == 2 && la_enabled) {
+        int slot = lookahead_slot(t);
+        if (slot < 0) { build_lookahead_block(t); slot = lookahead_slot(t); }
+        if (slot >= 0) { hh.exc_src = 1; hh.exc_slot = slot; phase_uses_lookahead = true; }
+    }
     CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
     launch_phase(1, nullptr, nullptr, nullptr);
 }
 
+// ---- excitation look-ahead ---------------------------------------------------------------------
+void hc_ensemble::setup_lookahead() {
+    la_enabled = false; la_len = 0; la_pos = 0; la_builds = 0; la_hits_this_block = 0; la_poor_blocks = 0;
+    if (wave_mode != 2 || n_eta == 0) return;
+    const int want = opts.exc_lookahead;
+    if (want == 1 || opts.dt_hint <= 0.0) return;
+    for (auto& G : groups) if (G->nd != 6 && G->nd != 12) return;
+    const int tiles = (Bp + 32 * kIPT - 1) / (32 * kIPT);
+    if (want == 0 && tiles < sm_count) return;             // auto: only when one CTA per instance tile fills the GPU
+    la_dt = opts.dt_hint;
+    la_times.assign(kLaT, 0.0);
+    d_la_cache.alloc(size_t(kLaT) * D * Bp);
+    d_la_times.alloc(kLaT);
+    for (auto& G : groups) {
+        G->la_idx.alloc(size_t(kLaT) * G->Le);
+        G->la_w1.alloc(size_t(kLaT) * G->Le);
+        G->la_w2.alloc(size_t(kLaT) * G->Le);
+        G->la_rows_cap = ((G->Le + kLaT + 8 + kLaRows - 1) / kLaRows + 1) * kLaRows;
+        G->la_taps.alloc(size_t(G->la_rows_cap) * kLaT * G->nd);
+    }
+    if (!ev_la[0]) { CUDA_CHECK(cudaEventCreate(&ev_la[0])); CUDA_CHECK(cudaEventCreate(&ev_la[1])); }
+    la_enabled = true;
+}
+
+// slot of the cached block whose predicted time is bitwise equal to t, or -1
+int hc_ensemble::lookahead_slot(double t) {
+    if (la_len == 0) return -1;
+    if (la_pos < la_len && la_times[la_pos] == t) { ++la_hits_this_block; return la_pos++; }
+    return -1;
+}
+
+void hc_ensemble::build_lookahead_block(double t) {
+    // prediction quality: a block that served fewer than 2 steps was (mostly) wasted work
+    if (la_builds > 0 && la_hits_this_block < 2) {
+        if (++la_poor_blocks >= 3) { la_enabled = false; la_len = 0; drop_graph(); return; }
+    } else {
+        la_poor_blocks = 0;
+    }
+    const double tmin = eta_t_h.front(), tmax = eta_t_h.back();
+    // predicted times: repeated addition of dt, as Chrono advances ChTime
+    int T = 0;
+    double tp = t;
+    for (int i = 0; i < kLaT; ++i) {
+        bool ok = true;
+        for (auto& G : groups) ok = ok && (tmin <= tp - G->tau_last) && (tp - G->tau_first <= tmax);
+        if (!ok) break;
+        la_times[i] = tp; ++T;
+        tp = tp + la_dt;
+    }
+    if (T == 0) { la_len = 0; return; }                     // begin_step already validated t itself; defensive
+    for (int i = T; i < kLaT; ++i) la_times[i] = la_times[T - 1];   // unused warps recompute the last time
+    CUDA_CHECK(cudaMemcpyAsync(d_la_times.p, la_times.data(), kLaT * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (profiling) CUDA_CHECK(cudaEventRecord(ev_la[0], stream));
+    auto row_of = [&](double tt) {                            // largest i with eta_t[i] <= tt
+        auto it = std::upper_bound(eta_t_h.begin(), eta_t_h.end(), tt);
+        return int(it - eta_t_h.begin()) - 1;
+    };
+    for (auto& Gp : groups) {
+        Group& G = *Gp;
+        int row0 = row_of(la_times[0] - G.tau_last) - 1;
+        if (row0 < 0) row0 = 0;
+        const int row_hi = std::min(n_eta - 1, row_of(la_times[T - 1] - G.tau_first) + 1);
+        const int nrows = row_hi - row0 + 1;
+        if (nrows > G.la_rows_cap - kLaRows) { la_enabled = false; la_len = 0; drop_graph(); return; }
+        LookaheadPlanArgs pa{};
+        pa.times = d_la_times.p; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
+        pa.idx = G.la_idx.p; pa.w1 = G.la_w1.p; pa.w2 = G.la_w2.p; pa.taps = G.la_taps.p;
+        pa.eta_dt = ip.simulation_dt; pa.n_eta = n_eta; pa.Le = G.Le; pa.nd = G.nd; pa.T = kLaT;
+        pa.row0 = row0; pa.nrows = nrows;
+        CUDA_CHECK(launch_lookahead_plan(pa, stream));
+        LookaheadArgs la{};
+        la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p;
+        la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = row0;
+        la.nchunk = (nrows + kLaRows - 1) / kLaRows;
+        CUDA_CHECK(launch_lookahead(la, stream));
+        prof.kernel_launches += 3;
+    }
+    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_la[1], stream)); la_events_pending = true; }
+    la_len = T; la_pos = 0; la_hits_this_block = 0; ++la_builds;
+}
+
 void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
     launch_phase(2, d_pose_in, d_vel_in, d_force_out);
-    prof.kernel_launches += 4 + (wave_mode == 2 ? (long long)groups.size() : 0);
+    prof.kernel_launches += 4 + ((wave_mode == 2 && !phase_uses_lookahead) ? (long long)groups.size() : 0);
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
     force_valid = true;
@@ -394,7 +513,7 @@ int hc_device_count(void) {
 void hc_ensemble_default_opts(hc_ensemble_opts* o) {
     std::memset(o, 0, sizeof(*o));
     o->device = 0; o->batch = 1; o->dt_hint = 0.0; o->bracket_snap = 0.0;
-    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->stream = nullptr;
+    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->stream = nullptr;
 }
 
 hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, hc_ensemble** out) {
@@ -422,11 +541,11 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_inputs, cudaEventDisableTiming));
 
     const int D = e->D, L = e->L;
-    // K staged as [lag][col][row]: one lag's D x D block is contiguous, rows fastest
+    // K * trapezoid width staged as [lag][col][row]: one lag's D x D block is contiguous, rows fastest
     std::vector<double> Kdev(size_t(L) * D * D);
     for (int r = 0; r < D; ++r)
         for (int c = 0; c < D; ++c)
-            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s];
+            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
     e->d_K.upload(Kdev);
     e->d_rirf_t.upload(t->rirf_t);
     e->d_rirf_w.upload(t->rirf_w);
@@ -471,6 +590,7 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->times.clear();
     e->head = -1;
+    e->la_len = 0; e->la_pos = 0;
     e->prev_time = -1.0;
     e->force_valid = false;
     CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
@@ -608,6 +728,7 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
 
     e->n_eta = 0; e->nf = 0;
     e->wave_mode = 2;
+    e->la_enabled = false; e->la_len = 0;
     e->drop_graph();
     const bool have_sea = (Hs_arr || p->wave_height != 0.0) && (Tp_arr || p->wave_period != 0.0);
     // --- eta time grid (CreateFreeSurfaceElevation, wave_types.cpp:717-744) ---
@@ -678,6 +799,7 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
     cudaEventElapsedTime(&ms, e->ev[EV_BEGIN], e->ev[EV_END]);
     e->prof.eta_synthesis_seconds += 1e-3 * ms;
     e->prof.kernel_launches += 1;
+    e->setup_lookahead();
     // phases/amplitudes are only needed for the synthesis; keep omega/amp small arrays, free the big ones
     e->d_phase.release();
     if (e->per_instance_spectrum) e->d_amp.release();
@@ -826,7 +948,10 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
     StepHeader hh{};
     hh.t = t; hh.snap = e->opts.bracket_snap; hh.head = e->head < 0 ? 0 : e->head; hh.len = 0; hh.cap = e->cap;
     CUDA_CHECK(cudaMemcpyAsync(e->d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, e->stream));
+    const bool saved_la = e->phase_uses_lookahead;
+    e->phase_uses_lookahead = false;                 // always the per-step kernels here
     e->enqueue_phase(1, nullptr, nullptr, nullptr, false);
+    e->phase_uses_lookahead = saved_la;
     if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
     FinalizeGroups fg{};
     if (e->wave_mode == 2)
@@ -857,7 +982,7 @@ hc_status hc_ensemble_refresh_rirf(hc_ensemble* e) {
     std::vector<double> Kdev(size_t(L) * D * D);
     for (int r = 0; r < D; ++r)
         for (int c = 0; c < D; ++c)
-            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s];
+            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
     CUDA_CHECK(cudaMemcpy(e->d_K.p, Kdev.data(), Kdev.size() * sizeof(double), cudaMemcpyHostToDevice));
     return HC_OK;
     HC_GUARD_END
@@ -944,6 +1069,16 @@ hc_status hc_get_kernel_ms(hc_ensemble* e, double* pre, double* rad, double* exc
     if (exc) *exc = e->acc_ms[2] / cnt;
     if (fin) *fin = e->acc_ms[3] / cnt;
     if (reset) { for (double& v : e->acc_ms) v = 0.0; e->ms_steps = 0; }
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// FP64 FMA throughput of the device (TFLOP/s), best of a few launches of a register-resident DFMA loop.
+hc_status hc_measure_fp64_peak(int device, double* tflops) {
+    HC_GUARD_BEGIN
+    if (!tflops) fail(HC_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(measure_dfma_peak(0.5, tflops));
     return HC_OK;
     HC_GUARD_END
 }

@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const
             const double* kk = Ks + (size_t)s * D * D;
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                const double sx = __dmul_rn(v[c].x, wd), sy = __dmul_rn(v[c].y, wd);   // contribution_scale
+                // the trapezoid width w[s] is folded into the staged kernel (K * w, see hc_ensemble_create):
+                // K * (v * w) becomes (K * w) * v -- one rounding moved, 24 FP64 multiplies per lag saved
+                const double sx = v[c].x, sy = v[c].y;
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
                     const double k = kk[c * D + r];
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationA
                 v.x = __dadd_rn(__dmul_rn(wo, u.x), __dmul_rn(wn, v.x));
                 v.y = __dadd_rn(__dmul_rn(wo, u.y), __dmul_rn(wn, v.y));
             }
-            const double sx = __dmul_rn(v.x, wd), sy = __dmul_rn(v.y, wd);
+            const double sx = v.x, sy = v.y;   // width folded into the staged kernel
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const double k = __ldg(kk + c * D + r0 + r);
@@ -361,6 +363,132 @@ __global__ void __launch_bounds__(kThreads, 2) k_excitation(const ExcitationArgs
 }
 
 // ------------------------------------------------------------------------------------------
+// Excitation look-ahead.  The wave force does not depend on the body state, so it may be evaluated ahead of
+// time for the (predicted) times of the next kLaT steps: one pass over the eta window then serves kLaT steps and
+// the eta traffic per step drops by kLaT.  Per block time i and lag j the bracket (idx, w1, w2) is exactly the
+// per-step plan; the lerp is folded into per-row taps
+//     F_i[d] = sum_j fw[j][d] (w1 eta[idx] + w2 eta[idx+1]) = sum_rows G_i[row][d] eta[row],
+//     G_i[row][d] = sum_{j: idx_ij = row} fw[j][d] w1_ij + sum_{j: idx_ij = row-1} fw[j][d] w2_ij   (ascending j).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_la_brackets(const LookaheadPlanArgs a) {
+    const int n = a.T * a.Le;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int i = q / a.Le, j = q - i * a.Le;
+        const double tt = a.times[i] - a.tau[j];
+        int r = (int)floor((tt - a.eta_t[0]) / a.eta_dt);
+        r = max(0, min(r, a.n_eta - 1));
+        while (r > 0 && a.eta_t[r] > tt) --r;
+        while (r + 1 < a.n_eta && a.eta_t[r + 1] <= tt) ++r;
+        double w1 = 1.0, w2 = 0.0;
+        const double t1 = a.eta_t[r];
+        if (tt != t1 && r + 1 < a.n_eta) {
+            const double t2 = a.eta_t[r + 1];
+            w1 = (t2 - tt) / (t2 - t1);
+            w2 = 1.0 - w1;
+        }
+        a.idx[q] = r; a.w1[q] = w1; a.w2[q] = w2;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_la_taps(const LookaheadPlanArgs a) {
+    // one thread per (block time i, eta row m); idx[i][.] is non-increasing in j
+    const int nchunk = (a.nrows + kLaRows - 1) / kLaRows;
+    const int n = a.T * nchunk * kLaRows;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int i = q / (nchunk * kLaRows), mr = q - i * nchunk * kLaRows;
+        const int row = a.row0 + mr;
+        const int* idx = a.idx + (size_t)i * a.Le;
+        // first j with idx[j] <= row, first j with idx[j] <= row - 1, first j with idx[j] <= row - 2
+        auto first_le = [&](int v) {
+            int lo = 0, hi = a.Le;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (idx[mid] <= v) hi = mid; else lo = mid + 1; }
+            return lo;
+        };
+        const int j0 = first_le(row), j1 = first_le(row - 1), j2 = first_le(row - 2);
+        const int chunk = mr / kLaRows, rr = mr - chunk * kLaRows;
+        double* out = a.taps + (((size_t)chunk * a.T + i) * kLaRows + rr) * a.nd;
+        for (int d = 0; d < a.nd; ++d) {
+            double g = 0.0;
+            if (mr < a.nrows) {
+                for (int j = j0; j < j1; ++j)        // idx == row: weight of the lower bracket sample
+                    g = __dadd_rn(g, __dmul_rn(a.fw[(size_t)j * a.nd + d], a.w1[(size_t)i * a.Le + j]));
+                for (int j = j1; j < j2; ++j)        // idx == row - 1: weight of the upper bracket sample
+                    g = __dadd_rn(g, __dmul_rn(a.fw[(size_t)j * a.nd + d], a.w2[(size_t)i * a.Le + j]));
+            }
+            out[d] = g;
+        }
+    }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(kLaT * 32, 2) k_exc_block(const LookaheadArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                 // 2 mbarriers (16 bytes)
+    constexpr int kStageDoubles = kLaT * kLaRows * ND;
+    double* const stage0 = reinterpret_cast<double*>(smem_raw + 16);        // two stages, back to back
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = (blockIdx.x * 32 + lane) * kIPT;
+    constexpr uint32_t kStageBytes = kStageDoubles * sizeof(double);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_expect_tx(&bars[0], kStageBytes);
+        bulk_g2s(stage0, a.taps, kStageBytes, &bars[0]);
+    }
+    __syncthreads();
+
+    double acc0[ND], acc1[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { acc0[d] = 0.0; acc1[d] = 0.0; }
+    const double* eta_b = a.eta + b0;
+
+    for (int c = 0; c < a.nchunk; ++c) {
+        const int st = c & 1;
+        if (threadIdx.x == 0 && c + 1 < a.nchunk) {      // prefetch the next stage (its readers left it at the
+            mbar_expect_tx(&bars[st ^ 1], kStageBytes);  // __syncthreads closing iteration c - 1)
+            bulk_g2s(stage0 + (st ^ 1) * kStageDoubles, a.taps + (size_t)(c + 1) * kStageDoubles, kStageBytes,
+                     &bars[st ^ 1]);
+        }
+        mbar_wait(&bars[st], (c >> 1) & 1);
+        // (pointer arithmetic on the extern shared array keeps the loads in the shared address space: LDS.128)
+        const double2* tp = reinterpret_cast<const double2*>(smem_raw + 16) +
+                            ((size_t)st * kStageDoubles + (size_t)warp * kLaRows * ND) / 2;
+        const int rbase = a.row0 + c * kLaRows;
+        if (b0 < a.Bp) {
+            constexpr int U = 8;
+#pragma unroll
+            for (int r0 = 0; r0 < kLaRows; r0 += U) {
+                double2 e[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int row = min(rbase + r0 + u, a.n_eta - 1);       // rows past the window carry zero taps
+                    e[u] = __ldg(reinterpret_cast<const double2*>(eta_b + (size_t)row * a.Bp));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double2* g = tp + (r0 + u) * (ND / 2);
+#pragma unroll
+                    for (int d = 0; d < ND; d += 2) {
+                        const double2 gd = g[d / 2];
+                        acc0[d] = fma(gd.x, e[u].x, acc0[d]);
+                        acc1[d] = fma(gd.x, e[u].y, acc1[d]);
+                        acc0[d + 1] = fma(gd.y, e[u].x, acc0[d + 1]);
+                        acc1[d + 1] = fma(gd.y, e[u].y, acc1[d + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (b0 < a.Bp) {
+        double* out = a.cache + ((size_t)warp * a.D + a.dof0) * a.Bp + b0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) *reinterpret_cast<double2*>(out + (size_t)d * a.Bp) = make_double2(acc0[d], acc1[d]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_finalize: one thread per instance.
 // ------------------------------------------------------------------------------------------
 
@@ -422,6 +550,8 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         // mag * A * cos(omega t + phase[rowEx])  (wave_types.cpp:322-323; phase of body 0, reference quirk)
         const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
         fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
+    } else if (a.wave_mode == 2 && h.exc_src == 1) {
+        fw = a.exc_cache[((size_t)h.exc_slot * D + d) * a.Bp + b];       // precomputed by k_exc_block
     } else if (a.wave_mode == 2) {
         for (int g = 0; g < a.exc_ngroups; ++g) {
             if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
@@ -623,6 +753,79 @@ cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st) {
     dim3 grid((a.Bp + 127) / 128, (a.n_eta + kEtaKT - 1) / kEtaKT);
     k_eta<<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();
+}
+
+// FP64 FMA peak microbenchmark (the FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 figure).
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+cudaError_t measure_dfma_peak(double seconds_budget, double* tflops) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    double* buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, size_t(blocks) * threads * sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0, spent = 0.0;
+    for (int rep = 0; rep < 50 && spent < seconds_budget; ++rep) {
+        cudaEventRecord(a);
+        k_dfma_peak<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        spent += ms * 1e-3;
+        const double tf = 2.0 * 8.0 * double(iters) * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    *tflops = best;
+    return e;
+}
+
+cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st) {
+    const int n1 = a.T * a.Le;
+    k_la_brackets<<<min((n1 + 255) / 256, 148 * 8), 256, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int nchunk = (a.nrows + kLaRows - 1) / kLaRows;
+    const int n2 = a.T * nchunk * kLaRows;
+    k_la_taps<<<min((n2 + 255) / 256, 148 * 8), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int ND>
+static cudaError_t launch_la_t(const LookaheadArgs& a, cudaStream_t st) {
+    const size_t smem = 16 + size_t(2) * kLaT * kLaRows * ND * sizeof(double);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_exc_block<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const int tiles = (a.Bp + 32 * kIPT - 1) / (32 * kIPT);
+    k_exc_block<ND><<<tiles, kLaT * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lookahead(const LookaheadArgs& a, cudaStream_t st) {
+    switch (a.nd) {
+        case 6: return launch_la_t<6>(a, st);
+        case 12: return launch_la_t<12>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_added_mass_mv(const double* M, int n_sys, int D, double c, const double* w, double* R, int B,

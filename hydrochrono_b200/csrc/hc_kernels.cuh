@@ -20,6 +20,8 @@ struct StepHeader {
     int len;           // history entries after pruning (newest first)
     int cap;           // ring capacity
     int flags;
+    int exc_src;       // 0: irregular wave force = sum of this step's lag-chunk partials; 1: look-ahead cache slot
+    int exc_slot;
 };
 
 struct HydrostaticTables {
@@ -75,6 +77,7 @@ struct FinalizeArgs {
     int wave_mode;            // 0 none, 1 regular, 2 irregular
     int exc_ngroups;
     int exc_ndmax;
+    const double* exc_cache;  // [T][D][Bp] look-ahead block of wave forces (hdr->exc_src == 1)
     int waves_only;           // 1: write only the wave force (WaveBase::GetForceAtTime), no state needed
 };
 
@@ -129,6 +132,31 @@ cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st);
 cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st);
+// ---- excitation look-ahead: the wave force of T consecutive (predicted) step times in one pass over eta ----
+constexpr int kLaT = 8;        // block length = warps per CTA of k_exc_block
+constexpr int kLaRows = 32;    // eta rows per shared-memory stage
+struct LookaheadPlanArgs {
+    const double* times;      // [T] block times
+    const double* tau;        // [Le]
+    const double* fw;         // [Le][nd]
+    const double* eta_t;      // [n_eta]
+    int* idx;                 // [T][Le]  largest i with eta_t[i] <= t - tau_j
+    double* w1;               // [T][Le]
+    double* w2;               // [T][Le]
+    double* taps;             // [nchunk][T][kLaRows][nd]
+    double eta_dt;
+    int n_eta, Le, nd, T, row0, nrows;   // rows row0 .. row0 + nrows - 1 of eta carry taps
+};
+struct LookaheadArgs {
+    const double* eta;        // [n_eta][Bp]
+    const double* taps;       // [nchunk][T][kLaRows][nd]
+    double* cache;            // [T][D][Bp]
+    int n_eta, Bp, D, dof0, nd, row0, nchunk;
+};
+cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
+cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);
+cudaError_t launch_lookahead(const LookaheadArgs& a, cudaStream_t st);
+
 cudaError_t launch_added_mass_mv(const double* M, int n_sys, int D, double c, const double* w, double* R, int B,
                                  cudaStream_t st);
 

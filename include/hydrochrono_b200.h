@@ -149,6 +149,12 @@ typedef struct hc_ensemble_opts {
     int rad_chunk;            /* radiation lags per CTA (0 = auto)   */
     int exc_chunk;            /* excitation lags per CTA (0 = auto)  */
     int use_graph;            /* 1: capture the per-step kernel sequence in a CUDA graph (default 1) */
+    int exc_lookahead;        /* irregular waves: 0 = auto (on when dt_hint > 0 and the batch fills the GPU), 1 = off,
+                                 > 1 = on.  The wave force is state-independent, so it is evaluated for the predicted
+                                 times t, t+dt, ... of the next 8 steps in one pass over eta (t advanced by repeated
+                                 addition of dt_hint, as Chrono advances ChTime); a step whose time is not bitwise
+                                 equal to the prediction falls back to / rebuilds from the actual time, so results
+                                 never depend on the prediction being right. */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;
 
@@ -248,6 +254,9 @@ HC_API hc_status hc_get_profile(hc_ensemble* e, hc_profile_stats* out);
 /* Average device time (ms) of the radiation / excitation / finalize kernels since the last call (needs profiling). */
 HC_API hc_status hc_get_kernel_ms(hc_ensemble* e, double* prestep_ms, double* radiation_ms, double* excitation_ms,
                                   double* finalize_ms, int reset);
+
+/* Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator for the FP64-bound kernels). */
+HC_API hc_status hc_measure_fp64_peak(int device, double* tflops);
 
 /* Pinned host memory helpers for callers that keep their own buffers. */
 HC_API void* hc_host_alloc(size_t bytes);

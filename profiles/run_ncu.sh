@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash profiles/run_ncu.sh r01a'
 # Outputs land in gpurun_out/ (scratch); summaries are copied into profiles/ by hand.
 TAG=${1:-r01}
-SKIP=$(( 1 + (6010 + 3 + 3) * 4 ))   # eta kernel + (prefill + warmups) x 4 kernels per step
+SKIP=$(( 1 + (6010 + 3 + 3) * 5 ))   # eta kernel + (prefill + warmups) x 5 kernels per step (plan, excitation, append, radiation, finalize)
 mkdir -p gpurun_out
 # (1) every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 200 --csv \

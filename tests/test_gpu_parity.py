@@ -176,13 +176,13 @@ def rm3():
 IRR = dict(dt=0.01, duration=20.0, ramp=5.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.0, nfreq=200, gamma=3.3)
 
 
-@pytest.mark.parametrize("snap", [0.0, 1e-9])
-def test_rm3_irregular_ensemble(rm3, snap):
+@pytest.mark.parametrize("snap,lookahead", [(0.0, 1), (1e-8, 1), (0.0, 2), (1e-8, 2)])
+def test_rm3_irregular_ensemble(rm3, snap, lookahead):
     """12-DoF coupled radiation + two-body excitation; B = 7 is ragged against the 64-instance lane tile.
-    snap = 0 is the bit-faithful bracket test; snap = 1e-9 is the configuration bench.py measures."""
+    snap = 0 is the bit-faithful bracket test; snap = 1e-8 + excitation look-ahead is what bench.py measures."""
     T, O = rm3
     B = 7
-    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap)
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=lookahead)
     seeds = list(range(1, B + 1))
     ens.set_waves_irregular(seeds=seeds, **IRR)
     insts = []
@@ -198,6 +198,11 @@ def test_rm3_irregular_ensemble(rm3, snap):
     _assert_parity(tot, rtot, "total")
     # bit-faithful bracketing differs from the oracle only by summation order / FMA contraction
     assert worst < (1e-11 if snap == 0.0 else 1e-9), worst
+    launches = ens.profile()["kernel_launches"]
+    if lookahead == 2:      # 700 steps = 88 blocks of 8: 4 kernels per step + 3 per block (+ eta synthesis)
+        assert launches == 1 + 4 * 700 + 3 * 88, launches
+    else:
+        assert launches == 1 + 5 * 700, launches
 
 
 def test_rm3_long_run_window_full(rm3):
@@ -278,6 +283,32 @@ def test_time_cache_duplicate_and_window_errors(sphere):
     ens.step(0.0, pose, vel)
     with pytest.raises(hc.EtaWindowError):
         ens.step(500.0, pose, vel)
+
+
+def test_lookahead_misprediction_falls_back(rm3):
+    """Excitation look-ahead predicts t + k dt; when the caller's times do not follow the prediction the results must
+    not change: every step is recomputed from the actual time and look-ahead switches itself off."""
+    T, O = rm3
+    B = 3
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, exc_lookahead=2)
+    kw = dict(IRR)
+    ens.set_waves_irregular(seed=4, **kw)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular(seed=4, share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    rng = np.random.default_rng(11)
+    # 40 regular steps (predictions hold), then jittered steps (predictions fail), then regular again
+    dts = np.concatenate([np.full(40, 0.01), rng.uniform(0.004, 0.012, size=60), np.full(40, 0.01)])
+    times = np.concatenate([[0.0], np.cumsum(dts)])
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
+    _assert_parity(wv, rwv, "excitation with mispredicted look-ahead")
+    _assert_parity(tot, rtot, "total")
+    # the wave-only entry point (WaveBase::GetForceAtTime) is independent of the look-ahead cache
+    t_probe = float(times[70])
+    w_at = ens.wave_force_at_time(t_probe)
+    _assert_parity(w_at[None], rwv[70][None], "wave-only force at a past time")
 
 
 def test_irregular_dt_and_ring_growth(sphere):
