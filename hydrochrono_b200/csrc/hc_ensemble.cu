@@ -59,7 +59,7 @@ struct PinBuf {
     }
 };
 
-enum { EV_BEGIN = 0, EV_PLAN, EV_EXC, EV_APPEND, EV_RAD, EV_END, EV_COUNT };
+enum { EV_BEGIN = 0, EV_PLAN, EV_EXC, EV_RAD, EV_APPEND, EV_END, EV_COUNT };
 
 }  // namespace hc
 
@@ -85,7 +85,8 @@ struct hc_ensemble {
 
     // radiation plan + partials
     DevBuf<int> d_pr_new, d_pr_old;
-    DevBuf<double> d_pr_wn, d_pr_wo, d_pr_wd, d_rad_partial;
+    DevBuf<double> d_pr_wn, d_pr_wo, d_pr_wd, d_pr_head, d_rad_partial;
+    DevBuf<int> d_pr_lead;
     int rad_chunk = 0, rad_nchunk = 0;
 
     // step I/O
@@ -138,6 +139,7 @@ struct hc_ensemble {
     const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
     bool phase_uses_lookahead = false;    // set per step: phase 1 skips the per-step excitation kernels
+    bool skip_radiation = false;          // wave-only evaluation (hc_waves_force_at_time)
     bool graph1_la = false;               // what the captured phase-1 graph contains
     cudaEvent_t ev[EV_COUNT] = {};
     hc_profile_stats prof{};
@@ -250,6 +252,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     pa.hdr = d_hdr.p; pa.vel = d_vel_in; pa.hist = d_hist.p; pa.times = d_times.p;
     pa.rirf_t = d_rirf_t.p; pa.rirf_w = d_rirf_w.p;
     pa.pr_new = d_pr_new.p; pa.pr_old = d_pr_old.p; pa.pr_wn = d_pr_wn.p; pa.pr_wo = d_pr_wo.p; pa.pr_wd = d_pr_wd.p;
+    pa.pr_head = d_pr_head.p; pa.pr_lead = d_pr_lead.p;
     pa.B = B; pa.Bp = Bp; pa.D = D; pa.L = L;
     pa.ngroups = 0;
     const bool per_step_exc = (wave_mode == 2) && !(la_enabled && phase_uses_lookahead);
@@ -276,17 +279,20 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
             }
         }
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
+        if (!skip_radiation) {
+            // convolution over the history that is already resident: every row except this step's own sample
+            RadiationArgs ra{};
+            ra.hdr = d_hdr.p; ra.K = d_K.p; ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
+            ra.times = d_times.p; ra.partial = d_rad_partial.p;
+            ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
+            CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
+        }
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
         return;
     }
     CUDA_CHECK(launch_prestep(pa, 1, stream));
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
 
-    RadiationArgs ra{};
-    ra.hdr = d_hdr.p; ra.K = d_K.p; ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
-    ra.times = d_times.p; ra.partial = d_rad_partial.p;
-    ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
-    CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
-    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
 
     FinalizeGroups fg{};
     if (wave_mode == 2)
@@ -301,6 +307,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
     fa.exc_cache = d_la_cache.p;
+    fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
     CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_END], stream));
 }
@@ -310,9 +317,9 @@ void hc_ensemble::collect_events() {
     float plan = 0, exc = 0, app = 0, rad = 0, fin = 0;
     cudaEventElapsedTime(&plan, ev[EV_BEGIN], ev[EV_PLAN]);
     cudaEventElapsedTime(&exc, ev[EV_PLAN], ev[EV_EXC]);
-    cudaEventElapsedTime(&app, ev[EV_EXC], ev[EV_APPEND]);
-    cudaEventElapsedTime(&rad, ev[EV_APPEND], ev[EV_RAD]);
-    cudaEventElapsedTime(&fin, ev[EV_RAD], ev[EV_END]);
+    cudaEventElapsedTime(&rad, ev[EV_EXC], ev[EV_RAD]);
+    cudaEventElapsedTime(&app, ev[EV_RAD], ev[EV_APPEND]);
+    cudaEventElapsedTime(&fin, ev[EV_APPEND], ev[EV_END]);
     if (la_events_pending) {
         float la = 0;
         cudaEventElapsedTime(&la, ev_la[0], ev_la[1]);
@@ -568,6 +575,7 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     cap = std::max(cap, 16);
     e->alloc_ring(cap);
     e->d_pr_new.alloc(L); e->d_pr_old.alloc(L); e->d_pr_wn.alloc(L); e->d_pr_wo.alloc(L); e->d_pr_wd.alloc(L);
+    e->d_pr_head.alloc(L); e->d_pr_lead.alloc(L);
     e->setup_radiation_chunks();
     e->d_hdr.alloc(1);
     const size_t bd = size_t(e->B) * D;
@@ -950,7 +958,9 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
     CUDA_CHECK(cudaMemcpyAsync(e->d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, e->stream));
     const bool saved_la = e->phase_uses_lookahead;
     e->phase_uses_lookahead = false;                 // always the per-step kernels here
+    e->skip_radiation = true;
     e->enqueue_phase(1, nullptr, nullptr, nullptr, false);
+    e->skip_radiation = false;
     e->phase_uses_lookahead = saved_la;
     if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
     FinalizeGroups fg{};
@@ -964,6 +974,7 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
     fa.reg_amp = e->d_reg_amp.p; fa.reg_omega = e->d_reg_omega.p; fa.reg_mag = e->d_reg_mag.p; fa.reg_phase = e->d_reg_phase.p;
     fa.B = e->B; fa.Bp = e->Bp; fa.D = e->D; fa.N = e->N; fa.rad_nchunk = 0; fa.wave_mode = e->wave_mode;
     fa.exc_ngroups = (e->wave_mode == 2) ? int(e->groups.size()) : 0; fa.exc_ndmax = e->exc_ndmax; fa.waves_only = 1;
+    fa.pr_lead = e->d_pr_lead.p; fa.pr_wd = e->d_pr_wd.p; fa.pr_head = e->d_pr_head.p; fa.K = e->d_K.p; fa.L = 0;
     CUDA_CHECK(launch_finalize(fa, e->hs, fg, e->stream));
     CUDA_CHECK(cudaMemcpyAsync(out, e->d_wave_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int 
     if (!(mode & 2)) return;
     for (int s = tid; s < a.L; s += nth) {
         int slot_new = 0, slot_old = 0;
-        double wn = 0.0, wo = 0.0, wd = 0.0;
+        double wn = 0.0, wo = 0.0, wd = 0.0, head_w = 0.0;
+        int lead = 0;
         if (h.len > 1) {
             const double q = h.t - a.rirf_t[s];                      // rirf_query_time, :601
             // AdvanceToBracket (:374-381): smallest i with time(i+1) <= q, i+1 < len
@@ -110,11 +111,21 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int 
                     wd = a.rirf_w[s];                                // step_width == 0 -> skipped (:622-625)
                     slot_new = h.head - lo; if (slot_new < 0) slot_new += h.cap;
                     slot_old = h.head - lo - 1; if (slot_old < 0) slot_old += h.cap;
+                    if (lo == 0) {
+                        lead = 1;
+                        // The newer bracket sample is THIS step's velocity, which may still be on its way to the
+                        // device: its share  (K w)[s] * (wn * v_now)  is added by k_finalize, the convolution
+                        // kernel only sees the older sample.  (lags with lo == 0 are the leading lags)
+                        head_w = wn;
+                        wn = 0.0;
+                    }
                 }
             }
         }
         a.pr_new[s] = slot_new; a.pr_old[s] = slot_old;
         a.pr_wn[s] = wn; a.pr_wo[s] = wo; a.pr_wd[s] = wd;
+        a.pr_head[s] = head_w;
+        a.pr_lead[s] = lead;
     }
 
     // (3) excitation plan (wave_types.cpp:796-829): largest i with eta_t[i] <= t - tau_j; exact hit or lerp.
@@ -179,15 +190,22 @@ __global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const
             const double wd = s_wd[s];
             if (wd == 0.0) continue;
             const double wn = s_wn[s], wo = s_wo[s];
+            if (wn == 0.0 && wo == 0.0) continue;          // exact hit on this step's own sample: k_finalize's share
             const double* rn = a.hist + (size_t)s_new[s] * row_stride + b0;
             const double* ro = a.hist + (size_t)s_old[s] * row_stride + b0;
             double2 v[D];
-            if (wo == 0.0) {
+            if (wo == 0.0 && wn == 1.0) {                  // exact hit on the newer sample
 #pragma unroll
                 for (int c = 0; c < D; ++c) v[c] = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
-            } else if (wn == 0.0) {
+            } else if (wn == 0.0 && wo == 1.0) {           // exact hit on the older sample
 #pragma unroll
                 for (int c = 0; c < D; ++c) v[c] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+            } else if (wn == 0.0) {                        // lerp whose newer sample is this step's: older share only
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    v[c] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+                    v[c].x = __dmul_rn(wo, v[c].x); v[c].y = __dmul_rn(wo, v[c].y);
+                }
             } else {
                 double2 u[D];
 #pragma unroll
@@ -236,14 +254,18 @@ __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationA
         const double wd = p.wd[s0 + s];
         if (wd == 0.0) continue;
         const double wn = p.wn[s0 + s], wo = p.wo[s0 + s];
+        if (wn == 0.0 && wo == 0.0) continue;
         const double* rn = a.hist + (size_t)p.nw[s0 + s] * row_stride + b0;
         const double* ro = a.hist + (size_t)p.od[s0 + s] * row_stride + b0;
         const double* kk = a.K + (size_t)(s0 + s) * D * D;
         for (int c = 0; c < D; ++c) {
             double2 v;
-            if (wo == 0.0) v = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
-            else if (wn == 0.0) v = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
-            else {
+            if (wo == 0.0 && wn == 1.0) v = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
+            else if (wn == 0.0 && wo == 1.0) v = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+            else if (wn == 0.0) {
+                v = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
+                v.x = __dmul_rn(wo, v.x); v.y = __dmul_rn(wo, v.y);
+            } else {
                 const double2 u = __ldg(reinterpret_cast<const double2*>(ro + (size_t)c * a.Bp));
                 v = __ldg(reinterpret_cast<const double2*>(rn + (size_t)c * a.Bp));
                 v.x = __dadd_rn(__dmul_rn(wo, u.x), __dmul_rn(wn, v.x));
@@ -543,6 +565,16 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
             fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
         }
         for (; ch < a.rad_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
+        // share of this step's own velocity sample (leading lags whose newer bracket sample is "now")
+        const double* vel = a.vel + (size_t)b * D;
+        for (int s = 0; s < a.L && a.pr_lead[s]; ++s) {   // leading lags: contiguous from lag 0
+            const double hw = a.pr_head[s];
+            if (hw == 0.0 || a.pr_wd[s] == 0.0) continue;
+            const double* kk = a.K + (size_t)s * D * D + d;            // (K w)[s][c][row d]
+            double acc = 0.0;
+            for (int c = 0; c < D; ++c) acc = fma(kk[(size_t)c * D], __dmul_rn(hw, vel[c]), acc);
+            fr = __dadd_rn(fr, acc);
+        }
     }
     // ---- waves ----
     double fw = 0.0;

@@ -78,6 +78,13 @@ struct FinalizeArgs {
     int exc_ngroups;
     int exc_ndmax;
     const double* exc_cache;  // [T][D][Bp] look-ahead block of wave forces (hdr->exc_src == 1)
+    // share of this step's own velocity sample in the radiation convolution
+    const double* vel;        // [B][D]
+    const double* K;          // [L][D][D]  (K w)
+    const int* pr_lead;
+    const double* pr_wd;
+    const double* pr_head;
+    int L;
     int waves_only;           // 1: write only the wave force (WaveBase::GetForceAtTime), no state needed
 };
 
@@ -103,6 +110,8 @@ struct PrestepArgs {
     double* pr_wn;         // [L] weight of the newer sample
     double* pr_wo;         // [L] weight of the older sample
     double* pr_wd;         // [L] trapezoid width (0 = lag skipped)
+    double* pr_head;       // [L] weight of THIS step's velocity sample (handled by k_finalize), 0 elsewhere
+    int* pr_lead;          // [L] 1 for the leading lags whose newer bracket sample is this step's
     int B, Bp, D, L;
     // excitation
     int ngroups;
