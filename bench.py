@@ -384,7 +384,8 @@ def main():
                                          "frac": exc_tf / fp64_peak if (exc_tf and fp64_peak) else None,
                                          "peak_source": "measured in this run (hc_measure_fp64_peak, DFMA loop)",
                                          "flops_per_step": exc_flops, "kernel_ms_per_step": kms["excitation"],
-                                         "hbm_gbs_per_step_equiv": ach_exc / 8 if ach_exc else None}
+                                         "traffic": (traffic or {}).get("exc_block_dram_bytes_per_launch"),
+                                         "traffic_note": "dram bytes per k_exc_block launch (one launch per 8 steps)"}
                                         if not args.no_lookahead else
                                         {"kernel": "k_excitation<12>", "bound": "hbm", "achieved": ach_exc, "peak": peak,
                                          "unit": "GB/s", "frac": (ach_exc / peak) if ach_exc else None,
