@@ -396,7 +396,17 @@ def main():
             "checksum": checksum,
         }
         if not args.no_cpu:
-            line["cpu_baseline"] = cpu_arm(args.cpu_instances, args.cpu_steps, prefill)
+            # the CPU leg runs in a fresh interpreter (no torch / CUDA threads competing for the cores): the same
+            # code path as `bench.py --impl reference`
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-instances",
+                                      str(args.cpu_instances), "--cpu-steps", str(args.cpu_steps), "--prefill", str(prefill),
+                                      "--batch", str(B)], capture_output=True, text=True, timeout=900,
+                                     env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                line["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as ex:   # never lose the GPU line because the CPU leg failed
+                line["cpu_baseline"] = {"value": None, "unit": "instance-steps/s", "cores": None, "kind": "port",
+                                        "sample": "cpu leg failed: %r" % (ex,)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
