@@ -69,14 +69,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices):
+        self.indices, self.proc, self.lines = list(indices), None, []
 
     def start(self):
+        # ONE nvidia-smi process for all the GPUs of the job (rank 0 only): NVML polling from every rank at once
+        # contends with the CUDA driver and slows kernel launches of an 8-rank run.
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                                          "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -111,8 +113,8 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": len(self.indices)}
 
 
 def hbm_peak():
@@ -293,11 +295,14 @@ def main():
     for _ in range(W):
         dev_step()
     ens.sync()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world)) if rank == 0 else None
     launches0 = ens.profile()["kernel_launches"]
     barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)          # let the first sample land inside the region even for short runs
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(stream)                              # CUDA events on the launching stream
@@ -309,7 +314,7 @@ def main():
     t_wall = time.perf_counter() - t0
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches = ens.profile()["kernel_launches"] - launches0
     t_dev = max_over_ranks(t_dev)
 
@@ -371,7 +376,7 @@ def main():
                                  "the library on the same stream" % t_wall},
             "e2e": {"value": e2e, "unit": "instance-steps/s", "h2d_bytes_per_step": 2 * B * DOFS * 8 + 64,
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_radiation<12>", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
