@@ -344,6 +344,48 @@ def test_gravity_vector_and_body_count_generic_path():
     _assert_parity(tot, rtot, "total D=18")
 
 
+@pytest.mark.parametrize("name,cfg", [
+    # BASELINE.json configs 2..4 as parity cases (their .h5 files are stripped from the reference snapshot, so the
+    # tables are synthetic with the demos' shapes and step sizes)
+    ("oswec_jonswap", dict(tables=dict(num_bodies=2, rirf_steps=601, rirf_duration=30.0, exc_irf_steps=401,
+                                       exc_half_window=24.0), dt=0.03, steps=1100,
+                           sea=dict(Hs=1.5, Tp=10.0, gamma=3.3, nfreq=150, ramp=3.0))),     # demos/oswec: N = 2, dt = 0.03
+    ("deepcwind_long_rirf", dict(tables=dict(num_bodies=1, rirf_steps=4001, rirf_duration=320.0, exc_irf_steps=601,
+                                             exc_half_window=48.0), dt=0.08, steps=4100,
+                                 sea=dict(Hs=6.0, Tp=12.0, gamma=2.2, nfreq=120, ramp=8.0))),  # demos/DeepCWind: N = 1, dt = 0.08
+    ("f3of_three_bodies", dict(tables=dict(num_bodies=3, rirf_steps=401, rirf_duration=20.0, exc_irf_steps=301,
+                                           exc_half_window=15.0), dt=0.02, steps=1050,
+                               sea=dict(Hs=1.0, Tp=6.0, gamma=1.0, nfreq=100, ramp=0.0))),   # demos/f3of: N = 3, D = 18
+])
+def test_baseline_config_shapes(name, cfg):
+    raw = synth.make_tables(**cfg["tables"])
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    N = cfg["tables"]["num_bodies"]
+    D, dt, steps = 6 * N, cfg["dt"], cfg["steps"]
+    B = 3
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, exc_lookahead=2 if N <= 2 else 0)
+    kw = dict(dt=dt, duration=steps * dt + 1.0, **cfg["sea"])
+    seeds = [3, 4, 5]
+    ens.set_waves_irregular(seeds=seeds, **kw)
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular(seed=seeds[b], share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    times = _acc_times(steps, dt)
+    check = set(range(0, steps, max(1, steps // 40))) | set(range(steps - 60, steps))
+    got, ref = [], []
+    for n, t in enumerate(times):
+        pose, vel = _motion(D, B, t)
+        F = ens.step(t, pose, vel, G981)
+        r = np.array([i.force(t, pose[b], vel[b], G981) for b, i in enumerate(insts)])
+        if n in check:
+            got.append(F.copy())
+            ref.append(r)
+    _assert_parity(np.array(got), np.array(ref), name)
+    assert ens.history_len() == insts[0].history_len()
+
+
 def test_added_mass_mv(rm3):
     T, O = rm3
     B, n_sys = 9, 18                               # one extra non-hydro body in the system
