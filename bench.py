@@ -30,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# headline workload (BASELINE.json metric) -- module-level names are rebound by select_workload()
 DT = 0.01
 DOFS = 12
 RIRF_STEPS = 1001
@@ -37,6 +38,30 @@ EXC_STEPS = 6000
 SEA = dict(Hs=2.5, Tp=8.0, gamma=3.3, fmin=0.001, fmax=1.0, nfreq=1000, ramp=20.0)
 SNAP = 1e-8
 GVEC = (0.0, 0.0, -9.81)
+WORKLOAD = "rm3_irregular_ensemble"
+PREFILL = 6010
+
+
+def workload_tables():
+    from hydrochrono_b200 import synth
+    if WORKLOAD == "sphere_irregular_ensemble":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "sphere_tables.npz"))
+        body = {k: z[k] for k in ("cg", "cb", "lin_matrix", "inf_added_mass", "rirf_K", "rirf_t", "exc_mag", "exc_phase",
+                                  "exc_irf_f", "exc_irf_t")}
+        body["disp_vol"] = float(z["disp_vol"])
+        return {"rho": float(z["rho"]), "g": float(z["g"]), "water_depth": float(z["water_depth"]), "w": z["w"],
+                "bodies": [body]}
+    return synth.rm3_like()
+
+
+def select_workload(name):
+    """Secondary workload on the reference's real tables: sphere x 16384, N = 1, D = 6, L = 1001 lags
+    with rirf spacing == dt = 0.015, excitation IRF resampled to 8334 lags, Hs 2 / Tp 12 / gamma 1."""
+    global DT, DOFS, RIRF_STEPS, EXC_STEPS, SEA, WORKLOAD, PREFILL
+    WORKLOAD = name
+    if name == "sphere_irregular_ensemble":
+        DT, DOFS, RIRF_STEPS, EXC_STEPS, PREFILL = 0.015, 6, 1001, 8334, 1010
+        SEA = dict(Hs=2.0, Tp=12.0, gamma=1.0, fmin=0.001, fmax=1.0, nfreq=1000, ramp=60.0)
 
 
 def parse():
@@ -55,6 +80,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
+    ap.add_argument("--workload", default="rm3_irregular_ensemble",
+                    choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
     return ap.parse_args()
 
 
@@ -140,7 +167,7 @@ def ncu_traffic():
 def cpu_arm(n_inst, n_steps, prefill, quiet=False):
     from hydrochrono_b200 import synth
     from oracle import hc_oracle as orc
-    raw = synth.rm3_like()
+    raw = workload_tables()
     T = orc.Tables(raw)
     cores = orc.num_threads()
     amp, om = synth.prescribed_motion(DOFS)
@@ -173,7 +200,7 @@ def cpu_arm(n_inst, n_steps, prefill, quiet=False):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    prefill = args.prefill if args.prefill >= 0 else 6010
+    prefill = args.prefill if args.prefill >= 0 else PREFILL
     t0 = time.time()
     res = None
     vals = []
@@ -186,7 +213,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "rm3_irregular_ensemble", "instances_per_gpu": args.batch, "dofs": DOFS,
+        "config": {"workload": WORKLOAD, "instances_per_gpu": args.batch, "dofs": DOFS,
                    "rirf_steps": RIRF_STEPS, "exc_irf_steps": EXC_STEPS, "dt": DT, "sea_state": SEA,
                    "note": "reference CPU path (oracle port; the reference itself needs Chrono/Eigen/HDF5 and cannot "
                            "be built here) on a bounded sample of the same workload; ms_per_step is the time the CPU "
@@ -202,6 +229,7 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    select_workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,10 +263,10 @@ def main():
 
     B = args.batch
     K, W = args.steps, max(args.warmup, 3)
-    prefill = args.prefill if args.prefill >= 0 else 6010
+    prefill = args.prefill if args.prefill >= 0 else PREFILL
     snap = 0.0 if args.faithful else SNAP
     total_steps = prefill + 2 * (W + K) + 128
-    raw = synth.rm3_like()
+    raw = workload_tables()
     T = hc.Tables.from_raw(raw)
     stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
@@ -253,7 +281,7 @@ def main():
                             fmin=SEA["fmin"], fmax=SEA["fmax"], nfreq=SEA["nfreq"], gamma=SEA["gamma"], seeds=seeds)
     eta_s = ens.profile()["eta_synthesis_seconds"]
     nf, n_eta, le = ens.irregular_sizes()
-    assert le == [EXC_STEPS, EXC_STEPS], le
+    assert le == [EXC_STEPS] * (DOFS // 6), le
 
     amp, om = synth.prescribed_motion(DOFS)
     NBUF = 8
@@ -288,7 +316,8 @@ def main():
     for _ in range(prefill):
         dev_step()
     ens.sync()
-    assert ens.history_len() >= min(prefill, 6000), ens.history_len()
+    assert ens.history_len() >= min(prefill, RIRF_STEPS - 1), ens.history_len()
+    hist_rows = ens.history_len()
     setup_s = time.time() - t_setup
 
     # ---- device-resident leg (value) -----------------------------------------------------------------
@@ -318,6 +347,19 @@ def main():
     launches = ens.profile()["kernel_launches"] - launches0
     t_dev = max_over_ranks(t_dev)
 
+    # ---- per-kernel device times (CUDA events on the ensemble's stream; graph off while profiling) ----
+    ens.set_profiling(True)
+    nprof = min(max(K // 4, 20), 100)
+    for _ in range(3):
+        dev_step()
+    ens.sync()
+    ens.kernel_ms(reset=True)
+    for _ in range(nprof):
+        dev_step()
+    ens.sync()
+    kms = ens.kernel_ms(reset=True)
+    ens.set_profiling(False)
+
     # ---- end-to-end leg (host buffers through hc_step) -----------------------------------------------
     for _ in range(W):
         host_step()
@@ -332,23 +374,33 @@ def main():
     t_e2e = max_over_ranks(t_e2e)
     checksum = float(h_force.numpy()[:, 2].sum())
 
-    # ---- per-kernel device times (CUDA events on the ensemble's stream; graph off while profiling) ----
-    ens.set_profiling(True)
-    nprof = min(max(K // 4, 20), 100)
-    for _ in range(3):
-        dev_step()
-    ens.sync()
-    ens.kernel_ms(reset=True)
-    for _ in range(nprof):
-        dev_step()
-    ens.sync()
-    kms = ens.kernel_ms(reset=True)
-    ens.set_profiling(False)
+    # ---- the same device-resident leg with bit-faithful bracketing (bracket_snap = 0), short ----------------
+    faithful = None
+    if snap > 0:
+        ens.set_bracket_snap(0.0)
+        kf = max(50, K // 5)
+        for _ in range(W):
+            dev_step()
+        ens.sync()
+        barrier()
+        ev0.record(stream)
+        for _ in range(kf):
+            dev_step()
+        ev1.record(stream)
+        ens.sync()
+        torch.cuda.synchronize()
+        t_f = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+        faithful = {"value": world * B * kf / t_f, "unit": "instance-steps/s", "steps": kf, "ms_per_step": 1e3 * t_f / kf,
+                    "note": "bracket_snap = 0: every convolution query is bracketed with the reference's == / lerp "
+                            "logic, a ~1e-9-weight second history row is read where the query misses a sample by "
+                            "floating-point noise"}
+        ens.set_bracket_snap(snap)
 
     fp64_peak = hc.measure_fp64_peak(local_rank) if rank == 0 else None
     if rank == 0:
         peak, peak_src = hbm_peak()
-        rows = RIRF_STEPS if snap > 0 else 2 * RIRF_STEPS      # distinct history rows touched per step
+        # distinct history rows touched per step: one per lag with exact hits / snapping, up to two otherwise
+        rows = RIRF_STEPS if snap > 0 else min(2 * RIRF_STEPS, hist_rows)
         rad_bytes = B * (8 * DOFS * rows + 8 * DOFS * 3) + 8 * DOFS * DOFS * RIRF_STEPS
         exc_bytes = B * 8 * (EXC_STEPS + 1) + 8 * (DOFS + 2) * EXC_STEPS
         ach = rad_bytes / (kms["radiation"] * 1e-3) / 1e9
@@ -357,20 +409,20 @@ def main():
         rad_flops = 2.0 * DOFS * DOFS * RIRF_STEPS * B
         exc_tf = exc_flops / (kms["excitation"] * 1e-3) / 1e12 if kms["excitation"] > 0 else None
         rad_tf = rad_flops / (kms["radiation"] * 1e-3) / 1e12
-        traffic = ncu_traffic()
+        traffic = ncu_traffic() if WORKLOAD == "rm3_irregular_ensemble" else None
         value = world * B * K / t_dev
         e2e = world * B * K / t_e2e
         line = {
             "metric": "batched sim-steps/sec (RM3 irregular ensemble)", "value": value, "unit": "instance-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "rm3_irregular_ensemble", "instances_per_gpu": B, "instances_total": world * B,
+            "config": {"workload": WORKLOAD, "instances_per_gpu": B, "instances_total": world * B,
                        "dofs": DOFS, "rirf_steps": RIRF_STEPS, "exc_irf_steps": EXC_STEPS, "dt": DT,
                        "spectrum_components": nf, "eta_samples": n_eta, "sea_state": SEA,
                        "bracket_snap": snap, "history_prefill_steps": prefill, "cuda_graph": not args.no_graph,
                        "excitation_lookahead_steps": 1 if args.no_lookahead else 8,
                        "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
-                             % (8e-9 * DOFS * B * 6002, 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
+                             % (8e-9 * DOFS * B * ens.history_len(), 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
                        "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s); "
                                  "e2e: wall clock around K synchronous hc_step calls; per-kernel ms: CUDA events inside "
                                  "the library on the same stream" % t_wall},
@@ -378,7 +430,7 @@ def main():
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_radiation<12>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_radiation<%d>" % DOFS, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
                          "kernel_ms": kms["radiation"],
@@ -399,12 +451,14 @@ def main():
             "kernel_ms": kms,
             "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},
             "checksum": checksum,
+            "faithful_bracketing": faithful,
         }
         if not args.no_cpu:
             # the CPU leg runs in a fresh interpreter (no torch / CUDA threads competing for the cores): the same
             # code path as `bench.py --impl reference`
             try:
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-instances",
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", WORKLOAD,
+                                      "--cpu-instances",
                                       str(args.cpu_instances), "--cpu-steps", str(args.cpu_steps), "--prefill", str(prefill),
                                       "--batch", str(B)], capture_output=True, text=True, timeout=900,
                                      env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})

@@ -328,6 +328,9 @@ class Ensemble:
     def reset(self):
         _check(lib.hc_ensemble_reset(self._h))
 
+    def set_bracket_snap(self, snap):
+        _check(lib.hc_ensemble_set_bracket_snap(self._h, float(snap)))
+
     def history_len(self):
         return lib.hc_ensemble_history_len(self._h)
 

@@ -94,6 +94,7 @@ SIGNATURES = {
     "hc_ensemble_batch": (C.c_int, [vp]),
     "hc_ensemble_dofs": (C.c_int, [vp]),
     "hc_ensemble_reset": (C.c_int, [vp]),
+    "hc_ensemble_set_bracket_snap": (C.c_int, [vp, C.c_double]),
     "hc_ensemble_host_buffers": (C.c_int, [vp, C.POINTER(dp), C.POINTER(dp), C.POINTER(dp)]),
     "hc_waves_none": (C.c_int, [vp]),
     "hc_waves_regular": (C.c_int, [vp, C.c_int, dp, dp, dp]),

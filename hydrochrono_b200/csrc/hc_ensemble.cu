@@ -607,6 +607,12 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     HC_GUARD_END
 }
 
+hc_status hc_ensemble_set_bracket_snap(hc_ensemble* e, double snap) {
+    if (!(snap >= 0.0) || snap >= 0.5) { set_last_error("bracket_snap must be in [0, 0.5)"); return HC_ERR_INVALID; }
+    e->opts.bracket_snap = snap;     // travels in the per-step header: takes effect at the next step
+    return HC_OK;
+}
+
 hc_status hc_ensemble_host_buffers(hc_ensemble* e, double** pose, double** vel, double** force) {
     if (pose) *pose = static_cast<double*>(e->h_pose.p);
     if (vel) *vel = static_cast<double*>(e->h_vel.p);

@@ -165,6 +165,8 @@ HC_API int hc_ensemble_batch(const hc_ensemble* e);
 HC_API int hc_ensemble_dofs(const hc_ensemble* e);      /* 6N */
 /* Drops the velocity history and the time cache (a fresh TestHydro), keeps the waves. */
 HC_API hc_status hc_ensemble_reset(hc_ensemble* e);
+/* Changes hc_ensemble_opts.bracket_snap for the following steps (0 = bit-faithful bracketing). */
+HC_API hc_status hc_ensemble_set_bracket_snap(hc_ensemble* e, double snap);
 /* Pinned host staging owned by the ensemble ([B][6N] each).  Filling/reading these in place makes hc_step
  * copy-free on the host side. */
 HC_API hc_status hc_ensemble_host_buffers(hc_ensemble* e, double** pose, double** vel, double** force);
