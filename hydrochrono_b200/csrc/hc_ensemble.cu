@@ -123,8 +123,12 @@ struct hc_ensemble {
     // excitation look-ahead (state-independent wave force evaluated kLaT predicted steps at a time)
     bool la_enabled = false;
     double la_dt = 0.0;
-    std::vector<double> la_times;     // predicted times of the current block
-    int la_len = 0, la_pos = 0;       // valid slots / next slot expected
+    struct LaBlock { std::vector<double> times; int len = 0; bool valid = false; };
+    LaBlock la_blk[2];                // double-buffered blocks of predicted times / cached wave forces
+    int la_cur = 0, la_pos = 0;       // block being consumed / next slot expected
+    bool la_background = false;       // next block evaluated on a side stream under the current block's steps
+    cudaStream_t la_stream = nullptr;
+    cudaEvent_t ev_la_done[2] = {nullptr, nullptr}, ev_la_free[2] = {nullptr, nullptr}, ev_la_build = nullptr;
     int la_builds = 0, la_hits_this_block = 0, la_poor_blocks = 0;
     DevBuf<double> d_la_cache, d_la_times;
     cudaEvent_t ev_la[2] = {nullptr, nullptr};
@@ -154,7 +158,11 @@ struct hc_ensemble {
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_inputs) cudaEventDestroy(ev_inputs);
+        if (la_stream) { cudaStreamSynchronize(la_stream); cudaStreamDestroy(la_stream); }
         for (auto& x : ev_la) if (x) cudaEventDestroy(x);
+        for (auto& x : ev_la_done) if (x) cudaEventDestroy(x);
+        for (auto& x : ev_la_free) if (x) cudaEventDestroy(x);
+        if (ev_la_build) cudaEventDestroy(ev_la_build);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -174,7 +182,8 @@ struct hc_ensemble {
     void begin_step(double t, const double* g);
     void setup_lookahead();
     int lookahead_slot(double t);
-    void build_lookahead_block(double t);
+    int enqueue_lookahead_block(int buf, double t0, cudaStream_t st);
+    void prefetch_lookahead(int buf);
     void finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void collect_events();
 };
@@ -322,6 +331,7 @@ void hc_ensemble::collect_events() {
     cudaEventElapsedTime(&fin, ev[EV_APPEND], ev[EV_END]);
     if (la_events_pending) {
         float la = 0;
+        cudaEventSynchronize(ev_la[1]);           // may have been recorded on the side stream
         cudaEventElapsedTime(&la, ev_la[0], ev_la[1]);
         exc += la;
         la_events_pending = false;
@@ -402,8 +412,7 @@ void hc_ensemble::begin_step(double t, const double* g) {
     hh.snap = opts.bracket_snap; hh.head = head; hh.len = int(times.size()); hh.cap = cap; hh.flags = 0;
     phase_uses_lookahead = false;
     if (wave_mode == 2 && la_enabled) {
-        int slot = lookahead_slot(t);
-        if (slot < 0) { build_lookahead_block(t); slot = lookahead_slot(t); }
+        const int slot = lookahead_slot(t);
         if (slot >= 0) { hh.exc_src = 1; hh.exc_slot = slot; phase_uses_lookahead = true; }
     }
     CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
@@ -412,7 +421,9 @@ void hc_ensemble::begin_step(double t, const double* g) {
 
 // ---- excitation look-ahead ---------------------------------------------------------------------
 void hc_ensemble::setup_lookahead() {
-    la_enabled = false; la_len = 0; la_pos = 0; la_builds = 0; la_hits_this_block = 0; la_poor_blocks = 0;
+    la_enabled = false; la_pos = 0; la_cur = 0; la_builds = 0; la_hits_this_block = 0; la_poor_blocks = 0;
+    la_blk[0].valid = la_blk[1].valid = false;
+    if (la_stream) CUDA_CHECK(cudaStreamSynchronize(la_stream));
     if (wave_mode != 2 || n_eta == 0) return;
     const int want = opts.exc_lookahead;
     if (want == 1 || opts.dt_hint <= 0.0) return;
@@ -420,9 +431,18 @@ void hc_ensemble::setup_lookahead() {
     const int tiles = (Bp + 32 * kIPT - 1) / (32 * kIPT);
     if (want == 0 && tiles < sm_count) return;             // auto: only when one CTA per instance tile fills the GPU
     la_dt = opts.dt_hint;
-    la_times.assign(kLaT, 0.0);
-    d_la_cache.alloc(size_t(kLaT) * D * Bp);
-    d_la_times.alloc(kLaT);
+    la_background = (want == 0 || want >= 3);
+    for (auto& b : la_blk) b.times.assign(kLaT, 0.0);
+    d_la_cache.alloc(size_t(2) * kLaT * D * Bp);
+    d_la_times.alloc(2 * kLaT);
+    if (!la_stream) {
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority
+        CUDA_CHECK(cudaStreamCreateWithPriority(&la_stream, cudaStreamNonBlocking, lo));
+        for (auto& x : ev_la_done) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        for (auto& x : ev_la_free) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_la_build, cudaEventDisableTiming));
+    }
     for (auto& G : groups) {
         G->la_idx.alloc(size_t(kLaT) * G->Le);
         G->la_w1.alloc(size_t(kLaT) * G->Le);
@@ -434,61 +454,100 @@ void hc_ensemble::setup_lookahead() {
     la_enabled = true;
 }
 
-// slot of the cached block whose predicted time is bitwise equal to t, or -1
-int hc_ensemble::lookahead_slot(double t) {
-    if (la_len == 0) return -1;
-    if (la_pos < la_len && la_times[la_pos] == t) { ++la_hits_this_block; return la_pos++; }
-    return -1;
-}
-
-void hc_ensemble::build_lookahead_block(double t) {
-    // prediction quality: a block that served fewer than 2 steps was (mostly) wasted work
-    if (la_builds > 0 && la_hits_this_block < 2) {
-        if (++la_poor_blocks >= 3) { la_enabled = false; la_len = 0; drop_graph(); return; }
-    } else {
-        la_poor_blocks = 0;
-    }
+// Builds the block of wave forces for the predicted times t0, t0+dt, ... into cache buffer `buf` on stream `st`.
+// Returns the number of valid block times (0: t0 is outside the eta window).  The per-group scratch (brackets,
+// taps) is shared by all builds, which are therefore chained through ev_la_build.
+int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
+    LaBlock& Bk = la_blk[buf];
+    Bk.valid = false; Bk.len = 0;
     const double tmin = eta_t_h.front(), tmax = eta_t_h.back();
-    // predicted times: repeated addition of dt, as Chrono advances ChTime
     int T = 0;
-    double tp = t;
+    double tp = t0;                                          // repeated addition of dt, as Chrono advances ChTime
     for (int i = 0; i < kLaT; ++i) {
         bool ok = true;
         for (auto& G : groups) ok = ok && (tmin <= tp - G->tau_last) && (tp - G->tau_first <= tmax);
         if (!ok) break;
-        la_times[i] = tp; ++T;
+        Bk.times[i] = tp; ++T;
         tp = tp + la_dt;
     }
-    if (T == 0) { la_len = 0; return; }                     // begin_step already validated t itself; defensive
-    for (int i = T; i < kLaT; ++i) la_times[i] = la_times[T - 1];   // unused warps recompute the last time
-    CUDA_CHECK(cudaMemcpyAsync(d_la_times.p, la_times.data(), kLaT * sizeof(double), cudaMemcpyHostToDevice, stream));
-    if (profiling) CUDA_CHECK(cudaEventRecord(ev_la[0], stream));
+    if (T == 0) return 0;
+    for (int i = T; i < kLaT; ++i) Bk.times[i] = Bk.times[T - 1];    // unused warps recompute the last time
+    CUDA_CHECK(cudaStreamWaitEvent(st, ev_la_build, 0));
+    double* d_times = d_la_times.p + size_t(buf) * kLaT;
+    CUDA_CHECK(cudaMemcpyAsync(d_times, Bk.times.data(), kLaT * sizeof(double), cudaMemcpyHostToDevice, st));
+    const bool timed = profiling;
+    if (timed) CUDA_CHECK(cudaEventRecord(ev_la[0], st));
     auto row_of = [&](double tt) {                            // largest i with eta_t[i] <= tt
         auto it = std::upper_bound(eta_t_h.begin(), eta_t_h.end(), tt);
         return int(it - eta_t_h.begin()) - 1;
     };
     for (auto& Gp : groups) {
         Group& G = *Gp;
-        int row0 = row_of(la_times[0] - G.tau_last) - 1;
+        int row0 = row_of(Bk.times[0] - G.tau_last) - 1;
         if (row0 < 0) row0 = 0;
-        const int row_hi = std::min(n_eta - 1, row_of(la_times[T - 1] - G.tau_first) + 1);
+        const int row_hi = std::min(n_eta - 1, row_of(Bk.times[T - 1] - G.tau_first) + 1);
         const int nrows = row_hi - row0 + 1;
-        if (nrows > G.la_rows_cap - kLaRows) { la_enabled = false; la_len = 0; drop_graph(); return; }
+        if (nrows > G.la_rows_cap - kLaRows) return 0;
         LookaheadPlanArgs pa{};
-        pa.times = d_la_times.p; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
+        pa.times = d_times; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
         pa.idx = G.la_idx.p; pa.w1 = G.la_w1.p; pa.w2 = G.la_w2.p; pa.taps = G.la_taps.p;
         pa.eta_dt = ip.simulation_dt; pa.n_eta = n_eta; pa.Le = G.Le; pa.nd = G.nd; pa.T = kLaT;
         pa.row0 = row0; pa.nrows = nrows;
-        CUDA_CHECK(launch_lookahead_plan(pa, stream));
+        CUDA_CHECK(launch_lookahead_plan(pa, st));
         LookaheadArgs la{};
-        la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p;
+        la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * kLaT * D * Bp;
         la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = row0;
         la.nchunk = (nrows + kLaRows - 1) / kLaRows;
-        CUDA_CHECK(launch_lookahead(la, stream));
+        CUDA_CHECK(launch_lookahead(la, st));
         prof.kernel_launches += 3;
     }
-    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_la[1], stream)); la_events_pending = true; }
-    la_len = T; la_pos = 0; la_hits_this_block = 0; ++la_builds;
+    if (timed) { CUDA_CHECK(cudaEventRecord(ev_la[1], st)); la_events_pending = true; }
+    CUDA_CHECK(cudaEventRecord(ev_la_build, st));
+    Bk.len = T; Bk.valid = true;
+    ++la_builds;
+    return T;
+}
+
+// Background mode: the block after the current one is evaluated on a low-priority side stream while the main stream
+// runs the steps of the current block (FP64-bound look-ahead kernel under the HBM-bound radiation kernel).
+void hc_ensemble::prefetch_lookahead(int buf) {
+    LaBlock& Cur = la_blk[la_cur];
+    la_blk[buf].valid = false;
+    // (profiling runs every kernel back-to-back in the main stream so that per-kernel event times are meaningful)
+    if (!la_background || profiling || !Cur.valid || Cur.len < kLaT) return;   // short block: end of the eta window
+    CUDA_CHECK(cudaStreamWaitEvent(la_stream, ev_la_free[buf], 0));
+    if (enqueue_lookahead_block(buf, Cur.times[kLaT - 1] + la_dt, la_stream) > 0)
+        CUDA_CHECK(cudaEventRecord(ev_la_done[buf], la_stream));
+}
+
+// Cache slot holding the wave force for time t (bitwise match with a predicted time), building / switching blocks as
+// needed; -1 when look-ahead cannot serve this step (the per-step kernels run instead).
+int hc_ensemble::lookahead_slot(double t) {
+    LaBlock& Cur = la_blk[la_cur];
+    if (Cur.valid && la_pos < Cur.len && Cur.times[la_pos] == t) { ++la_hits_this_block; return la_cur * kLaT + la_pos++; }
+    LaBlock& Nxt = la_blk[la_cur ^ 1];
+    if (la_background && !profiling && Nxt.valid && Nxt.len > 0 && Nxt.times[0] == t) {
+        const int old = la_cur;
+        la_cur ^= 1; la_pos = 0; la_hits_this_block = 1; la_poor_blocks = 0;
+        CUDA_CHECK(cudaStreamWaitEvent(stream, ev_la_done[la_cur], 0));
+        CUDA_CHECK(cudaEventRecord(ev_la_free[old], stream));     // every reader of `old` is already enqueued
+        prefetch_lookahead(old);
+        return la_cur * kLaT + la_pos++;
+    }
+    // miss: first step, end of a block without prefetch, or a time the prediction did not foresee
+    if (la_builds > 0 && la_hits_this_block < 2) {                // a block that served < 2 steps was wasted work
+        if (++la_poor_blocks >= 3) { la_enabled = false; la_blk[0].valid = la_blk[1].valid = false; drop_graph(); return -1; }
+    } else {
+        la_poor_blocks = 0;
+    }
+    la_pos = 0; la_hits_this_block = 0;
+    if (enqueue_lookahead_block(la_cur, t, stream) == 0) return -1;
+    if (la_background) {
+        CUDA_CHECK(cudaEventRecord(ev_la_free[la_cur ^ 1], stream));
+        prefetch_lookahead(la_cur ^ 1);
+    }
+    ++la_hits_this_block;
+    return la_cur * kLaT + la_pos++;
 }
 
 void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
@@ -598,7 +657,8 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->times.clear();
     e->head = -1;
-    e->la_len = 0; e->la_pos = 0;
+    if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
+    e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0;
     e->prev_time = -1.0;
     e->force_valid = false;
     CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
@@ -742,7 +802,8 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
 
     e->n_eta = 0; e->nf = 0;
     e->wave_mode = 2;
-    e->la_enabled = false; e->la_len = 0;
+    e->la_enabled = false; e->la_blk[0].valid = e->la_blk[1].valid = false;
+    if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->drop_graph();
     const bool have_sea = (Hs_arr || p->wave_height != 0.0) && (Tp_arr || p->wave_period != 0.0);
     // --- eta time grid (CreateFreeSurfaceElevation, wave_types.cpp:717-744) ---
@@ -1060,6 +1121,7 @@ hc_status hc_set_profiling(hc_ensemble* e, int enable) {
     e->use_device();
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     if (e->events_pending) e->collect_events();
+    if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->profiling = enable != 0;
     return HC_OK;
     HC_GUARD_END

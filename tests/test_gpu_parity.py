@@ -176,7 +176,7 @@ def rm3():
 IRR = dict(dt=0.01, duration=20.0, ramp=5.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.0, nfreq=200, gamma=3.3)
 
 
-@pytest.mark.parametrize("snap,lookahead", [(0.0, 1), (1e-8, 1), (0.0, 2), (1e-8, 2)])
+@pytest.mark.parametrize("snap,lookahead", [(0.0, 1), (1e-8, 1), (0.0, 2), (1e-8, 2), (0.0, 3), (1e-8, 3)])
 def test_rm3_irregular_ensemble(rm3, snap, lookahead):
     """12-DoF coupled radiation + two-body excitation; B = 7 is ragged against the 64-instance lane tile.
     snap = 0 is the bit-faithful bracket test; snap = 1e-8 + excitation look-ahead is what bench.py measures."""
@@ -201,6 +201,8 @@ def test_rm3_irregular_ensemble(rm3, snap, lookahead):
     launches = ens.profile()["kernel_launches"]
     if lookahead == 2:      # 700 steps = 88 blocks of 8: 4 kernels per step + 3 per block (+ eta synthesis)
         assert launches == 1 + 4 * 700 + 3 * 88, launches
+    elif lookahead == 3:    # background mode: one more block is prefetched on the side stream
+        assert launches == 1 + 4 * 700 + 3 * 89, launches
     else:
         assert launches == 1 + 5 * 700, launches
 
@@ -290,7 +292,7 @@ def test_lookahead_misprediction_falls_back(rm3):
     not change: every step is recomputed from the actual time and look-ahead switches itself off."""
     T, O = rm3
     B = 3
-    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, exc_lookahead=2)
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, exc_lookahead=3)
     kw = dict(IRR)
     ens.set_waves_irregular(seed=4, **kw)
     insts = []
