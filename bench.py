@@ -81,6 +81,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
     ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto, 2 in-stream blocks, 3 background blocks")
+    ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
     return ap.parse_args()
@@ -272,7 +273,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
                       exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream,
-                      exc_lookahead=1 if args.no_lookahead else args.lookahead_mode)
+                      exc_lookahead=1 if args.no_lookahead else args.lookahead_mode, rad_kernel=args.rad_kernel)
     from hydrochrono_b200 import shard
     # weak scaling: every rank owns a contiguous block of B instances of the (world * B)-instance ensemble
     lo, hi = shard.shard_range(world * B, world, rank)
@@ -437,7 +438,8 @@ def main():
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_radiation<%d>" % DOFS, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("k_radiation_mma12 (DMMA m8n8k4)" if (DOFS == 12 and args.rad_kernel == 2)
+                                                     else "k_radiation<%d>" % DOFS), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
                          "kernel_ms": kms["radiation"],

@@ -218,13 +218,14 @@ class Ensemble:
     """B lock-stepped TestHydro instances on one GPU."""
 
     def __init__(self, tables, batch=1, device=0, dt_hint=0.0, bracket_snap=0.0, rad_chunk=0, exc_chunk=0,
-                 use_graph=True, stream=None, exc_lookahead=0):
+                 use_graph=True, stream=None, exc_lookahead=0, rad_kernel=0):
         self.tables = tables  # keep alive
         o = _capi.EnsembleOpts()
         lib.hc_ensemble_default_opts(C.byref(o))
         o.device, o.batch, o.dt_hint, o.bracket_snap = device, batch, dt_hint, bracket_snap
         o.rad_chunk, o.exc_chunk, o.use_graph = rad_chunk, exc_chunk, int(use_graph)
         o.exc_lookahead = int(exc_lookahead)
+        o.rad_kernel = int(rad_kernel)
         o.stream = stream
         h = C.c_void_p()
         _check(lib.hc_ensemble_create(tables._h, C.byref(o), C.byref(h)))

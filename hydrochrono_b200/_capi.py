@@ -41,7 +41,7 @@ class TaperedOpts(C.Structure):
 class EnsembleOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("batch", C.c_int), ("dt_hint", C.c_double), ("bracket_snap", C.c_double),
                 ("rad_chunk", C.c_int), ("exc_chunk", C.c_int), ("use_graph", C.c_int), ("exc_lookahead", C.c_int),
-                ("stream", vp)]
+                ("rad_kernel", C.c_int), ("stream", vp)]
 
 
 class IrregularParams(C.Structure):

@@ -73,7 +73,8 @@ struct hc_ensemble {
     bool own_stream = false;
 
     // static tables on the device
-    DevBuf<double> d_K, d_rirf_t, d_rirf_w, d_ainf;
+    DevBuf<double> d_K, d_Kfrag, d_rirf_t, d_rirf_w, d_ainf;
+    bool rad_mma = false;             // D = 12: FP64 tensor-core (DMMA) radiation kernel
     HydrostaticTables hs{};
 
     // history ring
@@ -174,6 +175,7 @@ struct hc_ensemble {
     }
     void use_device() const { CUDA_CHECK(cudaSetDevice(dev)); }
 
+    void stage_kernel();
     void alloc_ring(int new_cap);
     void grow_ring();
     void setup_radiation_chunks();
@@ -187,6 +189,29 @@ struct hc_ensemble {
     void finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void collect_events();
 };
+
+// (K w) staged as [lag][col][row] (one lag's D x D block contiguous, rows fastest) and, for D = 12, additionally in
+// DMMA A-fragment order [lag][M-tile 0..1][k-step 0..2][lane]: element (row = mt*8 + lane/4, col = ks*4 + lane%4),
+// rows 12..15 zero.
+void hc_ensemble::stage_kernel() {
+    const hc_tables* t = T;
+    std::vector<double> Kdev(size_t(L) * D * D);
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c)
+            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+    d_K.upload(Kdev);
+    if (rad_mma) {
+        std::vector<double> Kf(size_t(L) * 192, 0.0);
+        for (int s = 0; s < L; ++s)
+            for (int mt = 0; mt < 2; ++mt)
+                for (int ks = 0; ks < 3; ++ks)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int r = mt * 8 + lane / 4, c = ks * 4 + lane % 4;
+                        if (r < D) Kf[(size_t(s) * 6 + mt * 3 + ks) * 32 + lane] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+                    }
+        d_Kfrag.upload(Kf);
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 void hc_ensemble::alloc_ring(int new_cap) {
@@ -242,7 +267,8 @@ void hc_ensemble::setup_radiation_chunks() {
     if (chunk <= 0) {
         const bool templated = (D == 6 || D == 12);
         const int occ = templated ? 2 : 4;
-        auto smem_of = templated ? radiation_smem_bytes : +[](int, int) -> size_t { return 0; };
+        auto smem_of = rad_mma ? +[](int, int chunk) -> size_t { return radiation_mma_smem_bytes(chunk); }
+                       : (templated ? radiation_smem_bytes : +[](int, int) -> size_t { return 0; });
         chunk = pick_chunk(L, tiles * (templated ? 1 : D / 6), sm_count, occ, size_t(110) * 1024, smem_of, D, 4);
     }
     chunk = std::max(1, std::min(chunk, L));
@@ -291,7 +317,8 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
         if (!skip_radiation) {
             // convolution over the history that is already resident: every row except this step's own sample
             RadiationArgs ra{};
-            ra.hdr = d_hdr.p; ra.K = d_K.p; ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
+            ra.hdr = d_hdr.p; ra.K = d_K.p; ra.Kfrag = rad_mma ? d_Kfrag.p : nullptr;
+            ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
             ra.times = d_times.p; ra.partial = d_rad_partial.p;
             ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
             CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
@@ -579,7 +606,7 @@ int hc_device_count(void) {
 void hc_ensemble_default_opts(hc_ensemble_opts* o) {
     std::memset(o, 0, sizeof(*o));
     o->device = 0; o->batch = 1; o->dt_hint = 0.0; o->bracket_snap = 0.0;
-    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->stream = nullptr;
+    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->rad_kernel = 0; o->stream = nullptr;
 }
 
 hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, hc_ensemble** out) {
@@ -607,12 +634,10 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_inputs, cudaEventDisableTiming));
 
     const int D = e->D, L = e->L;
-    // K * trapezoid width staged as [lag][col][row]: one lag's D x D block is contiguous, rows fastest
-    std::vector<double> Kdev(size_t(L) * D * D);
-    for (int r = 0; r < D; ++r)
-        for (int c = 0; c < D; ++c)
-            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
-    e->d_K.upload(Kdev);
+    // measured on B200 (profiles/README.md): the DMMA kernel runs below the power cap but pads 12 rows to 16 and ends
+    // up slower (0.319 ms vs 0.274 ms), so auto selects the FMA-pipe kernel
+    e->rad_mma = (D == 12) && (opts->rad_kernel == 2);
+    e->stage_kernel();
     e->d_rirf_t.upload(t->rirf_t);
     e->d_rirf_w.upload(t->rirf_w);
     std::vector<double> A(size_t(D) * D);
@@ -1055,13 +1080,7 @@ hc_status hc_ensemble_refresh_rirf(hc_ensemble* e) {
     HC_GUARD_BEGIN
     e->use_device();
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    const hc_tables* t = e->T;
-    const int D = e->D, L = e->L;
-    std::vector<double> Kdev(size_t(L) * D * D);
-    for (int r = 0; r < D; ++r)
-        for (int c = 0; c < D; ++c)
-            for (int s = 0; s < L; ++s) Kdev[(size_t(s) * D + c) * D + r] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
-    CUDA_CHECK(cudaMemcpy(e->d_K.p, Kdev.data(), Kdev.size() * sizeof(double), cudaMemcpyHostToDevice));
+    e->stage_kernel();
     return HC_OK;
     HC_GUARD_END
 }

@@ -240,6 +240,132 @@ __global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_radiation_mma12: the same convolution for D = 12 on the FP64 tensor cores (DMMA, mma.sync m8n8k4.f64).
+// Per lag the update  F[r][b] += sum_c (K w)[r][c] v[c][b]  is a (16 x 12) x (12 x 64) product per warp: A = the
+// kernel block padded to 16 rows (2 M-tiles x 3 k-steps, stored in shared memory in fragment order so that every
+// lane reads its element with one conflict-free LDS.64), B = the bracketing history row(s) (4 DoF x 8 instances per
+// fragment; one 16-byte load per lane feeds two N-tiles: even / odd instances), C = 2 x 8 accumulator tiles.
+// On B200 the DMMA path delivers the FP64 peak at ~45 % less dynamic power than the DFMA pipe
+// (profiles/microbench/fp64_pipes.cu), which matters because the step runs at the board's power cap.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kMmaFragDoubles = 2 * 3 * 32;     // per lag: 2 M-tiles x 3 k-steps x 32 lanes
+
+__global__ void __launch_bounds__(kThreads, 2) k_radiation_mma12(const RadiationArgs a, const RadPlanPtrs p) {
+    constexpr int D = 12;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int s0 = blockIdx.y * a.chunk;
+    const int ns = min(a.chunk, a.L - s0);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Kf = reinterpret_cast<double*>(smem_raw + 16);               // [chunk][2][3][32]
+    double* s_wn = Kf + (size_t)a.chunk * kMmaFragDoubles;
+    double* s_wo = s_wn + a.chunk;
+    double* s_wd = s_wo + a.chunk;
+    int* s_new = reinterpret_cast<int*>(s_wd + a.chunk);
+    int* s_old = s_new + a.chunk;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)ns * kMmaFragDoubles * sizeof(double);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(Kf, a.Kfrag + (size_t)s0 * kMmaFragDoubles, bytes, bar);
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        s_wn[i] = p.wn[s0 + i]; s_wo[i] = p.wo[s0 + i]; s_wd[i] = p.wd[s0 + i];
+        s_new[i] = p.nw[s0 + i]; s_old[i] = p.od[s0 + i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int b0w = (blockIdx.x * (kThreads / 32) + warp) * 64;          // 64 instances per warp
+    if (b0w >= a.Bp) return;
+    const size_t row_stride = (size_t)D * a.Bp;
+    // lane's element of a B fragment: DoF (k-step * 4 + q), instances b0w + ig * 16 + 2 g + {0, 1}
+    const size_t lane_off = (size_t)q * a.Bp + b0w + 2 * g;
+
+    double C[2][4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ig = 0; ig < 4; ++ig) { C[mt][ig][0][0] = C[mt][ig][0][1] = C[mt][ig][1][0] = C[mt][ig][1][1] = 0.0; }
+
+    for (int s = 0; s < ns; ++s) {
+        if (s_wd[s] == 0.0) continue;
+        const double wn = s_wn[s], wo = s_wo[s];
+        if (wn == 0.0 && wo == 0.0) continue;              // exact hit on this step's own sample: k_finalize's share
+        const double* rn = a.hist + (size_t)s_new[s] * row_stride + lane_off;
+        const double* ro = a.hist + (size_t)s_old[s] * row_stride + lane_off;
+        double2 v[3][4];
+        if (wo == 0.0 && wn == 1.0) {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig)
+                    v[ks][ig] = __ldg(reinterpret_cast<const double2*>(rn + (size_t)(ks * 4) * a.Bp + ig * 16));
+        } else if (wn == 0.0) {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig)
+                    v[ks][ig] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)(ks * 4) * a.Bp + ig * 16));
+            if (wo != 1.0) {                               // lerp whose newer sample is this step's: older share only
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                    for (int ig = 0; ig < 4; ++ig) {
+                        v[ks][ig].x = __dmul_rn(wo, v[ks][ig].x); v[ks][ig].y = __dmul_rn(wo, v[ks][ig].y);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig) {
+                    const double2 u = __ldg(reinterpret_cast<const double2*>(ro + (size_t)(ks * 4) * a.Bp + ig * 16));
+                    const double2 w = __ldg(reinterpret_cast<const double2*>(rn + (size_t)(ks * 4) * a.Bp + ig * 16));
+                    // weight_older*older + weight_newer*newer, unfused as on the host
+                    v[ks][ig].x = __dadd_rn(__dmul_rn(wo, u.x), __dmul_rn(wn, w.x));
+                    v[ks][ig].y = __dadd_rn(__dmul_rn(wo, u.y), __dmul_rn(wn, w.y));
+                }
+            }
+        }
+        const double* kf = Kf + (size_t)s * kMmaFragDoubles + lane;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const double a0 = kf[(0 * 3 + ks) * 32], a1 = kf[(1 * 3 + ks) * 32];
+#pragma unroll
+            for (int ig = 0; ig < 4; ++ig) {
+                dmma8x8x4(C[0][ig][0][0], C[0][ig][0][1], a0, v[ks][ig].x);
+                dmma8x8x4(C[0][ig][1][0], C[0][ig][1][1], a0, v[ks][ig].y);
+                dmma8x8x4(C[1][ig][0][0], C[1][ig][0][1], a1, v[ks][ig].x);
+                dmma8x8x4(C[1][ig][1][0], C[1][ig][1][1], a1, v[ks][ig].y);
+            }
+        }
+    }
+    // C[mt][ig][par][i]: row mt*8 + g, instance b0w + ig*16 + 2*(2q + i) + par  ->  4 consecutive instances per lane
+    double* out = a.partial + (size_t)blockIdx.y * row_stride + b0w + 4 * q;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 8 + g;
+        if (r < D) {
+#pragma unroll
+            for (int ig = 0; ig < 4; ++ig) {
+                double* o = out + (size_t)r * a.Bp + ig * 16;
+                *reinterpret_cast<double2*>(o) = make_double2(C[mt][ig][0][0], C[mt][ig][1][0]);
+                *reinterpret_cast<double2*>(o + 2) = make_double2(C[mt][ig][0][1], C[mt][ig][1][1]);
+            }
+        }
+    }
+}
+
 // Generic fallback for large body counts: D at run time, 6 rows (one body) per z-slice, K read from global/L2.
 __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationArgs a, const RadPlanPtrs p) {
     const int s0 = blockIdx.y * a.chunk;
@@ -671,6 +797,9 @@ __global__ void __launch_bounds__(128) k_added_mass_mv(const double* __restrict_
 size_t radiation_smem_bytes(int D, int chunk) {
     return 16 + (size_t)chunk * D * D * 8 + (size_t)chunk * 3 * 8 + (size_t)chunk * 2 * 4 + 16;
 }
+size_t radiation_mma_smem_bytes(int chunk) {
+    return 16 + (size_t)chunk * kMmaFragDoubles * 8 + (size_t)chunk * 3 * 8 + (size_t)chunk * 2 * 4 + 16;
+}
 size_t excitation_smem_bytes(int nd, int chunk) {
     return 16 + (size_t)chunk * nd * 8 + (size_t)chunk * 2 * 8 + (size_t)chunk * 4 + 16;
 }
@@ -694,6 +823,18 @@ cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const in
     RadPlanPtrs p{pr_new, pr_old, pr_wn, pr_wo, pr_wd};
     dim3 grid((a.Bp + kTileInst - 1) / kTileInst, a.nchunk, 1);
     const size_t smem = radiation_smem_bytes(a.D, a.chunk);
+    if (a.D == 12 && a.Kfrag != nullptr) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(k_radiation_mma12, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set[dev & 63] = true;
+        }
+        k_radiation_mma12<<<grid, kThreads, radiation_mma_smem_bytes(a.chunk), st>>>(a, p);
+        return cudaGetLastError();
+    }
     switch (a.D) {
         case 6: return launch_rad_t<6>(a, p, grid, smem, st);
         case 12: return launch_rad_t<12>(a, p, grid, smem, st);

@@ -34,7 +34,8 @@ struct HydrostaticTables {
 
 struct RadiationArgs {
     const StepHeader* hdr;
-    const double* K;          // [RT][L][D][DR]
+    const double* K;          // [L][D col][D row]  (K w)
+    const double* Kfrag;      // D = 12 only: [L][2][3][32] the same in DMMA A-fragment order (rows padded to 16); or null
     const double* rirf_t;     // [L]
     const double* rirf_w;     // [L]
     const double* hist;       // [cap][D][Bp]
@@ -130,6 +131,7 @@ struct FinalizeGroups {
 };
 
 size_t radiation_smem_bytes(int D, int chunk);
+size_t radiation_mma_smem_bytes(int chunk);
 size_t excitation_smem_bytes(int nd, int chunk);
 cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st);
 int radiation_ctas_per_sm(int D, int chunk);

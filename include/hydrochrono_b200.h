@@ -155,6 +155,9 @@ typedef struct hc_ensemble_opts {
                                  addition of dt_hint, as Chrono advances ChTime); a step whose time is not bitwise
                                  equal to the prediction falls back to / rebuilds from the actual time, so results
                                  never depend on the prediction being right. */
+    int rad_kernel;           /* radiation kernel for 6N = 12: 0 = auto (currently the FP64 FMA-pipe kernel), 1 = FMA pipe,
+                                 2 = FP64 tensor cores (DMMA m8n8k4; 12 rows padded to 16: lower power, slower).
+                                 Other body counts always use the FMA-pipe kernels. */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;
 

@@ -176,13 +176,14 @@ def rm3():
 IRR = dict(dt=0.01, duration=20.0, ramp=5.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.0, nfreq=200, gamma=3.3)
 
 
-@pytest.mark.parametrize("snap,lookahead", [(0.0, 1), (1e-8, 1), (0.0, 2), (1e-8, 2), (0.0, 3), (1e-8, 3)])
-def test_rm3_irregular_ensemble(rm3, snap, lookahead):
+@pytest.mark.parametrize("snap,lookahead,rad_kernel", [(0.0, 1, 2), (1e-8, 1, 1), (0.0, 2, 1), (1e-8, 2, 2), (0.0, 3, 2),
+                                                        (1e-8, 3, 1)])
+def test_rm3_irregular_ensemble(rm3, snap, lookahead, rad_kernel):
     """12-DoF coupled radiation + two-body excitation; B = 7 is ragged against the 64-instance lane tile.
     snap = 0 is the bit-faithful bracket test; snap = 1e-8 + excitation look-ahead is what bench.py measures."""
     T, O = rm3
     B = 7
-    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=lookahead)
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=lookahead, rad_kernel=rad_kernel)
     seeds = list(range(1, B + 1))
     ens.set_waves_irregular(seeds=seeds, **IRR)
     insts = []
