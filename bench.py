@@ -80,7 +80,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
-    ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto, 2 in-stream blocks, 3 background blocks")
+    ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto (= 5), 2 in-stream, 3 background, 4 in-stream DMMA, 5 background DMMA")
     ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
@@ -427,7 +427,8 @@ def main():
                        "bracket_snap": snap, "history_prefill_steps": prefill, "cuda_graph": not args.no_graph,
                        "excitation_lookahead_steps": 1 if args.no_lookahead else 8,
                        "excitation_lookahead_mode": ("off" if args.no_lookahead else
-                                                     {0: "background stream", 2: "in-stream", 3: "background stream"}
+                                                     {0: "background stream, DMMA", 2: "in-stream", 3: "background stream", 4: "in-stream, DMMA",
+                                                      5: "background stream, DMMA"}
                                                      .get(args.lookahead_mode, str(args.lookahead_mode))),
                        "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
                              % (8e-9 * DOFS * B * ens.history_len(), 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
@@ -445,7 +446,9 @@ def main():
                          "kernel_ms": kms["radiation"],
                          "fp64_tflops": rad_tf, "fp64_peak_tflops": fp64_peak,
                          "fp64_frac": rad_tf / fp64_peak if fp64_peak else None,
-                         "excitation": ({"kernel": "k_exc_block<12> (look-ahead, 8 steps per eta pass)", "bound": "fp64",
+                         "excitation": ({"kernel": ("k_exc_block_mma<%d> (look-ahead, 8 steps per eta pass, DMMA m8n8k4)" % DOFS
+                                                    if args.lookahead_mode in (0, 4, 5) else
+                                                    "k_exc_block<%d> (look-ahead, 8 steps per eta pass)" % DOFS), "bound": "fp64",
                                          "achieved": exc_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                          "frac": exc_tf / fp64_peak if (exc_tf and fp64_peak) else None,
                                          "peak_source": "measured in this run (hc_measure_fp64_peak, DFMA loop)",

@@ -128,6 +128,7 @@ struct hc_ensemble {
     LaBlock la_blk[2];                // double-buffered blocks of predicted times / cached wave forces
     int la_cur = 0, la_pos = 0;       // block being consumed / next slot expected
     bool la_background = false;       // next block evaluated on a side stream under the current block's steps
+    bool la_mma = false;              // look-ahead block on the FP64 tensor cores (DMMA)
     cudaStream_t la_stream = nullptr;
     cudaEvent_t ev_la_done[2] = {nullptr, nullptr}, ev_la_free[2] = {nullptr, nullptr}, ev_la_build = nullptr;
     int la_builds = 0, la_hits_this_block = 0, la_poor_blocks = 0;
@@ -458,7 +459,8 @@ void hc_ensemble::setup_lookahead() {
     const int tiles = (Bp + 32 * kIPT - 1) / (32 * kIPT);
     if (want == 0 && tiles < sm_count) return;             // auto: only when one CTA per instance tile fills the GPU
     la_dt = opts.dt_hint;
-    la_background = (want == 0 || want >= 3);
+    la_background = (want == 0 || want == 3 || want == 5);
+    la_mma = (want == 0 || want == 4 || want == 5);
     for (auto& b : la_blk) b.times.assign(kLaT, 0.0);
     d_la_cache.alloc(size_t(2) * kLaT * D * Bp);
     d_la_times.alloc(2 * kLaT);
@@ -519,12 +521,12 @@ int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
         pa.times = d_times; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
         pa.idx = G.la_idx.p; pa.w1 = G.la_w1.p; pa.w2 = G.la_w2.p; pa.taps = G.la_taps.p;
         pa.eta_dt = ip.simulation_dt; pa.n_eta = n_eta; pa.Le = G.Le; pa.nd = G.nd; pa.T = kLaT;
-        pa.row0 = row0; pa.nrows = nrows;
+        pa.row0 = row0; pa.nrows = nrows; pa.frag_order = la_mma ? 1 : 0;
         CUDA_CHECK(launch_lookahead_plan(pa, st));
         LookaheadArgs la{};
         la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * kLaT * D * Bp;
         la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = row0;
-        la.nchunk = (nrows + kLaRows - 1) / kLaRows;
+        la.nchunk = (nrows + kLaRows - 1) / kLaRows; la.use_mma = la_mma ? 1 : 0;
         CUDA_CHECK(launch_lookahead(la, st));
         prof.kernel_launches += 3;
     }

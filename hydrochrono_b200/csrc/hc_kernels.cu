@@ -556,6 +556,12 @@ __global__ void __launch_bounds__(256) k_la_taps(const LookaheadPlanArgs a) {
         const int chunk = mr / kLaRows, rr = mr - chunk * kLaRows;
         double* out = a.taps + (((size_t)chunk * a.T + i) * kLaRows + rr) * a.nd;
         for (int d = 0; d < a.nd; ++d) {
+            if (a.frag_order) {
+                // DMMA A-fragment order: [chunk][k-step = rr/4][M-tile][lane]; A row m = (block time i, dof d),
+                // A column = eta row within the k-step; lane = (m % 8) * 4 + rr % 4
+                const int m = i * a.nd + d, mtiles = a.T * a.nd / 8;
+                out = a.taps + ((((size_t)chunk * (kLaRows / 4) + rr / 4) * mtiles + m / 8) * 32 + (m % 8) * 4 + (rr & 3)) - d;
+            }
             double g = 0.0;
             if (mr < a.nrows) {
                 for (int j = j0; j < j1; ++j)        // idx == row: weight of the lower bracket sample
@@ -633,6 +639,84 @@ __global__ void __launch_bounds__(kLaT * 32, 2) k_exc_block(const LookaheadArgs 
         double* out = a.cache + ((size_t)warp * a.D + a.dof0) * a.Bp + b0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) *reinterpret_cast<double2*>(out + (size_t)d * a.Bp) = make_double2(acc0[d], acc1[d]);
+    }
+}
+
+// k_exc_block_mma<ND>: the look-ahead block on the FP64 tensor cores.  M = (block time, dof) = 8 * ND rows = ND
+// M-tiles with no padding, N = instances, K = eta rows: per k-step (4 eta rows) a warp issues ND * 2 DMMAs for its 16
+// instances from ONE 16-byte eta load per lane and ND conflict-free LDS.64 of taps; eta is read exactly once.
+template <int ND>
+__global__ void __launch_bounds__(128) k_exc_block_mma(const LookaheadArgs a) {
+    constexpr int MT = ND;                                   // kLaT * ND / 8 with kLaT == 8
+    constexpr int KS = kLaRows / 4;                          // k-steps per stage
+    constexpr int kStageDoubles = KS * MT * 32;
+    constexpr uint32_t kStageBytes = kStageDoubles * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    double* const stage0 = reinterpret_cast<double*>(smem_raw + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int b0 = (blockIdx.x * 4 + warp) * 16;             // 16 instances per warp
+    const bool active = b0 < a.Bp;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_expect_tx(&bars[0], kStageBytes);
+        bulk_g2s(stage0, a.taps, kStageBytes, &bars[0]);
+    }
+    __syncthreads();
+
+    double C[MT][2][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) { C[mt][0][0] = C[mt][0][1] = C[mt][1][0] = C[mt][1][1] = 0.0; }
+
+    // lane's B element: eta row (k-step * 4 + q), instances b0 + 2 g + {0, 1}
+    const double* eta_l = a.eta + (active ? b0 + 2 * g : 0);
+    auto load_stage = [&](int c, double2* dst) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int row = min(a.row0 + c * kLaRows + ks * 4 + q, a.n_eta - 1);   // rows past the window: zero taps
+            dst[ks] = __ldg(reinterpret_cast<const double2*>(eta_l + (size_t)row * a.Bp));
+        }
+    };
+    double2 cur[KS], nxt[KS];
+    if (active) load_stage(0, cur);
+
+    for (int c = 0; c < a.nchunk; ++c) {
+        const int st = c & 1;
+        if (threadIdx.x == 0 && c + 1 < a.nchunk) {
+            mbar_expect_tx(&bars[st ^ 1], kStageBytes);
+            bulk_g2s(stage0 + (st ^ 1) * kStageDoubles, a.taps + (size_t)(c + 1) * kStageDoubles, kStageBytes,
+                     &bars[st ^ 1]);
+        }
+        if (active && c + 1 < a.nchunk) load_stage(c + 1, nxt);           // eta of the next stage is in flight
+        mbar_wait(&bars[st], (c >> 1) & 1);
+        if (active) {
+            const double* tp = reinterpret_cast<const double*>(smem_raw + 16) + (size_t)st * kStageDoubles + lane;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double av = tp[(ks * MT + mt) * 32];
+                    dmma8x8x4(C[mt][0][0], C[mt][0][1], av, cur[ks].x);
+                    dmma8x8x4(C[mt][1][0], C[mt][1][1], av, cur[ks].y);
+                }
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) cur[ks] = nxt[ks];
+        }
+        __syncthreads();
+    }
+    if (active) {
+        // C[mt][par][e]: A row m = mt*8 + g -> (block time m / ND, dof m % ND); instance b0 + 2*(2q + e) + par
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int m = mt * 8 + g, i = m / ND, d = m - i * ND;
+            double* o = a.cache + ((size_t)i * a.D + a.dof0 + d) * a.Bp + b0 + 4 * q;
+            *reinterpret_cast<double2*>(o) = make_double2(C[mt][0][0], C[mt][1][0]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(C[mt][0][1], C[mt][1][1]);
+        }
     }
 }
 
@@ -993,7 +1077,30 @@ static cudaError_t launch_la_t(const LookaheadArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <int ND>
+static cudaError_t launch_la_mma_t(const LookaheadArgs& a, cudaStream_t st) {
+    const size_t smem = 16 + size_t(2) * (kLaRows / 4) * ND * 32 * sizeof(double);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_exc_block_mma<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const int tiles = (a.Bp + 63) / 64;                      // 4 warps x 16 instances per CTA
+    k_exc_block_mma<ND><<<tiles, 128, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lookahead(const LookaheadArgs& a, cudaStream_t st) {
+    if (a.use_mma) {
+        switch (a.nd) {
+            case 6: return launch_la_mma_t<6>(a, st);
+            case 12: return launch_la_mma_t<12>(a, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.nd) {
         case 6: return launch_la_t<6>(a, st);
         case 12: return launch_la_t<12>(a, st);

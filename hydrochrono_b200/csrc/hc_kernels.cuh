@@ -157,12 +157,14 @@ struct LookaheadPlanArgs {
     double* taps;             // [nchunk][T][kLaRows][nd]
     double eta_dt;
     int n_eta, Le, nd, T, row0, nrows;   // rows row0 .. row0 + nrows - 1 of eta carry taps
+    int frag_order;           // 1: taps in DMMA A-fragment order [chunk][k-step][M-tile][lane] (k_exc_block_mma)
 };
 struct LookaheadArgs {
     const double* eta;        // [n_eta][Bp]
     const double* taps;       // [nchunk][T][kLaRows][nd]
     double* cache;            // [T][D][Bp]
     int n_eta, Bp, D, dof0, nd, row0, nchunk;
+    int use_mma;              // 1: FP64 tensor-core kernel (taps in fragment order)
 };
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
 cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);
