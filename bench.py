@@ -81,7 +81,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
     ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto (= 5), 2 in-stream, 3 background, 4 in-stream DMMA, 5 background DMMA")
-    ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only)")
+    ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only), 3 tensor cores (rows 0-7) + FMA pipe (rows 8-11)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
     return ap.parse_args()
@@ -440,6 +440,7 @@ def main():
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": ("k_radiation_mma12 (DMMA m8n8k4)" if (DOFS == 12 and args.rad_kernel == 2)
+                                                     else "k_radiation_hybrid12 (DMMA + DFMA)" if (DOFS == 12 and args.rad_kernel == 3)
                                                      else "k_radiation<%d>" % DOFS), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,

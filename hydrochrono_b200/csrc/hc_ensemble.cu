@@ -73,8 +73,9 @@ struct hc_ensemble {
     bool own_stream = false;
 
     // static tables on the device
-    DevBuf<double> d_K, d_Kfrag, d_rirf_t, d_rirf_w, d_ainf;
+    DevBuf<double> d_K, d_Kfrag, d_Khyb, d_rirf_t, d_rirf_w, d_ainf;
     bool rad_mma = false;             // D = 12: FP64 tensor-core (DMMA) radiation kernel
+    bool rad_hybrid = false;          // D = 12: rows 0..7 on the tensor cores + rows 8..11 on the FMA pipe
     HydrostaticTables hs{};
 
     // history ring
@@ -212,6 +213,19 @@ void hc_ensemble::stage_kernel() {
                     }
         d_Kfrag.upload(Kf);
     }
+    if (rad_hybrid) {
+        std::vector<double> Kh(size_t(L) * 144, 0.0);
+        for (int s = 0; s < L; ++s) {
+            double* o = &Kh[size_t(s) * 144];
+            auto kw = [&](int r, int c) { return t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s]; };
+            for (int ks = 0; ks < 3; ++ks)
+                for (int lane = 0; lane < 32; ++lane) o[ks * 32 + lane] = kw(lane / 4, ks * 4 + lane % 4);
+            for (int q = 0; q < 4; ++q)
+                for (int ks = 0; ks < 3; ++ks)
+                    for (int r = 0; r < 4; ++r) o[96 + q * 12 + ks * 4 + r] = kw(8 + r, ks * 4 + q);
+        }
+        d_Khyb.upload(Kh);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -263,8 +277,10 @@ static int pick_chunk(int n_lags, int tiles, int sm_count, int occ_target, size_
 }
 
 void hc_ensemble::setup_radiation_chunks() {
-    const int tiles = (Bp + kTileInst - 1) / kTileInst;
+    const int tile_inst = rad_hybrid ? kHybTileInst : kTileInst;
+    const int tiles = (Bp + tile_inst - 1) / tile_inst;
     int chunk = opts.rad_chunk;
+    if (chunk <= 0 && rad_hybrid) chunk = pick_chunk(L, tiles, sm_count, 3, size_t(72) * 1024, radiation_smem_bytes, D, 4);
     if (chunk <= 0) {
         const bool templated = (D == 6 || D == 12);
         const int occ = templated ? 2 : 4;
@@ -319,6 +335,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
             // convolution over the history that is already resident: every row except this step's own sample
             RadiationArgs ra{};
             ra.hdr = d_hdr.p; ra.K = d_K.p; ra.Kfrag = rad_mma ? d_Kfrag.p : nullptr;
+            ra.Khyb = rad_hybrid ? d_Khyb.p : nullptr;
             ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
             ra.times = d_times.p; ra.partial = d_rad_partial.p;
             ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
@@ -639,6 +656,7 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     // measured on B200 (profiles/README.md): the DMMA kernel runs below the power cap but pads 12 rows to 16 and ends
     // up slower (0.319 ms vs 0.274 ms), so auto selects the FMA-pipe kernel
     e->rad_mma = (D == 12) && (opts->rad_kernel == 2);
+    e->rad_hybrid = (D == 12) && (opts->rad_kernel == 3);
     e->stage_kernel();
     e->d_rirf_t.upload(t->rirf_t);
     e->d_rirf_w.upload(t->rirf_w);

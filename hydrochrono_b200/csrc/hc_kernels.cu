@@ -366,6 +366,146 @@ __global__ void __launch_bounds__(kThreads, 2) k_radiation_mma12(const Radiation
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_radiation_hybrid12: D = 12 on BOTH FP64 engines at once.  Rows 0..7 of F form one full DMMA M-tile (no padding):
+// 24 DMMA per warp and lag on the tensor cores; rows 8..11 would waste half a tile, so they run on the FMA pipe from
+// the same B-fragment registers: every lane holds 3 of the 12 velocity DoF (k-step * 4 + q) for 8 instances, forms
+// its partial dot products (96 DFMA per lag) and the four lanes of a quad are summed once per CTA with shuffles.
+// Per warp and lag: 384 tensor-pipe cycles || 192 FMA-pipe cycles per SM sub-partition instead of 576 FMA-pipe cycles,
+// at a third of the DFMA count (the step runs at the board's power cap).
+// Shared memory per lag (144 doubles, as the FMA-pipe kernel): [3][32] A fragments of rows 0..7, then
+// [q 0..3][k-step 0..2][row 8..11] for the FMA part.
+// ------------------------------------------------------------------------------------------
+constexpr int kHybThreads = 128;
+__global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const RadiationArgs a, const RadPlanPtrs p) {
+    constexpr int D = 12, kLag = 144;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int s0 = blockIdx.y * a.chunk;
+    const int ns = min(a.chunk, a.L - s0);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Kh = reinterpret_cast<double*>(smem_raw + 16);               // [chunk][144]
+    double* s_wn = Kh + (size_t)a.chunk * kLag;
+    double* s_wo = s_wn + a.chunk;
+    double* s_wd = s_wo + a.chunk;
+    int* s_new = reinterpret_cast<int*>(s_wd + a.chunk);
+    int* s_old = s_new + a.chunk;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)ns * kLag * sizeof(double);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(Kh, a.Khyb + (size_t)s0 * kLag, bytes, bar);
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        s_wn[i] = p.wn[s0 + i]; s_wo[i] = p.wo[s0 + i]; s_wd[i] = p.wd[s0 + i];
+        s_new[i] = p.nw[s0 + i]; s_old[i] = p.od[s0 + i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int b0w = (blockIdx.x * (kHybThreads / 32) + warp) * 64;       // 64 instances per warp
+    if (b0w >= a.Bp) return;
+    const size_t row_stride = (size_t)D * a.Bp;
+    const size_t lane_off = (size_t)q * a.Bp + b0w + 2 * g;
+
+    double C0[4][2][2];        // tensor part: rows 0..7
+    double acc[4][4][2];       // FMA part: [row 8 + r][instance group][parity], partial over this lane's 3 DoF
+#pragma unroll
+    for (int ig = 0; ig < 4; ++ig) {
+        C0[ig][0][0] = C0[ig][0][1] = C0[ig][1][0] = C0[ig][1][1] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { acc[r][ig][0] = 0.0; acc[r][ig][1] = 0.0; }
+    }
+
+    for (int s = 0; s < ns; ++s) {
+        if (s_wd[s] == 0.0) continue;
+        const double wn = s_wn[s], wo = s_wo[s];
+        if (wn == 0.0 && wo == 0.0) continue;
+        const double* rn = a.hist + (size_t)s_new[s] * row_stride + lane_off;
+        const double* ro = a.hist + (size_t)s_old[s] * row_stride + lane_off;
+        double2 v[3][4];
+        if (wo == 0.0 && wn == 1.0) {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig)
+                    v[ks][ig] = __ldg(reinterpret_cast<const double2*>(rn + (size_t)(ks * 4) * a.Bp + ig * 16));
+        } else if (wn == 0.0) {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig)
+                    v[ks][ig] = __ldg(reinterpret_cast<const double2*>(ro + (size_t)(ks * 4) * a.Bp + ig * 16));
+            if (wo != 1.0) {
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                    for (int ig = 0; ig < 4; ++ig) {
+                        v[ks][ig].x = __dmul_rn(wo, v[ks][ig].x); v[ks][ig].y = __dmul_rn(wo, v[ks][ig].y);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+#pragma unroll
+                for (int ig = 0; ig < 4; ++ig) {
+                    const double2 u = __ldg(reinterpret_cast<const double2*>(ro + (size_t)(ks * 4) * a.Bp + ig * 16));
+                    const double2 w = __ldg(reinterpret_cast<const double2*>(rn + (size_t)(ks * 4) * a.Bp + ig * 16));
+                    v[ks][ig].x = __dadd_rn(__dmul_rn(wo, u.x), __dmul_rn(wn, w.x));
+                    v[ks][ig].y = __dadd_rn(__dmul_rn(wo, u.y), __dmul_rn(wn, w.y));
+                }
+            }
+        }
+        const double* kl = Kh + (size_t)s * kLag;
+        const double2* kq = reinterpret_cast<const double2*>(kl + 96 + q * 12);     // [k-step][row 8..11]
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const double a0 = kl[ks * 32 + lane];
+            const double2 k01 = kq[ks * 2], k23 = kq[ks * 2 + 1];
+#pragma unroll
+            for (int ig = 0; ig < 4; ++ig) {
+                dmma8x8x4(C0[ig][0][0], C0[ig][0][1], a0, v[ks][ig].x);
+                dmma8x8x4(C0[ig][1][0], C0[ig][1][1], a0, v[ks][ig].y);
+                acc[0][ig][0] = fma(k01.x, v[ks][ig].x, acc[0][ig][0]); acc[0][ig][1] = fma(k01.x, v[ks][ig].y, acc[0][ig][1]);
+                acc[1][ig][0] = fma(k01.y, v[ks][ig].x, acc[1][ig][0]); acc[1][ig][1] = fma(k01.y, v[ks][ig].y, acc[1][ig][1]);
+                acc[2][ig][0] = fma(k23.x, v[ks][ig].x, acc[2][ig][0]); acc[2][ig][1] = fma(k23.x, v[ks][ig].y, acc[2][ig][1]);
+                acc[3][ig][0] = fma(k23.y, v[ks][ig].x, acc[3][ig][0]); acc[3][ig][1] = fma(k23.y, v[ks][ig].y, acc[3][ig][1]);
+            }
+        }
+    }
+    double* base = a.partial + (size_t)blockIdx.y * row_stride + b0w;
+    // rows 0..7 from the accumulator tiles: row g, 4 consecutive instances per lane
+#pragma unroll
+    for (int ig = 0; ig < 4; ++ig) {
+        double* o = base + (size_t)g * a.Bp + ig * 16 + 4 * q;
+        *reinterpret_cast<double2*>(o) = make_double2(C0[ig][0][0], C0[ig][1][0]);
+        *reinterpret_cast<double2*>(o + 2) = make_double2(C0[ig][0][1], C0[ig][1][1]);
+    }
+    // rows 8..11: sum the quad's partial dot products, lane q of the quad stores row 8 + q
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int ig = 0; ig < 4; ++ig)
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                double x = acc[r][ig][par];
+                x += __shfl_xor_sync(0xffffffffu, x, 1);
+                x += __shfl_xor_sync(0xffffffffu, x, 2);
+                acc[r][ig][par] = x;
+            }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (q == r) {
+#pragma unroll
+            for (int ig = 0; ig < 4; ++ig)
+                *reinterpret_cast<double2*>(base + (size_t)(8 + r) * a.Bp + ig * 16 + 2 * g) =
+                    make_double2(acc[r][ig][0], acc[r][ig][1]);
+        }
+    }
+}
+
 // Generic fallback for large body counts: D at run time, 6 rows (one body) per z-slice, K read from global/L2.
 __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationArgs a, const RadPlanPtrs p) {
     const int s0 = blockIdx.y * a.chunk;
@@ -907,6 +1047,20 @@ cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const in
     RadPlanPtrs p{pr_new, pr_old, pr_wn, pr_wo, pr_wd};
     dim3 grid((a.Bp + kTileInst - 1) / kTileInst, a.nchunk, 1);
     const size_t smem = radiation_smem_bytes(a.D, a.chunk);
+    if (a.D == 12 && a.Khyb != nullptr) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(k_radiation_hybrid12, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set[dev & 63] = true;
+        }
+        const int tile = (kHybThreads / 32) * 64;
+        dim3 gridh((a.Bp + tile - 1) / tile, a.nchunk, 1);
+        k_radiation_hybrid12<<<gridh, kHybThreads, radiation_smem_bytes(12, a.chunk), st>>>(a, p);
+        return cudaGetLastError();
+    }
     if (a.D == 12 && a.Kfrag != nullptr) {
         static bool attr_set[64] = {};
         int dev = 0;

@@ -9,6 +9,7 @@ constexpr int kMaxBodies = 8;        // static hydrostatics tables live in kerne
 constexpr int kThreads = 256;        // CTA size of the convolution kernels
 constexpr int kIPT = 2;              // instances per thread (one 16-byte load per history value pair)
 constexpr int kTileInst = kThreads * kIPT;
+constexpr int kHybTileInst = 256;  // instances per CTA of k_radiation_hybrid12 (4 warps x 64)
 
 // Written by the host for every step (pinned -> device copy), read by every kernel of the step so that the
 // captured CUDA graph is static.
@@ -36,6 +37,7 @@ struct RadiationArgs {
     const StepHeader* hdr;
     const double* K;          // [L][D col][D row]  (K w)
     const double* Kfrag;      // D = 12 only: [L][2][3][32] the same in DMMA A-fragment order (rows padded to 16); or null
+    const double* Khyb;       // D = 12 only: [L][144] rows 0..7 as A fragments [3][32] + rows 8..11 as [q][k-step][row]; or null
     const double* rirf_t;     // [L]
     const double* rirf_w;     // [L]
     const double* hist;       // [cap][D][Bp]

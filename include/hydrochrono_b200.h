@@ -157,7 +157,8 @@ typedef struct hc_ensemble_opts {
                                  equal to the prediction falls back to / rebuilds from the actual time, so results
                                  never depend on the prediction being right. */
     int rad_kernel;           /* radiation kernel for 6N = 12: 0 = auto (currently the FP64 FMA-pipe kernel), 1 = FMA pipe,
-                                 2 = FP64 tensor cores (DMMA m8n8k4; 12 rows padded to 16: lower power, slower).
+                                 2 = FP64 tensor cores (DMMA m8n8k4; 12 rows padded to 16: lower power, slower),
+                                 3 = both engines: rows 0..7 on the tensor cores, rows 8..11 on the FMA pipe.
                                  Other body counts always use the FMA-pipe kernels. */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;

@@ -1,5 +1,5 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
-for args in "--lookahead-mode 3" "--lookahead-mode 4" "--lookahead-mode 5" "--workload sphere_irregular_ensemble"; do
+for args in "--rad-kernel 1" "--rad-kernel 3" "--rad-kernel 3 --rad-chunk 40" "--rad-kernel 3 --rad-chunk 64"; do
 python bench.py --steps 800 --warmup 10 --no-cpu $args 2>gpurun_out/bench_err.log | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())

@@ -177,7 +177,7 @@ IRR = dict(dt=0.01, duration=20.0, ramp=5.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.
 
 
 @pytest.mark.parametrize("snap,lookahead,rad_kernel", [(0.0, 1, 2), (1e-8, 1, 1), (0.0, 2, 1), (1e-8, 2, 2), (0.0, 3, 2),
-                                                        (1e-8, 3, 1), (0.0, 4, 1), (1e-8, 5, 1)])
+                                                        (1e-8, 3, 1), (0.0, 4, 3), (1e-8, 5, 3)])
 def test_rm3_irregular_ensemble(rm3, snap, lookahead, rad_kernel):
     """12-DoF coupled radiation + two-body excitation; B = 7 is ragged against the 64-instance lane tile.
     snap = 0 is the bit-faithful bracket test; snap = 1e-8 + excitation look-ahead is what bench.py measures."""
