@@ -81,6 +81,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
     ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto (= 5), 2 in-stream, 3 background, 4 in-stream DMMA, 5 background DMMA")
+    ap.add_argument("--rad-lookahead", type=int, default=0, help="radiation look-ahead block (12 DoF): 0 auto (on), 1 off, 2 on")
     ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only), 3 tensor cores (rows 0-7) + FMA pipe (rows 8-11)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
@@ -273,7 +274,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
                       exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream,
-                      exc_lookahead=1 if args.no_lookahead else args.lookahead_mode, rad_kernel=args.rad_kernel)
+                      exc_lookahead=1 if args.no_lookahead else args.lookahead_mode, rad_kernel=args.rad_kernel, rad_lookahead=args.rad_lookahead)
     from hydrochrono_b200 import shard
     # weak scaling: every rank owns a contiguous block of B instances of the (world * B)-instance ensemble
     lo, hi = shard.shard_range(world * B, world, rank)
@@ -351,15 +352,19 @@ def main():
 
     # ---- per-kernel device times (CUDA events on the ensemble's stream; graph off while profiling) ----
     ens.set_profiling(True)
-    nprof = min(max(K // 4, 20), 100)
+    rb_T = ens.rad_lookahead_steps()                 # steps per radiation look-ahead block (0: per-step kernel)
+    nprof = min(max(K // 4, 20), 100) if not rb_T else rb_T * max(2, round(100 / rb_T))   # whole blocks
     for _ in range(3):
         dev_step()
     ens.sync()
     ens.kernel_ms(reset=True)
+    ens.rad_block_stats(reset=True)
     for _ in range(nprof):
         dev_step()
     ens.sync()
     kms = ens.kernel_ms(reset=True)
+    rb_stats = ens.rad_block_stats(reset=True)
+    rb_on = bool(rb_T) and rb_stats["steps_served"] == nprof
     ens.set_profiling(False)
 
     # ---- end-to-end leg (host buffers through hc_step) -----------------------------------------------
@@ -399,6 +404,7 @@ def main():
         ens.set_bracket_snap(snap)
 
     fp64_peak = hc.measure_fp64_peak(local_rank) if rank == 0 else None
+    mma_peak = hc.measure_fp64_mma_peak(local_rank) if rank == 0 else None
     if rank == 0:
         peak, peak_src = hbm_peak()
         # distinct history rows touched per step: one per lag with exact hits / snapping, up to two otherwise
@@ -415,6 +421,42 @@ def main():
         value = world * B * K / t_dev
         step_bytes = rad_bytes + (exc_bytes if args.no_lookahead else (B * 8 * (EXC_STEPS + 8) // 8))
         step_flops = rad_flops + exc_flops
+        exc_mma = (not args.no_lookahead) and args.lookahead_mode in (0, 4, 5)
+        exc_peak = mma_peak if exc_mma else fp64_peak
+        rad_roof = {"bound": "hbm", "kernel": ("k_radiation_mma12 (DMMA m8n8k4)" if (DOFS == 12 and args.rad_kernel == 2)
+                                               else "k_radiation_hybrid12 (DMMA + DFMA)" if (DOFS == 12 and args.rad_kernel == 3)
+                                               else "k_radiation<%d>" % DOFS), "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
+                    "kernel_ms": kms["radiation"],
+                    "fp64_tflops": rad_tf, "fp64_peak_tflops": fp64_peak,
+                    "fp64_frac": rad_tf / fp64_peak if fp64_peak else None}
+        if rb_on:
+            # k_rad_block12: one launch = the resident rows' share of rb_T steps; lags served by the block at block
+            # step j: (L - 1) - floor(j / m)  (the younger lags belong to k_rad_step)
+            m = rb_T // 8
+            lag_steps = sum((RIRF_STEPS - 1) - (j // m) for j in range(rb_T))
+            blk_flops = 2.0 * DOFS * DOFS * lag_steps * B
+            blk_ms = rb_stats["avg_ms"]
+            blk_tf = blk_flops / (blk_ms * 1e-3) / 1e12
+            hist_bytes = 8.0 * DOFS * B * m * (RIRF_STEPS - 1)         # every resident row once per block
+            rad_roof = {"bound": "tensor", "kernel": "k_rad_block12 (radiation look-ahead: %d steps per pass over the "
+                                                     "history, FP64 tensor cores, DMMA m8n8k4)" % rb_T,
+                        "achieved": blk_tf, "peak": mma_peak, "unit": "TFLOP/s", "frac": blk_tf / mma_peak,
+                        "traffic": (traffic or {}).get("rad_block_dram_bytes_per_launch"),
+                        "peak_source": "FP64 tensor-core peak measured in this run (hc_measure_fp64_mma_peak, DMMA m8n8k4 "
+                                       "loop); MEASURED_PEAKS.json holds no FP64 figure (B200 nominal: 40 TFLOP/s)",
+                        "algorithmic_flops_per_launch": blk_flops, "launch_ms": blk_ms, "steps_per_launch": rb_T,
+                        "history_bytes_per_launch": hist_bytes,
+                        "kernel_ms": kms["radiation"],
+                        "kernel_ms_note": "radiation per step = k_rad_block12 launch / %d + k_rad_step" % rb_T,
+                        "hbm_view": {"algorithmic_bytes_per_step": rad_bytes, "gbs": ach, "hbm_peak": peak, "frac": ach / peak,
+                                     "note": "SURVEY 8(d) bytes of the per-step formulation over the measured radiation "
+                                             "time per step: the block pass reads each history row once per %d steps, "
+                                             "so the per-step HBM roofline no longer binds (frac > 1); "
+                                             "--rad-lookahead 1 measures the per-step kernel k_radiation<12> against "
+                                             "that roofline" % rb_T}}
+            step_bytes = hist_bytes / rb_T + (B * 8 * (EXC_STEPS + 8) // 8)
         step_s = t_dev / K
         e2e = world * B * K / t_e2e
         line = {
@@ -426,6 +468,7 @@ def main():
                        "spectrum_components": nf, "eta_samples": n_eta, "sea_state": SEA,
                        "bracket_snap": snap, "history_prefill_steps": prefill, "cuda_graph": not args.no_graph,
                        "excitation_lookahead_steps": 1 if args.no_lookahead else 8,
+                       "radiation_lookahead_steps": rb_T if rb_on else 1,
                        "excitation_lookahead_mode": ("off" if args.no_lookahead else
                                                      {0: "background stream, DMMA", 2: "in-stream", 3: "background stream", 4: "in-stream, DMMA",
                                                       5: "background stream, DMMA"}
@@ -439,20 +482,14 @@ def main():
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": ("k_radiation_mma12 (DMMA m8n8k4)" if (DOFS == 12 and args.rad_kernel == 2)
-                                                     else "k_radiation_hybrid12 (DMMA + DFMA)" if (DOFS == 12 and args.rad_kernel == 3)
-                                                     else "k_radiation<%d>" % DOFS), "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": (traffic or {}).get("radiation_dram_bytes_per_launch"),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": rad_bytes,
-                         "kernel_ms": kms["radiation"],
-                         "fp64_tflops": rad_tf, "fp64_peak_tflops": fp64_peak,
-                         "fp64_frac": rad_tf / fp64_peak if fp64_peak else None,
+            "roofline": {**rad_roof,
                          "excitation": ({"kernel": ("k_exc_block_mma<%d> (look-ahead, 8 steps per eta pass, DMMA m8n8k4)" % DOFS
                                                     if args.lookahead_mode in (0, 4, 5) else
                                                     "k_exc_block<%d> (look-ahead, 8 steps per eta pass)" % DOFS), "bound": "fp64",
-                                         "achieved": exc_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                                         "frac": exc_tf / fp64_peak if (exc_tf and fp64_peak) else None,
-                                         "peak_source": "measured in this run (hc_measure_fp64_peak, DFMA loop)",
+                                         "achieved": exc_tf, "peak": exc_peak, "unit": "TFLOP/s",
+                                         "frac": exc_tf / exc_peak if (exc_tf and exc_peak) else None,
+                                         "peak_source": "measured in this run (%s)" % ("hc_measure_fp64_mma_peak, DMMA loop" if exc_mma
+                                                                                        else "hc_measure_fp64_peak, DFMA loop"),
                                          "flops_per_step": exc_flops, "kernel_ms_per_step": kms["excitation"],
                                          "traffic": (traffic or {}).get("exc_block_dram_bytes_per_launch"),
                                          "traffic_note": "dram bytes per k_exc_block launch (one launch per 8 steps)"}
@@ -463,12 +500,14 @@ def main():
                                          "traffic": (traffic or {}).get("excitation_dram_bytes_per_launch")})},
             "step_roofline": {"hbm_gbs": step_bytes / step_s / 1e9, "hbm_frac": step_bytes / step_s / 1e9 / peak,
                               "fp64_tflops": step_flops / step_s / 1e12,
-                              "fp64_frac": (step_flops / step_s / 1e12 / fp64_peak) if fp64_peak else None,
+                              "fp64_frac": (step_flops / step_s / 1e12 / max(fp64_peak, mma_peak)) if fp64_peak else None,
+                              "fp64_peaks_tflops": {"fma_pipe": fp64_peak, "tensor_dmma": mma_peak},
                               "note": "whole step (all kernels, overlapped): algorithmic bytes and flops per step over "
                                       "the measured step time; the step needs both resources at once"},
             "kernel_ms": kms,
             "kernel_ms_note": "isolated kernel durations (the profiling pass runs every kernel back-to-back in one "
-                              "stream; excitation = look-ahead block time / 8).  In the timed region the look-ahead "
+                              "stream; excitation = look-ahead block time / 8; radiation = look-ahead block time / "
+                              "steps per block + k_rad_step when the radiation look-ahead is on).  In the timed region the look-ahead "
                               "block of the NEXT 8 steps runs on a low-priority side stream underneath the per-step "
                               "kernels, so ms_per_step < sum(kernel_ms)",
             "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},

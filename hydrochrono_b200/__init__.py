@@ -58,6 +58,13 @@ def measure_fp64_peak(device=0):
     return v.value
 
 
+def measure_fp64_mma_peak(device=0):
+    """Measured FP64 tensor-core (DMMA m8n8k4) peak of the device, TFLOP/s."""
+    v = C.c_double()
+    _check(lib.hc_measure_fp64_mma_peak(device, C.byref(v)))
+    return v.value
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -218,7 +225,7 @@ class Ensemble:
     """B lock-stepped TestHydro instances on one GPU."""
 
     def __init__(self, tables, batch=1, device=0, dt_hint=0.0, bracket_snap=0.0, rad_chunk=0, exc_chunk=0,
-                 use_graph=True, stream=None, exc_lookahead=0, rad_kernel=0):
+                 use_graph=True, stream=None, exc_lookahead=0, rad_kernel=0, rad_lookahead=0):
         self.tables = tables  # keep alive
         o = _capi.EnsembleOpts()
         lib.hc_ensemble_default_opts(C.byref(o))
@@ -226,6 +233,7 @@ class Ensemble:
         o.rad_chunk, o.exc_chunk, o.use_graph = rad_chunk, exc_chunk, int(use_graph)
         o.exc_lookahead = int(exc_lookahead)
         o.rad_kernel = int(rad_kernel)
+        o.rad_lookahead = int(rad_lookahead)
         o.stream = stream
         h = C.c_void_p()
         _check(lib.hc_ensemble_create(tables._h, C.byref(o), C.byref(h)))
@@ -357,6 +365,15 @@ class Ensemble:
         v = [C.c_double() for _ in range(4)]
         _check(lib.hc_get_kernel_ms(self._h, *[C.byref(x) for x in v], int(reset)))
         return dict(zip(("prestep", "radiation", "excitation", "finalize"), [x.value for x in v]))
+
+    def rad_lookahead_steps(self):
+        """Steps per radiation look-ahead block (0: not active)."""
+        return lib.hc_ensemble_rad_lookahead_steps(self._h)
+
+    def rad_block_stats(self, reset=True):
+        n, served, ms = C.c_longlong(), C.c_longlong(), C.c_double()
+        _check(lib.hc_get_rad_block_stats(self._h, C.byref(n), C.byref(served), C.byref(ms), int(reset)))
+        return {"launches": n.value, "steps_served": served.value, "avg_ms": ms.value}
 
     def close(self):
         if getattr(self, "_h", None):

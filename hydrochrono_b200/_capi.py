@@ -41,7 +41,7 @@ class TaperedOpts(C.Structure):
 class EnsembleOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("batch", C.c_int), ("dt_hint", C.c_double), ("bracket_snap", C.c_double),
                 ("rad_chunk", C.c_int), ("exc_chunk", C.c_int), ("use_graph", C.c_int), ("exc_lookahead", C.c_int),
-                ("rad_kernel", C.c_int), ("stream", vp)]
+                ("rad_kernel", C.c_int), ("rad_lookahead", C.c_int), ("stream", vp)]
 
 
 class IrregularParams(C.Structure):
@@ -118,6 +118,9 @@ SIGNATURES = {
     "hc_get_profile": (C.c_int, [vp, C.POINTER(ProfileStats)]),
     "hc_get_kernel_ms": (C.c_int, [vp, dp, dp, dp, dp, C.c_int]),
     "hc_measure_fp64_peak": (C.c_int, [C.c_int, dp]),
+    "hc_measure_fp64_mma_peak": (C.c_int, [C.c_int, dp]),
+    "hc_ensemble_rad_lookahead_steps": (C.c_int, [vp]),
+    "hc_get_rad_block_stats": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp, C.c_int]),
     "hc_host_alloc": (vp, [C.c_size_t]),
     "hc_host_free": (None, [vp]),
     "hc_pierson_moskowitz_spectrum_hz": (C.c_int, [C.c_int, dp, C.c_double, C.c_double, dp]),

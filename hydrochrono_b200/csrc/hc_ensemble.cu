@@ -91,6 +91,23 @@ struct hc_ensemble {
     DevBuf<int> d_pr_lead;
     int rad_chunk = 0, rad_nchunk = 0;
 
+    // radiation look-ahead (D = 12): resident rows' share of the next kRbT steps in one pass (k_rad_block12)
+    bool rb_enabled = false, rb_use = false;      // configured / serving the current step
+    int rb_R = 0, rb_nchunk = 0, rb_m = 1;        // rows per chunk, chunks, history rows per RIRF lag
+    DevBuf<double> d_Kpad, d_rb_partial, d_rb_total;
+    DevBuf<int> d_rb_smax;
+    std::vector<double> rb_scratch;
+    struct RbBlock {
+        double times[kRbT * kRbMaxM]; int smax[kRbT * kRbMaxM];
+        int len = 0, pos = 0, nchunk_used = 0; bool valid = false;
+    } rb;
+    int rb_builds = 0, rb_hits_this_block = 0, rb_poor_blocks = 0;
+    long long rb_launches = 0, rb_steps_served = 0, rb_timed = 0;
+    double rb_ms_sum = 0.0;
+    cudaEvent_t ev_rb[2] = {nullptr, nullptr};
+    bool rb_events_pending = false;
+    int graph_key[3] = {-1, -1, -1};              // what the captured graph of each phase contains
+
     // step I/O
     DevBuf<StepHeader> d_hdr;
     DevBuf<double> d_pose, d_vel, d_force, d_comp, d_wave_tmp;
@@ -145,6 +162,7 @@ struct hc_ensemble {
     cudaEvent_t ev_inputs = nullptr;
     const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
+    int phase1_launches = 0;
     bool phase_uses_lookahead = false;    // set per step: phase 1 skips the per-step excitation kernels
     bool skip_radiation = false;          // wave-only evaluation (hc_waves_force_at_time)
     bool graph1_la = false;               // what the captured phase-1 graph contains
@@ -166,6 +184,7 @@ struct hc_ensemble {
         for (auto& x : ev_la_done) if (x) cudaEventDestroy(x);
         for (auto& x : ev_la_free) if (x) cudaEventDestroy(x);
         if (ev_la_build) cudaEventDestroy(ev_la_build);
+        for (auto& x : ev_rb) if (x) cudaEventDestroy(x);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -181,6 +200,9 @@ struct hc_ensemble {
     void alloc_ring(int new_cap);
     void grow_ring();
     void setup_radiation_chunks();
+    void setup_radiation_block();
+    bool rb_step_plan(const double* tm, int len, double snap, int& smax) const;
+    int radiation_block_slot(double t, StepHeader& hh);
     void enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
     void launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void begin_step(double t, const double* g);
@@ -225,6 +247,16 @@ void hc_ensemble::stage_kernel() {
                     for (int r = 0; r < 4; ++r) o[96 + q * 12 + ks * 4 + r] = kw(8 + r, ks * 4 + q);
         }
         d_Khyb.upload(Kh);
+    }
+    if (rb_enabled) {
+        // [lag][row][col] with lag stride kRbStride, zero beyond lag L - 1 (rows older than the kernel's support)
+        const int lags = rb_nchunk * rb_R + kRbT + 1;
+        std::vector<double> Kp(size_t(lags) * kRbStride, 0.0);
+        for (int s = 0; s < L; ++s)
+            for (int r = 0; r < D; ++r)
+                for (int c = 0; c < D; ++c)
+                    Kp[size_t(s) * kRbStride + r * D + c] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+        d_Kpad.upload(Kp);
     }
 }
 
@@ -295,6 +327,127 @@ void hc_ensemble::setup_radiation_chunks() {
     d_rad_partial.alloc(size_t(rad_nchunk) * D * Bp);
 }
 
+// Radiation look-ahead configuration: m = RIRF lag spacing / step size (an integer), row chunks of R rows per
+// residue class such that (instance tiles x chunks x m) fills whole waves of 3 resident CTAs per SM.
+void hc_ensemble::setup_radiation_block() {
+    rb_enabled = false; rb.valid = false;
+    const int want = opts.rad_lookahead;
+    if (want == 1 || D != 12 || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
+    for (int s = 1; s < L; ++s) if (!(T->rirf_t[s] > T->rirf_t[s - 1])) return;     // lags must ascend
+    const double lag_dt = (T->rirf_t.back() - T->rirf_t.front()) / (L - 1);
+    const long long m = std::llround(lag_dt / opts.dt_hint);
+    if (m < 1 || m > kRbMaxM || std::fabs(lag_dt - double(m) * opts.dt_hint) > 1e-6 * opts.dt_hint) return;
+    const int tiles = Bp / kRbTileInst;
+    if (want == 0 && (tiles < sm_count || !(opts.bracket_snap > 0.0))) return;       // auto: large ensembles only
+    rb_m = int(m);
+    rb_R = pick_chunk(L - 1, tiles * rb_m, sm_count, 3, size_t(74) * 1024, rad_block_smem_bytes, D, 8);
+    rb_nchunk = (L - 1 + rb_R - 1) / rb_R;
+    d_rb_partial.alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+    d_rb_total.alloc(size_t(D) * Bp);
+    d_rb_smax.alloc(kRbT * kRbMaxM);
+    if (!ev_rb[0]) { CUDA_CHECK(cudaEventCreate(&ev_rb[0])); CUDA_CHECK(cudaEventCreate(&ev_rb[1])); }
+    rb_builds = 0; rb_hits_this_block = 0; rb_poor_blocks = 0;
+    rb_enabled = true;
+}
+
+// The radiation plan of one step (k_prestep's bracket arithmetic, same IEEE operations) reduced to the question the
+// block kernel needs answered: does every lag s that has a bracket resolve to exactly history row m s with weight 1?
+// tm[0 .. len) = the time history as it will be at that step, newest first.  smax = the largest lag with a bracket.
+bool hc_ensemble::rb_step_plan(const double* tm, int len, double snap, int& smax) const {
+    smax = -1;
+    if (len <= 1) return false;
+    const double* rt = T->rirf_t.data();
+    const int m = rb_m;
+    const double oldest = tm[len - 1];
+    for (int s = 0; s < L; ++s) {
+        const double q = tm[0] - rt[s];
+        if (!(oldest <= q)) break;                           // no bracket; none for the later (older) lags either
+        auto is_bracket = [&](int i) {                       // smallest i with tm[i+1] <= q
+            return i >= 0 && i + 1 < len && tm[i + 1] <= q && (i == 0 || !(tm[i] <= q));
+        };
+        const int want = m * s;
+        int i;
+        if (is_bracket(want - 1)) i = want - 1;
+        else if (is_bracket(want)) i = want;
+        else return false;
+        const double newer = tm[i], older = tm[i + 1];
+        int row;
+        if (q == older) row = i + 1;
+        else if (q == newer) row = i;
+        else if (q > older && q < newer) {
+            const double delta = newer - older;
+            const double wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
+            const double wn = 1.0 - wo;
+            if (snap > 0.0 && wo <= snap) row = i;
+            else if (snap > 0.0 && wn <= snap) row = i + 1;
+            else return false;
+        } else return false;
+        if (row != want) return false;
+        smax = s;
+    }
+    return smax >= 0;
+}
+
+// Position of the step at time t inside the current radiation block, starting a new block (k_rad_block12 on the main
+// stream) when t is not the predicted next time; -1: the per-step kernels serve this step.  Called after the step's
+// time was pushed onto `times`.
+int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
+    auto fill = [&](int j) {
+        ++rb_steps_served;
+        hh.rad_src = 1; hh.rb_j = j; hh.rb_smax = rb.smax[j]; hh.rb_nchunk = rb.nchunk_used;
+        return j;
+    };
+    if (rb.valid && rb.pos < rb.len && rb.times[rb.pos] == t) { ++rb_hits_this_block; return fill(rb.pos++); }
+    rb.valid = false;
+    if (rb_builds > 0 && rb_hits_this_block < 2) {
+        if (++rb_poor_blocks >= 3) { rb_enabled = false; return -1; }      // unpredictable stepping: stop trying
+    } else {
+        rb_poor_blocks = 0;
+    }
+    rb_hits_this_block = 0;
+    if (times.size() < 2) return -1;
+    // simulate the block's steps on the host: predicted times, PruneHistory, plan purity.
+    // all[] = predicted times newest first, then the current history; step j sees all[TT - 1 - j ...]
+    const int TT = kRbT * rb_m;
+    const double snap = opts.bracket_snap;
+    const double window = T->rirf_t.back();
+    rb_scratch.resize(size_t(TT - 1) + times.size());
+    double* all = rb_scratch.data();
+    std::copy(times.begin(), times.end(), all + (TT - 1));
+    double tp = t;
+    int len = int(times.size());
+    rb.len = 0;
+    for (int j = 0; j < TT; ++j) {
+        double* tm = all + (TT - 1 - j);
+        if (j > 0) {
+            tp = tp + opts.dt_hint;                                         // as Chrono advances ChTime
+            tm[0] = tp;
+            ++len;
+            const double t_min = tp - window;                               // PruneHistory
+            while (len > 1 && tm[len - 2] < t_min) --len;
+        }
+        int smax = -1;
+        if (!rb_step_plan(tm, len, snap, smax)) break;
+        rb.times[j] = tp; rb.smax[j] = smax; rb.len = j + 1;
+    }
+    if (rb.len < TT / 2) { ++rb_builds; return -1; }                        // not worth a block pass
+    for (int j = rb.len; j < TT; ++j) { rb.times[j] = rb.times[rb.len - 1]; rb.smax[j] = -1; }
+    const int n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));      // rows resident before this step's append
+    const int nu = (n_res + rb_m - 1) / rb_m;                               // rows of the fullest residue class
+    rb.nchunk_used = std::max(1, std::min(rb_nchunk, (nu + rb_R - 1) / rb_R));
+    CUDA_CHECK(cudaMemcpyAsync(d_rb_smax.p, rb.smax, TT * sizeof(int), cudaMemcpyHostToDevice, stream));
+    RadBlockArgs ba{};
+    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial.p; ba.smax = d_rb_smax.p;
+    ba.head0 = head; ba.cap = cap; ba.n_res = n_res; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m;
+    if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], stream));
+    CUDA_CHECK(launch_rad_block(ba, rb.nchunk_used, stream));
+    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], stream)); rb_events_pending = true; }
+    prof.kernel_launches += 1;
+    ++rb_builds; ++rb_launches;
+    rb.valid = true; rb.pos = 1; rb_hits_this_block = 1;
+    return fill(0);
+}
+
 // The per-step kernel sequence in two phases.  Phase 1 needs only the step header (time): interpolation plans +
 // excitation convolution.  Phase 2 needs the step's state: history append, radiation convolution, finalize.
 // hc_step overlaps the pose/velocity H2D copy with phase 1.
@@ -318,7 +471,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     }
     if (phase == 1) {
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
-        CUDA_CHECK(launch_prestep(pa, 2, stream));
+        if (!rb_use || per_step_exc) CUDA_CHECK(launch_prestep(pa, 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
         if (per_step_exc) {
             ExcitationArgs ea{};
@@ -331,7 +484,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
             }
         }
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
-        if (!skip_radiation) {
+        if (!skip_radiation && !rb_use) {
             // convolution over the history that is already resident: every row except this step's own sample
             RadiationArgs ra{};
             ra.hdr = d_hdr.p; ra.K = d_K.p; ra.Kfrag = rad_mma ? d_Kfrag.p : nullptr;
@@ -344,7 +497,14 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
         return;
     }
-    CUDA_CHECK(launch_prestep(pa, 1, stream));
+    if (rb_use) {
+        RadStepArgs sa{};
+        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
+        sa.partial = d_rb_partial.p; sa.total = d_rb_total.p; sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
+        CUDA_CHECK(launch_rad_step(sa, stream));
+    } else {
+        CUDA_CHECK(launch_prestep(pa, 1, stream));
+    }
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
 
 
@@ -361,6 +521,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
     fa.exc_cache = d_la_cache.p;
+    fa.rb_total = d_rb_total.p;
     fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
     CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_END], stream));
@@ -381,6 +542,14 @@ void hc_ensemble::collect_events() {
         exc += la;
         la_events_pending = false;
     }
+    if (rb_events_pending) {
+        float rbm = 0;
+        cudaEventElapsedTime(&rbm, ev_rb[0], ev_rb[1]);
+        rad += rbm;
+        rb_ms_sum += rbm; ++rb_timed;
+        rb_events_pending = false;
+    }
+    if (rb_use) { rad += app; app = 0; }      // k_rad_step: append + the block's per-step share
     acc_ms[0] += plan + app; acc_ms[1] += rad; acc_ms[2] += exc; acc_ms[3] += fin;
     ms_steps++;
     events_pending = false;
@@ -399,8 +568,10 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
     }
     cudaGraph_t& g = phase == 1 ? graph1 : graph;
     cudaGraphExec_t& ge = phase == 1 ? graph1_exec : graph_exec;
-    bool valid = phase == 1 ? (graph1_valid && graph1_la == phase_uses_lookahead)
-                            : (graph_valid && graph_pose == d_pose_in && graph_vel == d_vel_in && graph_force == d_force_out);
+    const int key = (phase_uses_lookahead ? 1 : 0) | (rb_use ? 2 : 0) | (skip_radiation ? 4 : 0);
+    bool valid = phase == 1 ? (graph1_valid && graph_key[1] == key)
+                            : (graph_valid && graph_key[2] == key && graph_pose == d_pose_in && graph_vel == d_vel_in &&
+                               graph_force == d_force_out);
     if (!valid) {
         if (ge) cudaGraphExecDestroy(ge);
         if (g) cudaGraphDestroy(g);
@@ -416,6 +587,7 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
         }
         CUDA_CHECK(cudaStreamEndCapture(stream, &g));
         CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+        graph_key[phase] = key;
         if (phase == 1) { graph1_valid = true; graph1_la = phase_uses_lookahead; }
         else { graph_valid = true; graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out; }
     }
@@ -441,7 +613,7 @@ void hc_ensemble::begin_step(double t, const double* g) {
                      std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.");
         }
     }
-    if (int(times.size()) >= cap) grow_ring();
+    if (int(times.size()) >= cap) { grow_ring(); rb.valid = false; }
     times.push_front(t);
     head = (head + 1) % cap;
     const double t_min = t - T->rirf_t.back();                        // history_min_time (:552)
@@ -460,7 +632,13 @@ void hc_ensemble::begin_step(double t, const double* g) {
         const int slot = lookahead_slot(t);
         if (slot >= 0) { hh.exc_src = 1; hh.exc_slot = slot; phase_uses_lookahead = true; }
     }
+    rb_use = false;
+    if (rb_enabled && !skip_radiation) rb_use = radiation_block_slot(t, hh) >= 0;
     CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
+    phase1_launches = 0;
+    const bool per_step_exc = (wave_mode == 2) && !(la_enabled && phase_uses_lookahead);
+    if (rb_use && !per_step_exc && !profiling) return;          // phase 1 is empty
+    phase1_launches = (rb_use ? 0 : 1) + ((rb_use && !per_step_exc) ? 0 : 1) + (per_step_exc ? int(groups.size()) : 0);
     launch_phase(1, nullptr, nullptr, nullptr);
 }
 
@@ -598,7 +776,7 @@ int hc_ensemble::lookahead_slot(double t) {
 
 void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
     launch_phase(2, d_pose_in, d_vel_in, d_force_out);
-    prof.kernel_launches += 4 + ((wave_mode == 2 && !phase_uses_lookahead) ? (long long)groups.size() : 0);
+    prof.kernel_launches += phase1_launches + 2;
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
     force_valid = true;
@@ -625,7 +803,8 @@ int hc_device_count(void) {
 void hc_ensemble_default_opts(hc_ensemble_opts* o) {
     std::memset(o, 0, sizeof(*o));
     o->device = 0; o->batch = 1; o->dt_hint = 0.0; o->bracket_snap = 0.0;
-    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->rad_kernel = 0; o->stream = nullptr;
+    o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->rad_kernel = 0; o->rad_lookahead = 0;
+    o->stream = nullptr;
 }
 
 hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, hc_ensemble** out) {
@@ -657,6 +836,9 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     // up slower (0.319 ms vs 0.274 ms), so auto selects the FMA-pipe kernel
     e->rad_mma = (D == 12) && (opts->rad_kernel == 2);
     e->rad_hybrid = (D == 12) && (opts->rad_kernel == 3);
+    const int lane_tile0 = 32 * kIPT;
+    (void)lane_tile0;
+    e->setup_radiation_block();
     e->stage_kernel();
     e->d_rirf_t.upload(t->rirf_t);
     e->d_rirf_w.upload(t->rirf_w);
@@ -704,6 +886,7 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     e->head = -1;
     if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0;
+    e->rb.valid = false; e->rb_hits_this_block = 0; e->rb_builds = 0; e->rb_poor_blocks = 0;
     e->prev_time = -1.0;
     e->force_valid = false;
     CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
@@ -715,6 +898,8 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
 hc_status hc_ensemble_set_bracket_snap(hc_ensemble* e, double snap) {
     if (!(snap >= 0.0) || snap >= 0.5) { set_last_error("bracket_snap must be in [0, 0.5)"); return HC_ERR_INVALID; }
     e->opts.bracket_snap = snap;     // travels in the per-step header: takes effect at the next step
+    e->rb.valid = false;
+    if (e->d_Kpad.p) { e->rb_enabled = true; e->rb_builds = 0; e->rb_hits_this_block = 0; e->rb_poor_blocks = 0; }
     return HC_OK;
 }
 
@@ -1069,11 +1254,14 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
     hh.t = t; hh.snap = e->opts.bracket_snap; hh.head = e->head < 0 ? 0 : e->head; hh.len = 0; hh.cap = e->cap;
     CUDA_CHECK(cudaMemcpyAsync(e->d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, e->stream));
     const bool saved_la = e->phase_uses_lookahead;
+    const bool saved_rb = e->rb_use;
     e->phase_uses_lookahead = false;                 // always the per-step kernels here
+    e->rb_use = false;
     e->skip_radiation = true;
     e->enqueue_phase(1, nullptr, nullptr, nullptr, false);
     e->skip_radiation = false;
     e->phase_uses_lookahead = saved_la;
+    e->rb_use = saved_rb;
     if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
     FinalizeGroups fg{};
     if (e->wave_mode == 2)
@@ -1192,6 +1380,29 @@ hc_status hc_get_kernel_ms(hc_ensemble* e, double* pre, double* rad, double* exc
 }
 
 // FP64 FMA throughput of the device (TFLOP/s), best of a few launches of a register-resident DFMA loop.
+int hc_ensemble_rad_lookahead_steps(const hc_ensemble* e) { return e->rb_enabled ? kRbT * e->rb_m : 0; }
+
+hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, long long* steps_served, double* avg_ms, int reset) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    if (e->events_pending) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); e->collect_events(); }
+    if (launches) *launches = e->rb_launches;
+    if (steps_served) *steps_served = e->rb_steps_served;
+    if (avg_ms) *avg_ms = e->rb_timed ? e->rb_ms_sum / double(e->rb_timed) : 0.0;
+    if (reset) { e->rb_launches = 0; e->rb_steps_served = 0; e->rb_timed = 0; e->rb_ms_sum = 0.0; }
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_measure_fp64_mma_peak(int device, double* tflops) {
+    HC_GUARD_BEGIN
+    if (!tflops) fail(HC_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(measure_dmma_peak(0.5, tflops));
+    return HC_OK;
+    HC_GUARD_END
+}
+
 hc_status hc_measure_fp64_peak(int device, double* tflops) {
     HC_GUARD_BEGIN
     if (!tflops) fail(HC_ERR_INVALID, "null argument");

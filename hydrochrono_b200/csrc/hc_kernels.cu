@@ -506,6 +506,174 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Radiation look-ahead (D = 12).  When the step times are predictable (t, t + dt, ...) and every lag of every step
+// lands exactly on one history row -- lag s on row m s, m = RIRF lag spacing / dt an integer; the host verifies this
+// per step with the same bracket arithmetic as k_prestep, see hc_ensemble::rb_step_plan -- the steps j = rho + m g
+// (g = 0..7) of a block of 8 m steps all read the resident rows r = m u + (m - 1 - rho), and
+//     F_j = sum_{u >= 0} (K w)[u + g + 1] v_res[m u + m - 1 - rho]     (rows resident when the block starts, r = 0 newest)
+//         + sum_{l <= j / m} (K w)[l] v_young[j - m l]                  (rows appended by the block's own steps)
+// k_rad_block12 evaluates the first sum for all 8 m steps in ONE pass over the history: blockIdx.z = rho, per row and
+// warp a (96 x 12) x (12 x 16) product on the FP64 tensor cores.  M-tile d = the 8 steps of force row d:
+// A[g][c] = (K w)[u + g + 1][d][c], read from a shared-memory tile of R + 7 lags with one conflict-free LDS.64 per
+// fragment (lag stride 148 doubles); B = the history row, one 16-byte load per lane and k-step feeding two N-tiles.
+// HBM traffic per step falls to 1/8 of the per-step kernel's; the kernel is bound by the FP64 tensor pipe.
+// k_rad_step (phase 2 of every step) appends the step's velocities, sums the row-chunk partials in fixed order and
+// adds the second sum (at most 8 rows).
+// ------------------------------------------------------------------------------------------
+size_t rad_block_smem_bytes(int, int R) { return 16 + size_t(R + kRbT - 1) * kRbStride * sizeof(double); }
+
+__global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
+    constexpr int D = 12;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    const double* Ks = reinterpret_cast<const double*>(smem_raw + 16);
+    const int rho = blockIdx.z;
+    const int off = a.m - 1 - rho;                            // first resident row of this residue class
+    const int nu = a.n_res > off ? (a.n_res - off + a.m - 1) / a.m : 0;
+    const int r0 = blockIdx.y * a.R;                          // first u of this chunk
+    const int nr = min(a.R, nu - r0);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)(a.R + kRbT - 1) * kRbStride * sizeof(double);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(const_cast<double*>(Ks), a.Kpad + (size_t)(r0 + 1) * kRbStride, bytes, bar);
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int b0 = blockIdx.x * kRbTileInst + warp * 16;
+    const bool active = b0 < a.Bp;
+    // row u feeds step rho + m g iff its lag u + g + 1 has a bracket at that step
+    const int rmax_g = __ldg(a.smax + rho + a.m * g) - g - 1;
+    int rmax_min = rmax_g;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) rmax_min = min(rmax_min, __shfl_xor_sync(0xffffffffu, rmax_min, o));
+
+    double C[D][2][2];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { C[d][0][0] = C[d][0][1] = C[d][1][0] = C[d][1][1] = 0.0; }
+
+    const size_t row_stride = (size_t)D * a.Bp;
+    const double* hl = a.hist + (size_t)q * a.Bp + (active ? b0 + 2 * g : 0);
+    auto load_row = [&](int u, double2* dst) {
+        int slot = (a.head0 - 1 - off - a.m * u) % a.cap;
+        if (slot < 0) slot += a.cap;
+        const double* p = hl + (size_t)slot * row_stride;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) dst[ks] = __ldg(reinterpret_cast<const double2*>(p + (size_t)(ks * 4) * a.Bp));
+    };
+    double2 cur[3], nxt[3];
+    if (active && nr > 0) load_row(r0, cur);
+    mbar_wait(bar, 0);
+    if (active) {
+        const double* kl = Ks + (size_t)g * kRbStride + q;
+        for (int i = 0; i < nr; ++i) {
+            const int r = r0 + i;
+            if (i + 1 < nr) load_row(r + 1, nxt);
+            const double* kr = kl + (size_t)i * kRbStride;       // lag (r + g + 1) = tile lag i + g
+            if (r <= rmax_min) {
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const double av = kr[d * 12 + ks * 4];
+                        dmma8x8x4(C[d][0][0], C[d][0][1], av, cur[ks].x);
+                        dmma8x8x4(C[d][1][0], C[d][1][1], av, cur[ks].y);
+                    }
+            } else {
+                const bool on = r <= rmax_g;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const double av = on ? kr[d * 12 + ks * 4] : 0.0;
+                        dmma8x8x4(C[d][0][0], C[d][0][1], av, cur[ks].x);
+                        dmma8x8x4(C[d][1][0], C[d][1][1], av, cur[ks].y);
+                    }
+            }
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) cur[ks] = nxt[ks];
+        }
+        // C[d][par][e]: step j = rho + m g, force row d, instance b0 + 2 (2 q + e) + par
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double* o = a.partial + (((size_t)(rho + a.m * g) * a.nchunk + blockIdx.y) * D + d) * a.Bp + b0 + 4 * q;
+            *reinterpret_cast<double2*>(o) = make_double2(C[d][0][0], C[d][1][0]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(C[d][0][1], C[d][1][1]);
+        }
+    }
+}
+
+// One CTA = 32 instances x 12 DoF; thread (b, d).
+constexpr int kRsInst = 32;
+__global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) {
+    constexpr int D = 12;
+    __shared__ double s_K[kRbT * D * D];             // (K w)[lag 0..7][col][row]
+    __shared__ double s_v[kRbT][D][kRsInst];         // young rows, [lag][col][instance]
+    const StepHeader h = *a.hdr;
+    const int j = h.rb_j;
+    const int nl = min(min(j / a.m, h.rb_smax), a.L - 1) + 1;    // young lags 0 .. nl - 1
+    const int tid = threadIdx.x;
+    const int bl = tid % kRsInst, d = tid / kRsInst;
+    const int b0 = blockIdx.x * kRsInst;
+    for (int i = tid; i < nl * D * D; i += blockDim.x) s_K[i] = a.K[i];
+    // this step's sample: the CTA's [32][12] tile of vel is contiguous
+    {
+        const int lb = tid / D, c = tid - lb * D;
+        const int b = b0 + lb;
+        s_v[0][c][lb] = (b < a.B) ? a.vel[(size_t)b * D + c] : 0.0;
+    }
+    const size_t row_stride = (size_t)D * a.Bp;
+    for (int l = 1; l < nl; ++l) {                                // lag l: the row appended m l steps ago
+        int slot = (h.head - a.m * l) % h.cap;
+        if (slot < 0) slot += h.cap;
+        s_v[l][d][bl] = a.hist[(size_t)slot * row_stride + (size_t)d * a.Bp + b0 + bl];
+    }
+    __syncthreads();
+    const int b = b0 + bl;
+    a.hist[(size_t)h.head * row_stride + (size_t)d * a.Bp + b] = s_v[0][d][bl];
+    if (blockIdx.x == 0 && tid == 0) a.times[h.head] = h.t;
+    // fixed-order sum of the row-chunk partials of block step j
+    double fr = 0.0;
+    const double* p = a.partial + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
+    int ch = 0;
+    for (; ch + 4 <= h.rb_nchunk; ch += 4) {
+        const double p0 = p[(size_t)ch * row_stride], p1 = p[(size_t)(ch + 1) * row_stride];
+        const double p2 = p[(size_t)(ch + 2) * row_stride], p3 = p[(size_t)(ch + 3) * row_stride];
+        fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
+    }
+    for (; ch < h.rb_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * row_stride]);
+    for (int l = nl - 1; l >= 0; --l) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc = fma(s_K[(l * D + c) * D + d], s_v[l][c][bl], acc);
+        fr = __dadd_rn(fr, acc);
+    }
+    a.total[(size_t)d * a.Bp + b] = fr;
+}
+
+cudaError_t launch_rad_block(const RadBlockArgs& a, int nchunk_used, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_rad_block12, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    if (nchunk_used <= 0) return cudaSuccess;
+    dim3 grid((a.Bp + kRbTileInst - 1) / kRbTileInst, nchunk_used, a.m);
+    k_rad_block12<<<grid, 128, rad_block_smem_bytes(12, a.R), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st) {
+    k_rad_step<<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // Generic fallback for large body counts: D at run time, 6 rows (one body) per z-slice, K read from global/L2.
 __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationArgs a, const RadPlanPtrs p) {
     const int s0 = blockIdx.y * a.chunk;
@@ -905,7 +1073,9 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
     }
     // ---- radiation: fixed-order sum of lag-chunk partials ----
     double fr = 0.0;
-    if (!a.waves_only) {
+    if (!a.waves_only && h.rad_src == 1) {
+        fr = a.rb_total[(size_t)d * a.Bp + b];                           // k_rad_block12 + k_rad_step
+    } else if (!a.waves_only) {
         const double* p = a.rad_partial + (size_t)d * a.Bp + b;
         const size_t stride = (size_t)D * a.Bp;
         int ch = 0;
@@ -1196,6 +1366,50 @@ cudaError_t measure_dfma_peak(double seconds_budget, double* tflops) {
         cudaEventElapsedTime(&ms, a, b);
         spent += ms * 1e-3;
         const double tf = 2.0 * 8.0 * double(iters) * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    *tflops = best;
+    return e;
+}
+
+// FP64 tensor-core (DMMA m8n8k4) peak: 8 independent accumulator tiles per warp.
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = threadIdx.x - i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma8x8x4(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+cudaError_t measure_dmma_peak(double seconds_budget, double* tflops) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 4, threads = 256, iters = 1 << 12;
+    double* buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, size_t(blocks) * threads * sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0, spent = 0.0;
+    for (int rep = 0; rep < 50 && spent < seconds_budget; ++rep) {
+        cudaEventRecord(a);
+        k_dmma_peak<<<blocks, threads>>>(buf, iters, 1e-3, 1e-3);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        spent += ms * 1e-3;
+        // one m8n8k4 DMMA = 8 * 8 * 4 FMA = 512 flop per warp
+        const double tf = 512.0 * 8.0 * double(iters) * blocks * (threads / 32) / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(a); cudaEventDestroy(b);

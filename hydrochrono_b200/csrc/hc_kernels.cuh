@@ -23,6 +23,10 @@ struct StepHeader {
     int flags;
     int exc_src;       // 0: irregular wave force = sum of this step's lag-chunk partials; 1: look-ahead cache slot
     int exc_slot;
+    int rad_src;       // 0: radiation = this step's lag-chunk partials + head-row share; 1: radiation block (rb_total)
+    int rb_j;          // position of this step inside the radiation block
+    int rb_smax;       // largest lag with a bracket at this step
+    int rb_nchunk;     // row chunks of the block that hold data
 };
 
 struct HydrostaticTables {
@@ -89,6 +93,7 @@ struct FinalizeArgs {
     const double* pr_head;
     int L;
     int waves_only;           // 1: write only the wave force (WaveBase::GetForceAtTime), no state needed
+    const double* rb_total;   // [D][Bp] radiation force of this step when hdr->rad_src == 1
 };
 
 struct EtaArgs {
@@ -168,7 +173,35 @@ struct LookaheadArgs {
     int n_eta, Bp, D, dof0, nd, row0, nchunk;
     int use_mma;              // 1: FP64 tensor-core kernel (taps in fragment order)
 };
+// ---- radiation look-ahead: the share of the resident history rows in the next kRbT steps' convolutions, one pass ----
+constexpr int kRbT = 8;            // steps per M-tile (rows of one DMMA tile); a block covers kRbT * m steps
+constexpr int kRbMaxM = 8;         // largest supported ratio m = RIRF lag spacing / step size
+constexpr int kRbStride = 148;     // doubles per lag of the padded kernel table ([row][col] + 4: conflict-free LDS.64)
+constexpr int kRbTileInst = 64;    // instances per CTA of k_rad_block12
+struct RadBlockArgs {
+    const double* hist;       // [cap][12][Bp]
+    const double* Kpad;       // [lags + pad][kRbStride]  (K w)[lag][row][col], zero beyond the last lag
+    double* partial;          // [kRbT * m][nchunk][12][Bp]
+    const int* smax;          // [kRbT * m] per block step: largest lag with a bracket
+    int head0;                // ring slot of the block's first step (resident row r lives in slot head0 - 1 - r)
+    int cap, n_res, Bp, R, nchunk;
+    int m;                    // history rows per RIRF lag (lag s of a step = history row m s)
+};
+struct RadStepArgs {
+    const StepHeader* hdr;
+    const double* vel;        // [B][12]
+    double* hist;
+    double* times;
+    const double* K;          // [L][col][row]
+    const double* partial;    // [kRbT * m][nchunk][12][Bp]
+    double* total;            // [12][Bp]
+    int B, Bp, nchunk, L, m;
+};
+size_t rad_block_smem_bytes(int, int R);
+cudaError_t launch_rad_block(const RadBlockArgs& a, int nchunk_used, cudaStream_t st);
+cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st);
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
+cudaError_t measure_dmma_peak(double seconds_budget, double* tflops);
 cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);
 cudaError_t launch_lookahead(const LookaheadArgs& a, cudaStream_t st);
 
