@@ -81,7 +81,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
     ap.add_argument("--lookahead-mode", type=int, default=0, help="0 auto (= 5), 2 in-stream, 3 background, 4 in-stream DMMA, 5 background DMMA")
-    ap.add_argument("--rad-lookahead", type=int, default=0, help="radiation look-ahead block (12 DoF): 0 auto (on), 1 off, 2 on")
+    ap.add_argument("--rad-lookahead", type=int, default=0, help="radiation look-ahead block (12 DoF): 0 auto (on, background), 1 off, 2 on (background), 3 on (in-stream)")
     ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only), 3 tensor cores (rows 0-7) + FMA pipe (rows 8-11)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
@@ -271,7 +271,9 @@ def main():
     total_steps = prefill + 2 * (W + K) + 128
     raw = workload_tables()
     T = hc.Tables.from_raw(raw)
-    stream = torch.cuda.Stream(device=dev)          # the ensemble launches on this stream; events are recorded on it
+    # the ensemble launches on this stream and the events are recorded on it; high priority so that the per-step
+    # kernels outrank the look-ahead passes the library runs on its low-priority side streams
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     ens = hc.Ensemble(T, batch=B, device=local_rank, dt_hint=DT, bracket_snap=snap, rad_chunk=args.rad_chunk,
                       exc_chunk=args.exc_chunk, use_graph=not args.no_graph, stream=stream.cuda_stream,
                       exc_lookahead=1 if args.no_lookahead else args.lookahead_mode, rad_kernel=args.rad_kernel, rad_lookahead=args.rad_lookahead)

@@ -5,6 +5,9 @@
 // time values alone, which are shared by every instance, so they run once on the host; everything that touches
 // per-instance data runs in the kernels of hc_kernels.cu.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -94,19 +97,32 @@ struct hc_ensemble {
     // radiation look-ahead (D = 12): resident rows' share of the next kRbT steps in one pass (k_rad_block12)
     bool rb_enabled = false, rb_use = false;      // configured / serving the current step
     int rb_R = 0, rb_nchunk = 0, rb_m = 1;        // rows per chunk, chunks, history rows per RIRF lag
-    DevBuf<double> d_Kpad, d_rb_partial, d_rb_total;
-    DevBuf<int> d_rb_smax;
+    DevBuf<double> d_Kpad, d_rb_partial[2], d_rb_total;
+    DevBuf<int> d_rb_smax[2];
     std::vector<double> rb_scratch;
     struct RbBlock {
         double times[kRbT * kRbMaxM]; int smax[kRbT * kRbMaxM];
-        int len = 0, pos = 0, nchunk_used = 0; bool valid = false;
-    } rb;
+        int len = 0, nchunk_used = 0, base = 0; bool valid = false;
+    } rbk[2];                                     // double-buffered: the block being served / the one evaluated ahead
+    int rb_cur = 0, rb_pos = 0;
+    bool rb_ahead = false;                        // next block evaluated one block ahead, one slice after every step
+    struct RbPass { RadBlockArgs args{}; int items = 0, next_slice = 0, nslices = 0; bool active = false; } rb_pass;
+    cudaStream_t rb_stream = nullptr;             // slices run here, each gated by its step's phase 2
+    cudaEvent_t ev_rb_side = nullptr;             // last slice enqueued on rb_stream
+    bool rb_side_pending = false;
+    bool host_stepping = false;                   // the current step came through hc_step (host buffers)
     int rb_builds = 0, rb_hits_this_block = 0, rb_poor_blocks = 0;
-    long long rb_launches = 0, rb_steps_served = 0, rb_timed = 0;
+    long long rb_launches = 0, rb_steps_served = 0, rb_items_timed = 0;
+    int rb_items_pending = 0, rb_items_per_pass = 0;
     double rb_ms_sum = 0.0;
     cudaEvent_t ev_rb[2] = {nullptr, nullptr};
     bool rb_events_pending = false;
-    int graph_key[3] = {-1, -1, -1};              // what the captured graph of each phase contains
+    int graph_key[3] = {-1, -1, -1};
+    // HC_TRACE=1: device-side timeline of hc_step (H2D, wait for phase 2 to start, phase 2, D2H), printed at destroy
+    bool trace = false;
+    cudaEvent_t ev_tr[6] = {};
+    double tr_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long tr_n = 0;              // what the captured graph of each phase contains
 
     // step I/O
     DevBuf<StepHeader> d_hdr;
@@ -159,7 +175,7 @@ struct hc_ensemble {
     cudaGraphExec_t graph_exec = nullptr, graph1_exec = nullptr;
     bool graph_valid = false, graph1_valid = false;
     cudaStream_t copy_stream = nullptr;                     // H2D of pose/vel overlaps phase 1
-    cudaEvent_t ev_inputs = nullptr;
+    cudaEvent_t ev_inputs = nullptr, ev_force = nullptr;   // state uploaded / forces of the step ready
     const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
     int phase1_launches = 0;
@@ -174,17 +190,25 @@ struct hc_ensemble {
 
     ~hc_ensemble() {
         cudaSetDevice(dev);
+        if (trace && tr_n > 0)
+            fprintf(stderr, "[hc trace] steps %lld  h2d %.1f us  h2d_end->phase2_start %.1f us  phase2 %.1f us  d2h %.1f us  "
+                            "device total %.1f us  host call %.1f us\n", tr_n, 1e3 * tr_ms[0] / tr_n, 1e3 * tr_ms[1] / tr_n,
+                    1e3 * tr_ms[2] / tr_n, 1e3 * tr_ms[3] / tr_n, 1e3 * tr_ms[4] / tr_n, 1e3 * tr_ms[5] / tr_n);
+        for (auto& x : ev_tr) if (x) cudaEventDestroy(x);
         drop_graph();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_inputs) cudaEventDestroy(ev_inputs);
+        if (ev_force) cudaEventDestroy(ev_force);
         if (la_stream) { cudaStreamSynchronize(la_stream); cudaStreamDestroy(la_stream); }
         for (auto& x : ev_la) if (x) cudaEventDestroy(x);
         for (auto& x : ev_la_done) if (x) cudaEventDestroy(x);
         for (auto& x : ev_la_free) if (x) cudaEventDestroy(x);
         if (ev_la_build) cudaEventDestroy(ev_la_build);
         for (auto& x : ev_rb) if (x) cudaEventDestroy(x);
+        if (rb_stream) { cudaStreamSynchronize(rb_stream); cudaStreamDestroy(rb_stream); }
+        if (ev_rb_side) cudaEventDestroy(ev_rb_side);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -203,6 +227,11 @@ struct hc_ensemble {
     void setup_radiation_block();
     bool rb_step_plan(const double* tm, int len, double snap, int& smax) const;
     int radiation_block_slot(double t, StepHeader& hh);
+    int rb_plan_block(RbBlock& Bk, double t, int base);
+    void rb_setup_pass(int buf);
+    void rb_launch_slices(int count, bool side);
+    void rb_begin_ahead(int buf, double t);
+    void rb_invalidate() { rbk[0].valid = rbk[1].valid = false; rb_pos = 0; rb_pass.active = false; }
     void enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
     void launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void begin_step(double t, const double* g);
@@ -250,7 +279,7 @@ void hc_ensemble::stage_kernel() {
     }
     if (rb_enabled) {
         // [lag][row][col] with lag stride kRbStride, zero beyond lag L - 1 (rows older than the kernel's support)
-        const int lags = rb_nchunk * rb_R + kRbT + 1;
+        const int lags = rb_nchunk * rb_R + 2 * kRbT + 1;
         std::vector<double> Kp(size_t(lags) * kRbStride, 0.0);
         for (int s = 0; s < L; ++s)
             for (int r = 0; r < D; ++r)
@@ -330,7 +359,7 @@ void hc_ensemble::setup_radiation_chunks() {
 // Radiation look-ahead configuration: m = RIRF lag spacing / step size (an integer), row chunks of R rows per
 // residue class such that (instance tiles x chunks x m) fills whole waves of 3 resident CTAs per SM.
 void hc_ensemble::setup_radiation_block() {
-    rb_enabled = false; rb.valid = false;
+    rb_enabled = false; rb_invalidate();
     const int want = opts.rad_lookahead;
     if (want == 1 || D != 12 || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
     for (int s = 1; s < L; ++s) if (!(T->rirf_t[s] > T->rirf_t[s - 1])) return;     // lags must ascend
@@ -342,10 +371,19 @@ void hc_ensemble::setup_radiation_block() {
     rb_m = int(m);
     rb_R = pick_chunk(L - 1, tiles * rb_m, sm_count, 3, size_t(74) * 1024, rad_block_smem_bytes, D, 8);
     rb_nchunk = (L - 1 + rb_R - 1) / rb_R;
-    d_rb_partial.alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+    rb_ahead = (want != 3);                                        // 3 = whole pass at the block's first step
+    for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) {
+        d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+        d_rb_smax[i].alloc(kRbT * kRbMaxM);
+    }
     d_rb_total.alloc(size_t(D) * Bp);
-    d_rb_smax.alloc(kRbT * kRbMaxM);
     if (!ev_rb[0]) { CUDA_CHECK(cudaEventCreate(&ev_rb[0])); CUDA_CHECK(cudaEventCreate(&ev_rb[1])); }
+    if (rb_ahead && !rb_stream) {
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority (numerically largest)
+        CUDA_CHECK(cudaStreamCreateWithPriority(&rb_stream, cudaStreamNonBlocking, (lo + hi) / 2));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_rb_side, cudaEventDisableTiming));
+    }
     rb_builds = 0; rb_hits_this_block = 0; rb_poor_blocks = 0;
     rb_enabled = true;
 }
@@ -388,17 +426,127 @@ bool hc_ensemble::rb_step_plan(const double* tm, int len, double snap, int& smax
     return smax >= 0;
 }
 
-// Position of the step at time t inside the current radiation block, starting a new block (k_rad_block12 on the main
-// stream) when t is not the predicted next time; -1: the per-step kernels serve this step.  Called after the step's
-// time was pushed onto `times`.
+// Plans the block whose first step comes `base` steps after the current one (time t, already on `times`): predicted
+// times, PruneHistory and plan purity are simulated on the host.  all[] = predicted times newest first, then the
+// current history; the step jj after the current one sees all[n - 1 - jj ...].  Returns the number of block steps
+// that can be served (every one before the first step that needs a true interpolation).
+int hc_ensemble::rb_plan_block(RbBlock& Bk, double t, int base) {
+    const int TT = kRbT * rb_m, n = base + TT;
+    const double snap = opts.bracket_snap;
+    const double window = T->rirf_t.back();
+    rb_scratch.resize(size_t(n - 1) + times.size());
+    double* all = rb_scratch.data();
+    std::copy(times.begin(), times.end(), all + (n - 1));
+    double tp = t;
+    int len = int(times.size());
+    Bk.len = 0; Bk.base = base; Bk.valid = false;
+    for (int jj = 0; jj < n; ++jj) {
+        double* tm = all + (n - 1 - jj);
+        if (jj > 0) {
+            tp = tp + opts.dt_hint;                                         // as Chrono advances ChTime
+            tm[0] = tp;
+            ++len;
+            const double t_min = tp - window;                               // PruneHistory
+            while (len > 1 && tm[len - 2] < t_min) --len;
+        }
+        if (jj < base) continue;                                            // steps of the block being served
+        int smax = -1;
+        if (!rb_step_plan(tm, len, snap, smax)) break;
+        Bk.times[jj - base] = tp; Bk.smax[jj - base] = smax; Bk.len = jj - base + 1;
+    }
+    for (int j = Bk.len; j < TT; ++j) { Bk.times[j] = Bk.len ? Bk.times[Bk.len - 1] : t; Bk.smax[j] = -1; }
+    const int n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));      // rows resident before this step's append
+    const int nu = (n_res + rb_m - 1) / rb_m;                               // rows of the fullest residue class
+    Bk.nchunk_used = std::max(1, std::min(rb_nchunk, (nu + rb_R - 1) / rb_R));
+    return Bk.len;
+}
+
+// Prepares the pass that evaluates block `buf` from the current snapshot of the history (head, resident rows).
+void hc_ensemble::rb_setup_pass(int buf) {
+    RbBlock& Bk = rbk[buf];
+    const int TT = kRbT * rb_m;
+    CUDA_CHECK(cudaMemcpyAsync(d_rb_smax[buf].p, Bk.smax, TT * sizeof(int), cudaMemcpyHostToDevice, stream));
+    RadBlockArgs& ba = rb_pass.args;
+    ba = RadBlockArgs{};
+    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p; ba.smax = d_rb_smax[buf].p;
+    ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));
+    ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
+    ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;
+    rb_pass.items = rad_block_items(ba);
+    rb_items_per_pass = rb_pass.items;
+    rb_pass.next_slice = 0; rb_pass.nslices = TT; rb_pass.active = true;
+    ++rb_launches;
+    Bk.valid = true;
+}
+
+// Launches the next `count` slices of the pending pass (slice i = items [N i / n, N (i + 1) / n)): on the main stream,
+// or on the side stream behind the step's forces (ev_force) so that the pass never runs ahead of the steps it is
+// interleaved with and the main stream never queues behind it.
+void hc_ensemble::rb_launch_slices(int count, bool side) {
+    if (!rb_pass.active) return;
+    side = side && !profiling && rb_stream;
+    cudaStream_t st = side ? rb_stream : stream;
+    const int s0 = rb_pass.next_slice, s1 = std::min(rb_pass.nslices, s0 + count);
+    // Device-resident stepping (hc_step_device) queues steps back to back: slice boundaries on whole waves of
+    // resident CTAs (3 per SM), so that no slice ends in a nearly empty wave.  Host-buffer stepping (hc_step) leaves
+    // the GPU a window of copies + caller turnaround after every step: equal slices fit that window best.
+    const long long N = rb_pass.items, n = rb_pass.nslices, wave = host_stepping ? 1 : (long long)sm_count * 3;
+    auto cut = [&](int sl) -> int {
+        if (sl >= n) return int(N);
+        const long long x = N * sl / n;
+        return int(std::min(N, (x + wave / 2) / wave * wave));
+    };
+    const int i0 = cut(s0), i1 = cut(s1);
+    rb_pass.next_slice = s1;
+    if (s1 >= rb_pass.nslices) rb_pass.active = false;
+    if (i1 <= i0) return;
+    RadBlockArgs ba = rb_pass.args;
+    ba.item0 = i0;
+    if (side) CUDA_CHECK(cudaStreamWaitEvent(rb_stream, ev_force, 0));
+    if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], st));
+    CUDA_CHECK(launch_rad_block(ba, i1 - i0, st));
+    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], st)); rb_events_pending = true; rb_items_pending = i1 - i0; }
+    if (side) { CUDA_CHECK(cudaEventRecord(ev_rb_side, rb_stream)); rb_side_pending = true; }
+    prof.kernel_launches += 1;
+}
+
+// Look-ahead by one block: at the first step of a block, the NEXT block is planned from the same snapshot of the
+// history (g0 = 8) and its pass is cut into one slice per step of the current block, launched on the main stream
+// right after each step's phase 2 -- underneath the device -> host copy of the step's forces, the caller's turnaround
+// and the next step's host -> device copies.  The ring must not wrap into the snapshot's rows before the pass ends.
+void hc_ensemble::rb_begin_ahead(int buf, double t) {
+    rbk[buf].valid = false;
+    const int TT = kRbT * rb_m;
+    RbBlock& Cur = rbk[buf ^ 1];
+    if (!rb_ahead || !Cur.valid || Cur.len < TT) return;
+    if (int(times.size()) + TT + 2 > cap) return;
+    if (rb_plan_block(rbk[buf], t, TT) < TT / 2) return;
+    rb_setup_pass(buf);
+}
+
+// Position of the step at time t inside the current radiation block, switching to the block evaluated ahead or
+// starting a new one (whole pass on the main stream) when needed; -1: the per-step kernels serve this step.  Called
+// after the step's time was pushed onto `times`.
 int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
+    const int TT = kRbT * rb_m;
     auto fill = [&](int j) {
-        ++rb_steps_served;
-        hh.rad_src = 1; hh.rb_j = j; hh.rb_smax = rb.smax[j]; hh.rb_nchunk = rb.nchunk_used;
+        const RbBlock& Bk = rbk[rb_cur];
+        ++rb_steps_served; ++rb_hits_this_block;
+        hh.rad_src = 1; hh.rb_j = j; hh.rb_jj = Bk.base + j; hh.rb_smax = Bk.smax[j]; hh.rb_nchunk = Bk.nchunk_used;
+        hh.rb_buf = rb_cur;
         return j;
     };
-    if (rb.valid && rb.pos < rb.len && rb.times[rb.pos] == t) { ++rb_hits_this_block; return fill(rb.pos++); }
-    rb.valid = false;
+    RbBlock& Cur = rbk[rb_cur];
+    if (Cur.valid && rb_pos < Cur.len && Cur.times[rb_pos] == t) return fill(rb_pos++);
+    RbBlock& Nxt = rbk[rb_cur ^ 1];
+    if (rb_ahead && Cur.valid && rb_pos == TT && Nxt.valid && !rb_pass.active && Nxt.len > 0 && Nxt.times[0] == t) {
+        rb_cur ^= 1; rb_pos = 0; rb_hits_this_block = 0; rb_poor_blocks = 0;
+        if (rb_side_pending) { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_rb_side, 0)); rb_side_pending = false; }
+        rb_begin_ahead(rb_cur ^ 1, t);
+        return fill(rb_pos++);
+    }
+    // miss: first steps, end of a block that has no successor, or a time the prediction did not foresee
+    rb_invalidate();
     if (rb_builds > 0 && rb_hits_this_block < 2) {
         if (++rb_poor_blocks >= 3) { rb_enabled = false; return -1; }      // unpredictable stepping: stop trying
     } else {
@@ -406,46 +554,14 @@ int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
     }
     rb_hits_this_block = 0;
     if (times.size() < 2) return -1;
-    // simulate the block's steps on the host: predicted times, PruneHistory, plan purity.
-    // all[] = predicted times newest first, then the current history; step j sees all[TT - 1 - j ...]
-    const int TT = kRbT * rb_m;
-    const double snap = opts.bracket_snap;
-    const double window = T->rirf_t.back();
-    rb_scratch.resize(size_t(TT - 1) + times.size());
-    double* all = rb_scratch.data();
-    std::copy(times.begin(), times.end(), all + (TT - 1));
-    double tp = t;
-    int len = int(times.size());
-    rb.len = 0;
-    for (int j = 0; j < TT; ++j) {
-        double* tm = all + (TT - 1 - j);
-        if (j > 0) {
-            tp = tp + opts.dt_hint;                                         // as Chrono advances ChTime
-            tm[0] = tp;
-            ++len;
-            const double t_min = tp - window;                               // PruneHistory
-            while (len > 1 && tm[len - 2] < t_min) --len;
-        }
-        int smax = -1;
-        if (!rb_step_plan(tm, len, snap, smax)) break;
-        rb.times[j] = tp; rb.smax[j] = smax; rb.len = j + 1;
-    }
-    if (rb.len < TT / 2) { ++rb_builds; return -1; }                        // not worth a block pass
-    for (int j = rb.len; j < TT; ++j) { rb.times[j] = rb.times[rb.len - 1]; rb.smax[j] = -1; }
-    const int n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));      // rows resident before this step's append
-    const int nu = (n_res + rb_m - 1) / rb_m;                               // rows of the fullest residue class
-    rb.nchunk_used = std::max(1, std::min(rb_nchunk, (nu + rb_R - 1) / rb_R));
-    CUDA_CHECK(cudaMemcpyAsync(d_rb_smax.p, rb.smax, TT * sizeof(int), cudaMemcpyHostToDevice, stream));
-    RadBlockArgs ba{};
-    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial.p; ba.smax = d_rb_smax.p;
-    ba.head0 = head; ba.cap = cap; ba.n_res = n_res; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m;
-    if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], stream));
-    CUDA_CHECK(launch_rad_block(ba, rb.nchunk_used, stream));
-    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], stream)); rb_events_pending = true; }
-    prof.kernel_launches += 1;
-    ++rb_builds; ++rb_launches;
-    rb.valid = true; rb.pos = 1; rb_hits_this_block = 1;
-    return fill(0);
+    ++rb_builds;
+    if (rb_plan_block(rbk[rb_cur], t, 0) < TT / 2) return -1;              // not worth a block pass
+    if (rb_side_pending) { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_rb_side, 0)); rb_side_pending = false; }
+    rb_setup_pass(rb_cur);
+    rb_launch_slices(TT, false);                                           // the whole pass, now
+    rb_pos = 0;
+    rb_begin_ahead(rb_cur ^ 1, t);
+    return fill(rb_pos++);
 }
 
 // The per-step kernel sequence in two phases.  Phase 1 needs only the step header (time): interpolation plans +
@@ -500,7 +616,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     if (rb_use) {
         RadStepArgs sa{};
         sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
-        sa.partial = d_rb_partial.p; sa.total = d_rb_total.p; sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
+        sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.total = d_rb_total.p; sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
         CUDA_CHECK(launch_rad_step(sa, stream));
     } else {
         CUDA_CHECK(launch_prestep(pa, 1, stream));
@@ -546,7 +662,7 @@ void hc_ensemble::collect_events() {
         float rbm = 0;
         cudaEventElapsedTime(&rbm, ev_rb[0], ev_rb[1]);
         rad += rbm;
-        rb_ms_sum += rbm; ++rb_timed;
+        rb_ms_sum += rbm; rb_items_timed += rb_items_pending;
         rb_events_pending = false;
     }
     if (rb_use) { rad += app; app = 0; }      // k_rad_step: append + the block's per-step share
@@ -613,7 +729,11 @@ void hc_ensemble::begin_step(double t, const double* g) {
                      std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.");
         }
     }
-    if (int(times.size()) >= cap) { grow_ring(); rb.valid = false; }
+    if (int(times.size()) >= cap) {
+        if (rb_stream) CUDA_CHECK(cudaStreamSynchronize(rb_stream));
+        grow_ring();
+        rb_invalidate();
+    }
     times.push_front(t);
     head = (head + 1) % cap;
     const double t_min = t - T->rirf_t.back();                        // history_min_time (:552)
@@ -776,6 +896,8 @@ int hc_ensemble::lookahead_slot(double t) {
 
 void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
     launch_phase(2, d_pose_in, d_vel_in, d_force_out);
+    CUDA_CHECK(cudaEventRecord(ev_force, stream));
+    if (rb_use) rb_launch_slices(1, true);        // this step's share of the next block's pass
     prof.kernel_launches += phase1_launches + 2;
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
@@ -826,10 +948,18 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     const int lane_tile = 32 * kIPT;
     e->Bp = ((e->B + lane_tile - 1) / lane_tile) * lane_tile;
     if (opts->stream) { e->stream = static_cast<cudaStream_t>(opts->stream); }
-    else { CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+    else {
+        int lo = 0, hi = 0;                      // per-step kernels outrank the look-ahead passes on the side streams
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+        e->own_stream = true;
+    }
     for (auto& ev : e->ev) CUDA_CHECK(cudaEventCreate(&ev));
+    if (const char* tr = std::getenv("HC_TRACE")) e->trace = std::atoi(tr) != 0;
+    if (e->trace) for (auto& ev : e->ev_tr) CUDA_CHECK(cudaEventCreate(&ev));
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_inputs, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_force, cudaEventDisableTiming));
 
     const int D = e->D, L = e->L;
     // measured on B200 (profiles/README.md): the DMMA kernel runs below the power cap but pads 12 rows to 16 and ends
@@ -858,6 +988,7 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     const double window = t->rirf_t.back() - t->rirf_t.front();
     double dt = opts->dt_hint > 0.0 ? opts->dt_hint : (t->rirf_t[1] - t->rirf_t[0]);
     int cap = int(std::ceil(window / dt)) + 8;
+    if (e->rb_enabled && e->rb_ahead) cap += kRbT * e->rb_m + 8;   // a pass spread over a block's steps must not be lapped
     cap = std::max(cap, 16);
     e->alloc_ring(cap);
     e->d_pr_new.alloc(L); e->d_pr_old.alloc(L); e->d_pr_wn.alloc(L); e->d_pr_wo.alloc(L); e->d_pr_wd.alloc(L);
@@ -886,7 +1017,8 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     e->head = -1;
     if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0;
-    e->rb.valid = false; e->rb_hits_this_block = 0; e->rb_builds = 0; e->rb_poor_blocks = 0;
+    if (e->rb_stream) CUDA_CHECK(cudaStreamSynchronize(e->rb_stream));
+    e->rb_invalidate(); e->rb_hits_this_block = 0; e->rb_builds = 0; e->rb_poor_blocks = 0;
     e->prev_time = -1.0;
     e->force_valid = false;
     CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
@@ -898,7 +1030,7 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
 hc_status hc_ensemble_set_bracket_snap(hc_ensemble* e, double snap) {
     if (!(snap >= 0.0) || snap >= 0.5) { set_last_error("bracket_snap must be in [0, 0.5)"); return HC_ERR_INVALID; }
     e->opts.bracket_snap = snap;     // travels in the per-step header: takes effect at the next step
-    e->rb.valid = false;
+    e->rb_invalidate();
     if (e->d_Kpad.p) { e->rb_enabled = true; e->rb_builds = 0; e->rb_hits_this_block = 0; e->rb_poor_blocks = 0; }
     return HC_OK;
 }
@@ -1191,6 +1323,7 @@ hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, const d
         if (recomputed) *recomputed = 0;
         return HC_OK;
     }
+    e->host_stepping = false;
     e->begin_step(t, g);
     e->finish_step(t, d_pose, d_vel, e->d_force.p);
     if (d_force != e->d_force.p)
@@ -1207,11 +1340,16 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
     e->use_device();
     const size_t bytes = size_t(e->B) * e->D * sizeof(double);
     int re = 0;
+    const bool tr = e->trace && t != e->prev_time;
+    const auto h0 = std::chrono::steady_clock::now();
     if (t != e->prev_time) {
         // state upload on the copy stream, overlapped with the state-independent phase 1 on the main stream
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[0], e->copy_stream));
         CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, e->copy_stream));
         CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[1], e->copy_stream));
         CUDA_CHECK(cudaEventRecord(e->ev_inputs, e->copy_stream));
+        e->host_stepping = true;
         try {
             e->begin_step(t, g);
         } catch (...) {
@@ -1219,11 +1357,27 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
             throw;
         }
         CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_inputs, 0));
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[2], e->stream));
         e->finish_step(t, e->d_pose.p, e->d_vel.p, e->d_force.p);
         re = 1;
     }
-    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    // forces back on the copy stream: the main stream is free to run look-ahead work queued behind the step
+    CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_force, 0));
+    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[3], e->copy_stream));
+    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[4], e->copy_stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+    if (tr) {
+        float a = 0, b = 0, c = 0, d = 0, f = 0;
+        cudaEventElapsedTime(&a, e->ev_tr[0], e->ev_tr[1]);
+        cudaEventElapsedTime(&b, e->ev_tr[1], e->ev_tr[2]);
+        cudaEventElapsedTime(&c, e->ev_tr[2], e->ev_tr[3]);
+        cudaEventElapsedTime(&d, e->ev_tr[3], e->ev_tr[4]);
+        cudaEventElapsedTime(&f, e->ev_tr[0], e->ev_tr[4]);
+        e->tr_ms[0] += a; e->tr_ms[1] += b; e->tr_ms[2] += c; e->tr_ms[3] += d; e->tr_ms[4] += f;
+        e->tr_ms[5] += 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+        ++e->tr_n;
+    }
     if (e->events_pending) e->collect_events();
     if (recomputed) *recomputed = re;
     return HC_OK;
@@ -1388,8 +1542,9 @@ hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, long long*
     if (e->events_pending) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); e->collect_events(); }
     if (launches) *launches = e->rb_launches;
     if (steps_served) *steps_served = e->rb_steps_served;
-    if (avg_ms) *avg_ms = e->rb_timed ? e->rb_ms_sum / double(e->rb_timed) : 0.0;
-    if (reset) { e->rb_launches = 0; e->rb_steps_served = 0; e->rb_timed = 0; e->rb_ms_sum = 0.0; }
+    // duration of one whole pass, extrapolated from the slices timed while profiling was on
+    if (avg_ms) *avg_ms = e->rb_items_timed ? e->rb_ms_sum / double(e->rb_items_timed) * e->rb_items_per_pass : 0.0;
+    if (reset) { e->rb_launches = 0; e->rb_steps_served = 0; e->rb_items_timed = 0; e->rb_ms_sum = 0.0; }
     return HC_OK;
     HC_GUARD_END
 }

@@ -19,6 +19,7 @@
 // instance-innermost, so a warp reads one contiguous 512-byte segment per (row, dof).  Convolution kernels
 // (K / f*w tiles) are staged per CTA in shared memory with a TMA bulk copy and broadcast to all lanes.
 #include "hc_kernels.cuh"
+#include <cstdlib>
 
 namespace hc {
 
@@ -511,9 +512,12 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
 // lands exactly on one history row -- lag s on row m s, m = RIRF lag spacing / dt an integer; the host verifies this
 // per step with the same bracket arithmetic as k_prestep, see hc_ensemble::rb_step_plan -- the steps j = rho + m g
 // (g = 0..7) of a block of 8 m steps all read the resident rows r = m u + (m - 1 - rho), and
-//     F_j = sum_{u >= 0} (K w)[u + g + 1] v_res[m u + m - 1 - rho]     (rows resident when the block starts, r = 0 newest)
-//         + sum_{l <= j / m} (K w)[l] v_young[j - m l]                  (rows appended by the block's own steps)
-// k_rad_block12 evaluates the first sum for all 8 m steps in ONE pass over the history: blockIdx.z = rho, per row and
+//     F_j = sum_{u >= 0} (K w)[u + g + 1] v_res[m u + m - 1 - rho]     (rows resident at the snapshot, r = 0 newest)
+//         + sum_{l <= j / m} (K w)[l] v_young[j - m l]                  (rows appended since the snapshot)
+// (j counts steps from the snapshot of the history the block works on; a block evaluated in the background one block
+// ahead has j = 8 m + its own step index, i.e. g runs over 8..15: RadBlockArgs::g0)
+// k_rad_block12 evaluates the first sum for all 8 m steps in ONE pass over the history (work item = instance tile x row
+// chunk x residue class rho; a pass can be launched in slices of consecutive items): per row and
 // warp a (96 x 12) x (12 x 16) product on the FP64 tensor cores.  M-tile d = the 8 steps of force row d:
 // A[g][c] = (K w)[u + g + 1][d][c], read from a shared-memory tile of R + 7 lags with one conflict-free LDS.64 per
 // fragment (lag stride 148 doubles); B = the history row, one 16-byte load per lane and k-step feeding two N-tiles.
@@ -528,25 +532,28 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const double* Ks = reinterpret_cast<const double*>(smem_raw + 16);
-    const int rho = blockIdx.z;
+    const int tiles = (a.Bp + kRbTileInst - 1) / kRbTileInst;
+    const int item = a.item0 + blockIdx.x;
+    const int tile = item % tiles, rest = item / tiles;
+    const int chunk = rest % a.nchunk_used, rho = rest / a.nchunk_used;
     const int off = a.m - 1 - rho;                            // first resident row of this residue class
     const int nu = a.n_res > off ? (a.n_res - off + a.m - 1) / a.m : 0;
-    const int r0 = blockIdx.y * a.R;                          // first u of this chunk
+    const int r0 = chunk * a.R;                               // first u of this chunk
     const int nr = min(a.R, nu - r0);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         const uint32_t bytes = (uint32_t)(a.R + kRbT - 1) * kRbStride * sizeof(double);
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(const_cast<double*>(Ks), a.Kpad + (size_t)(r0 + 1) * kRbStride, bytes, bar);
+        bulk_g2s(const_cast<double*>(Ks), a.Kpad + (size_t)(r0 + 1 + a.g0) * kRbStride, bytes, bar);
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int b0 = blockIdx.x * kRbTileInst + warp * 16;
+    const int b0 = tile * kRbTileInst + warp * 16;
     const bool active = b0 < a.Bp;
     // row u feeds step rho + m g iff its lag u + g + 1 has a bracket at that step
-    const int rmax_g = __ldg(a.smax + rho + a.m * g) - g - 1;
+    const int rmax_g = __ldg(a.smax + rho + a.m * g) - (g + a.g0) - 1;
     int rmax_min = rmax_g;
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) rmax_min = min(rmax_min, __shfl_xor_sync(0xffffffffu, rmax_min, o));
@@ -572,7 +579,7 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
         for (int i = 0; i < nr; ++i) {
             const int r = r0 + i;
             if (i + 1 < nr) load_row(r + 1, nxt);
-            const double* kr = kl + (size_t)i * kRbStride;       // lag (r + g + 1) = tile lag i + g
+            const double* kr = kl + (size_t)i * kRbStride;       // lag (r + g0 + g + 1) = tile lag i + g
             if (r <= rmax_min) {
 #pragma unroll
                 for (int ks = 0; ks < 3; ++ks)
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
         // C[d][par][e]: step j = rho + m g, force row d, instance b0 + 2 (2 q + e) + par
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            double* o = a.partial + (((size_t)(rho + a.m * g) * a.nchunk + blockIdx.y) * D + d) * a.Bp + b0 + 4 * q;
+            double* o = a.partial + (((size_t)(rho + a.m * g) * a.nchunk + chunk) * D + d) * a.Bp + b0 + 4 * q;
             *reinterpret_cast<double2*>(o) = make_double2(C[d][0][0], C[d][1][0]);
             *reinterpret_cast<double2*>(o + 2) = make_double2(C[d][0][1], C[d][1][1]);
         }
@@ -608,53 +615,62 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
 
 // One CTA = 32 instances x 12 DoF; thread (b, d).
 constexpr int kRsInst = 32;
+constexpr int kRsLags = 8;                           // young lags staged per pass
 __global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) {
     constexpr int D = 12;
-    __shared__ double s_K[kRbT * D * D];             // (K w)[lag 0..7][col][row]
-    __shared__ double s_v[kRbT][D][kRsInst];         // young rows, [lag][col][instance]
+    __shared__ double s_K[kRsLags * D * D];          // (K w)[lag][col][row]
+    __shared__ double s_v[kRsLags][D][kRsInst];      // young rows, [lag][col][instance]
     const StepHeader h = *a.hdr;
     const int j = h.rb_j;
-    const int nl = min(min(j / a.m, h.rb_smax), a.L - 1) + 1;    // young lags 0 .. nl - 1
+    const int nl = min(min(h.rb_jj / a.m, h.rb_smax), a.L - 1) + 1;   // young lags 0 .. nl - 1
     const int tid = threadIdx.x;
     const int bl = tid % kRsInst, d = tid / kRsInst;
     const int b0 = blockIdx.x * kRsInst;
-    for (int i = tid; i < nl * D * D; i += blockDim.x) s_K[i] = a.K[i];
-    // this step's sample: the CTA's [32][12] tile of vel is contiguous
-    {
-        const int lb = tid / D, c = tid - lb * D;
-        const int b = b0 + lb;
-        s_v[0][c][lb] = (b < a.B) ? a.vel[(size_t)b * D + c] : 0.0;
-    }
-    const size_t row_stride = (size_t)D * a.Bp;
-    for (int l = 1; l < nl; ++l) {                                // lag l: the row appended m l steps ago
-        int slot = (h.head - a.m * l) % h.cap;
-        if (slot < 0) slot += h.cap;
-        s_v[l][d][bl] = a.hist[(size_t)slot * row_stride + (size_t)d * a.Bp + b0 + bl];
-    }
-    __syncthreads();
     const int b = b0 + bl;
-    a.hist[(size_t)h.head * row_stride + (size_t)d * a.Bp + b] = s_v[0][d][bl];
-    if (blockIdx.x == 0 && tid == 0) a.times[h.head] = h.t;
+    const size_t row_stride = (size_t)D * a.Bp;
     // fixed-order sum of the row-chunk partials of block step j
     double fr = 0.0;
-    const double* p = a.partial + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
-    int ch = 0;
-    for (; ch + 4 <= h.rb_nchunk; ch += 4) {
-        const double p0 = p[(size_t)ch * row_stride], p1 = p[(size_t)(ch + 1) * row_stride];
-        const double p2 = p[(size_t)(ch + 2) * row_stride], p3 = p[(size_t)(ch + 3) * row_stride];
-        fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
+    {
+        const double* p = a.partial[h.rb_buf] + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
+        int ch = 0;
+        for (; ch + 4 <= h.rb_nchunk; ch += 4) {
+            const double p0 = p[(size_t)ch * row_stride], p1 = p[(size_t)(ch + 1) * row_stride];
+            const double p2 = p[(size_t)(ch + 2) * row_stride], p3 = p[(size_t)(ch + 3) * row_stride];
+            fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
+        }
+        for (; ch < h.rb_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * row_stride]);
     }
-    for (; ch < h.rb_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * row_stride]);
-    for (int l = nl - 1; l >= 0; --l) {
-        double acc = 0.0;
+    for (int l0 = ((nl - 1) / kRsLags) * kRsLags; l0 >= 0; l0 -= kRsLags) {     // oldest lag group first
+        const int n = min(kRsLags, nl - l0);
+        __syncthreads();
+        for (int i = tid; i < n * D * D; i += blockDim.x) s_K[i] = a.K[(size_t)l0 * D * D + i];
+        for (int l = 0; l < n; ++l) {
+            if (l0 + l == 0) {
+                // this step's sample: the CTA's [32][12] tile of vel is contiguous
+                const int lb = tid / D, c = tid - lb * D;
+                s_v[0][c][lb] = (b0 + lb < a.B) ? a.vel[(size_t)(b0 + lb) * D + c] : 0.0;
+            } else {                                               // lag l: the row appended m l steps ago
+                int slot = (h.head - a.m * (l0 + l)) % h.cap;
+                if (slot < 0) slot += h.cap;
+                s_v[l][d][bl] = a.hist[(size_t)slot * row_stride + (size_t)d * a.Bp + b];
+            }
+        }
+        __syncthreads();
+        if (l0 == 0) {
+            a.hist[(size_t)h.head * row_stride + (size_t)d * a.Bp + b] = s_v[0][d][bl];
+            if (blockIdx.x == 0 && tid == 0) a.times[h.head] = h.t;
+        }
+        for (int l = n - 1; l >= 0; --l) {
+            double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc = fma(s_K[(l * D + c) * D + d], s_v[l][c][bl], acc);
-        fr = __dadd_rn(fr, acc);
+            for (int c = 0; c < D; ++c) acc = fma(s_K[(l * D + c) * D + d], s_v[l][c][bl], acc);
+            fr = __dadd_rn(fr, acc);
+        }
     }
     a.total[(size_t)d * a.Bp + b] = fr;
 }
 
-cudaError_t launch_rad_block(const RadBlockArgs& a, int nchunk_used, cudaStream_t st) {
+cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -663,9 +679,8 @@ cudaError_t launch_rad_block(const RadBlockArgs& a, int nchunk_used, cudaStream_
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
-    if (nchunk_used <= 0) return cudaSuccess;
-    dim3 grid((a.Bp + kRbTileInst - 1) / kRbTileInst, nchunk_used, a.m);
-    k_rad_block12<<<grid, 128, rad_block_smem_bytes(12, a.R), st>>>(a);
+    if (nitems <= 0) return cudaSuccess;
+    k_rad_block12<<<nitems, 128, rad_block_smem_bytes(12, a.R), st>>>(a);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,9 @@ struct StepHeader {
     int rb_j;          // position of this step inside the radiation block
     int rb_smax;       // largest lag with a bracket at this step
     int rb_nchunk;     // row chunks of the block that hold data
+    int rb_jj;         // steps since the block's snapshot of the history (rb_j, or rb_j + block length for a
+                       // block that was evaluated in the background one block ahead)
+    int rb_buf;        // which of the two partial buffers holds the block
 };
 
 struct HydrostaticTables {
@@ -186,6 +189,9 @@ struct RadBlockArgs {
     int head0;                // ring slot of the block's first step (resident row r lives in slot head0 - 1 - r)
     int cap, n_res, Bp, R, nchunk;
     int m;                    // history rows per RIRF lag (lag s of a step = history row m s)
+    int g0;                   // 0: the block starts at the snapshot; kRbT: it starts kRbT * m steps after it
+    int nchunk_used;          // chunks that hold rows; work items = (instance tile, chunk, residue class), tile fastest
+    int item0;                // first work item of this launch (a pass can be cut into slices of consecutive items)
 };
 struct RadStepArgs {
     const StepHeader* hdr;
@@ -193,12 +199,13 @@ struct RadStepArgs {
     double* hist;
     double* times;
     const double* K;          // [L][col][row]
-    const double* partial;    // [kRbT * m][nchunk][12][Bp]
+    const double* partial[2]; // [kRbT * m][nchunk][12][Bp], double-buffered
     double* total;            // [12][Bp]
     int B, Bp, nchunk, L, m;
 };
 size_t rad_block_smem_bytes(int, int R);
-cudaError_t launch_rad_block(const RadBlockArgs& a, int nchunk_used, cudaStream_t st);
+cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st);
+inline int rad_block_items(const RadBlockArgs& a) { return ((a.Bp + kRbTileInst - 1) / kRbTileInst) * a.nchunk_used * a.m; }
 cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st);
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
 cudaError_t measure_dmma_peak(double seconds_budget, double* tflops);

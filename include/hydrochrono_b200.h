@@ -165,7 +165,9 @@ typedef struct hc_ensemble_opts {
                                  tensor cores, 1/8 of the per-step HBM traffic.  Served only for steps whose plan puts
                                  every lag exactly on one history row (uniform stepping on the RIRF grid, within
                                  bracket_snap) and whose time matches the prediction bitwise; other steps run the per-
-                                 step kernel.  0 = auto (on for large ensembles with bracket_snap > 0), 1 = off, 2 = on */
+                                 step kernel.  0 = auto (on for large ensembles with bracket_snap > 0), 1 = off, 2 = on (each
+                                 block is evaluated one block ahead on a low-priority side stream), 3 = on, blocks
+                                 evaluated in the main stream at their first step */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;
 

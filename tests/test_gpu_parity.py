@@ -208,18 +208,19 @@ def test_rm3_irregular_ensemble(rm3, snap, lookahead, rad_kernel):
         assert launches == 1 + 5 * 700, launches
 
 
-@pytest.mark.parametrize("snap,exc_la,m", [(1e-8, 5, 6), (1e-8, 1, 6), (0.0, 1, 6), (1e-8, 1, 1), (1e-8, 4, 2)])
-def test_rm3_radiation_lookahead(rm3, snap, exc_la, m):
+@pytest.mark.parametrize("snap,exc_la,m,rad_la", [(1e-8, 5, 6, 2), (1e-8, 1, 6, 3), (1e-8, 1, 6, 2), (0.0, 1, 6, 2),
+                                                   (1e-8, 1, 1, 2), (1e-8, 4, 2, 3), (1e-8, 1, 2, 2)])
+def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la):
     """Radiation look-ahead (k_rad_block12 + k_rad_step): the resident rows' share of 8 m steps per pass over the
     history, m = RIRF lag spacing / dt.  With snap = 0 and dt = 0.01 the lags are true interpolations, so every step
-    must fall back to the per-step kernel."""
+    must fall back to the per-step kernel.  rad_la = 2: blocks evaluated one block ahead on a side stream; 3: in-stream."""
     if m == 6:
         T, O = rm3
     else:   # lag spacing 0.01 (m = 1) / 0.02 (m = 2): history window shorter than the run, so rows get pruned
         raw = synth.make_tables(num_bodies=2, rirf_steps=401 if m == 1 else 201, rirf_duration=4.0)
         T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
     B = 5
-    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=exc_la, rad_lookahead=2)
+    ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=exc_la, rad_lookahead=rad_la)
     seeds = list(range(3, B + 3))
     ens.set_waves_irregular(seeds=seeds, **IRR)
     insts = []
@@ -235,13 +236,18 @@ def test_rm3_radiation_lookahead(rm3, snap, exc_la, m):
     _assert_parity(tot, rtot, "total")
     assert worst < (1e-11 if snap == 0.0 else 1e-9), worst
     launches = ens.profile()["kernel_launches"]
+    st = ens.rad_block_stats()
     nblocks = -(-699 // (8 * m))
     if snap == 0.0:
-        assert launches == 1 + 5 * 700, launches
-    elif exc_la == 1:     # step 0 per-step (5), then 699 steps of 4 kernels + one block pass per 8 m steps
+        assert launches == 1 + 5 * 700 and st["steps_served"] == 0, (launches, st)
+        return
+    assert st["steps_served"] == 699, st                # every step but the first (empty history)
+    # rad_la = 2 plans one block ahead (one more pass started than blocks served)
+    assert st["launches"] == nblocks + (1 if rad_la == 2 else 0), st
+    if exc_la == 1 and rad_la == 3:     # step 0 per-step (5), then 699 steps of 4 kernels + one whole pass per block
         assert launches == 1 + 5 + 4 * 699 + nblocks, launches
-    else:                 # 2 kernels per step + radiation blocks + excitation blocks (3 kernels each)
-        assert launches <= 1 + 4 + 2 * 699 + nblocks + 3 * 89, launches
+    elif exc_la == 1:                   # + one slice of the next block's pass after every step
+        assert launches <= 1 + 5 + 4 * 699 + 1 + 699, launches
 
 
 @pytest.mark.parametrize("rad_la,snap", [(1, 0.0), (1, 1e-8), (2, 1e-8)])
@@ -274,7 +280,7 @@ def test_rm3_long_run_window_full(rm3, rad_la, snap):
     assert 6000 <= ens.history_len() <= 6003
     if rad_la == 2:
         st = ens.rad_block_stats()
-        assert st["steps_served"] == 6299 and st["launches"] == -(-6299 // 48), st
+        assert st["steps_served"] == 6299 and st["launches"] == -(-6299 // 48) + 1, st
 
 
 def test_regular_waves_two_bodies_phase_quirk(rm3):
