@@ -163,6 +163,7 @@ struct hc_ensemble {
     int la_cur = 0, la_pos = 0;       // block being consumed / next slot expected
     bool la_background = false;       // next block evaluated on a side stream under the current block's steps
     bool la_mma = false;              // look-ahead block on the FP64 tensor cores (DMMA)
+    int la_S = 1;                     // eta-row segments of the DMMA block kernel (partials summed by k_finalize)
     cudaStream_t la_stream = nullptr;
     cudaEvent_t ev_la_done[2] = {nullptr, nullptr}, ev_la_free[2] = {nullptr, nullptr}, ev_la_build = nullptr;
     int la_builds = 0, la_hits_this_block = 0, la_poor_blocks = 0;
@@ -636,7 +637,7 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.reg_amp = d_reg_amp.p; fa.reg_omega = d_reg_omega.p; fa.reg_mag = d_reg_mag.p; fa.reg_phase = d_reg_phase.p;
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
-    fa.exc_cache = d_la_cache.p;
+    fa.exc_cache = d_la_cache.p; fa.exc_S = la_S;
     fa.rb_total = d_rb_total.p;
     fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
     CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
@@ -777,7 +778,19 @@ void hc_ensemble::setup_lookahead() {
     la_background = (want == 0 || want == 3 || want == 5);
     la_mma = (want == 0 || want == 4 || want == 5);
     for (auto& b : la_blk) b.times.assign(kLaT, 0.0);
-    d_la_cache.alloc(size_t(2) * kLaT * D * Bp);
+    // DMMA kernel: (instance tiles x segments) should fill whole waves of 3 resident CTAs per SM, >= 8 stages each
+    la_S = 1;
+    if (la_mma) {
+        const int mtiles = (Bp + 63) / 64, slots = sm_count * 3;
+        int min_stages = 1 << 30;
+        for (auto& G : groups) min_stages = std::min(min_stages, (G->Le + kLaT + 8) / kLaRows + 1);
+        double best = 0.0;
+        for (int S = 1; S <= 24 && min_stages / S >= 8; ++S) {
+            const double w = double(mtiles) * S / slots, eff = w / std::ceil(w);
+            if (eff > best + 0.02) { best = eff; la_S = S; }
+        }
+    }
+    d_la_cache.alloc(size_t(2) * la_S * kLaT * D * Bp);
     d_la_times.alloc(2 * kLaT);
     if (!la_stream) {
         int lo = 0, hi = 0;
@@ -839,7 +852,8 @@ int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
         pa.row0 = row0; pa.nrows = nrows; pa.frag_order = la_mma ? 1 : 0;
         CUDA_CHECK(launch_lookahead_plan(pa, st));
         LookaheadArgs la{};
-        la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * kLaT * D * Bp;
+        la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * la_S * kLaT * D * Bp;
+        la.S = la_mma ? la_S : 1;
         la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = row0;
         la.nchunk = (nrows + kLaRows - 1) / kLaRows; la.use_mma = la_mma ? 1 : 0;
         CUDA_CHECK(launch_lookahead(la, st));

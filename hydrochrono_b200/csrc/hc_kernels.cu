@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(kLaT * 32, 2) k_exc_block(const LookaheadArgs 
 // M-tiles with no padding, N = instances, K = eta rows: per k-step (4 eta rows) a warp issues ND * 2 DMMAs for its 16
 // instances from ONE 16-byte eta load per lane and ND conflict-free LDS.64 of taps; eta is read exactly once.
 template <int ND>
-__global__ void __launch_bounds__(128) k_exc_block_mma(const LookaheadArgs a) {
+__global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a) {
     constexpr int MT = ND;                                   // kLaT * ND / 8 with kLaT == 8
     constexpr int KS = kLaRows / 4;                          // k-steps per stage
     constexpr int kStageDoubles = KS * MT * 32;
@@ -981,12 +981,17 @@ __global__ void __launch_bounds__(128) k_exc_block_mma(const LookaheadArgs a) {
     const int g = lane >> 2, q = lane & 3;
     const int b0 = (blockIdx.x * 4 + warp) * 16;             // 16 instances per warp
     const bool active = b0 < a.Bp;
+    // this CTA's segment of the stages (eta rows): [c0, c1)
+    const int cps = (a.nchunk + a.S - 1) / a.S;
+    const int c0 = blockIdx.y * cps, c1 = min(a.nchunk, c0 + cps);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
-        mbar_expect_tx(&bars[0], kStageBytes);
-        bulk_g2s(stage0, a.taps, kStageBytes, &bars[0]);
+        if (c0 < c1) {
+            mbar_expect_tx(&bars[0], kStageBytes);
+            bulk_g2s(stage0, a.taps + (size_t)c0 * kStageDoubles, kStageBytes, &bars[0]);
+        }
     }
     __syncthreads();
 
@@ -1004,17 +1009,17 @@ __global__ void __launch_bounds__(128) k_exc_block_mma(const LookaheadArgs a) {
         }
     };
     double2 cur[KS], nxt[KS];
-    if (active) load_stage(0, cur);
+    if (active && c0 < c1) load_stage(c0, cur);
 
-    for (int c = 0; c < a.nchunk; ++c) {
-        const int st = c & 1;
-        if (threadIdx.x == 0 && c + 1 < a.nchunk) {
+    for (int c = c0; c < c1; ++c) {
+        const int st = (c - c0) & 1;
+        if (threadIdx.x == 0 && c + 1 < c1) {
             mbar_expect_tx(&bars[st ^ 1], kStageBytes);
             bulk_g2s(stage0 + (st ^ 1) * kStageDoubles, a.taps + (size_t)(c + 1) * kStageDoubles, kStageBytes,
                      &bars[st ^ 1]);
         }
-        if (active && c + 1 < a.nchunk) load_stage(c + 1, nxt);           // eta of the next stage is in flight
-        mbar_wait(&bars[st], (c >> 1) & 1);
+        if (active && c + 1 < c1) load_stage(c + 1, nxt);                 // eta of the next stage is in flight
+        mbar_wait(&bars[st], ((c - c0) >> 1) & 1);
         if (active) {
             const double* tp = reinterpret_cast<const double*>(smem_raw + 16) + (size_t)st * kStageDoubles + lane;
 #pragma unroll
@@ -1033,10 +1038,11 @@ __global__ void __launch_bounds__(128) k_exc_block_mma(const LookaheadArgs a) {
     }
     if (active) {
         // C[mt][par][e]: A row m = mt*8 + g -> (block time m / ND, dof m % ND); instance b0 + 2*(2q + e) + par
+        double* cache = a.cache + (size_t)blockIdx.y * kLaT * a.D * a.Bp;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int m = mt * 8 + g, i = m / ND, d = m - i * ND;
-            double* o = a.cache + ((size_t)i * a.D + a.dof0 + d) * a.Bp + b0 + 4 * q;
+            double* o = cache + ((size_t)i * a.D + a.dof0 + d) * a.Bp + b0 + 4 * q;
             *reinterpret_cast<double2*>(o) = make_double2(C[mt][0][0], C[mt][1][0]);
             *reinterpret_cast<double2*>(o + 2) = make_double2(C[mt][0][1], C[mt][1][1]);
         }
@@ -1118,7 +1124,10 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
         fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
     } else if (a.wave_mode == 2 && h.exc_src == 1) {
-        fw = a.exc_cache[((size_t)h.exc_slot * D + d) * a.Bp + b];       // precomputed by k_exc_block
+        // precomputed by k_exc_block(_mma): slot = buffer * T + block step; S row-segment partials in fixed order
+        const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
+        const double* p = a.exc_cache + (((size_t)buf * a.exc_S * kLaT + pos) * D + d) * a.Bp + b;
+        for (int sg = 0; sg < a.exc_S; ++sg) fw = __dadd_rn(fw, p[(size_t)sg * kLaT * D * a.Bp]);
     } else if (a.wave_mode == 2) {
         for (int g = 0; g < a.exc_ngroups; ++g) {
             if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
@@ -1472,7 +1481,7 @@ static cudaError_t launch_la_mma_t(const LookaheadArgs& a, cudaStream_t st) {
         attr_set[dev & 63] = true;
     }
     const int tiles = (a.Bp + 63) / 64;                      // 4 warps x 16 instances per CTA
-    k_exc_block_mma<ND><<<tiles, 128, smem, st>>>(a);
+    k_exc_block_mma<ND><<<dim3(tiles, a.S, 1), 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 

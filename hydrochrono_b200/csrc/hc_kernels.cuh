@@ -87,7 +87,8 @@ struct FinalizeArgs {
     int wave_mode;            // 0 none, 1 regular, 2 irregular
     int exc_ngroups;
     int exc_ndmax;
-    const double* exc_cache;  // [T][D][Bp] look-ahead block of wave forces (hdr->exc_src == 1)
+    const double* exc_cache;  // [2][S][T][D][Bp] look-ahead blocks of wave forces (hdr->exc_src == 1), S row segments
+    int exc_S;
     // share of this step's own velocity sample in the radiation convolution
     const double* vel;        // [B][D]
     const double* K;          // [L][D][D]  (K w)
@@ -172,9 +173,10 @@ struct LookaheadPlanArgs {
 struct LookaheadArgs {
     const double* eta;        // [n_eta][Bp]
     const double* taps;       // [nchunk][T][kLaRows][nd]
-    double* cache;            // [T][D][Bp]
+    double* cache;            // [S][T][D][Bp]: one partial block per segment of eta rows
     int n_eta, Bp, D, dof0, nd, row0, nchunk;
     int use_mma;              // 1: FP64 tensor-core kernel (taps in fragment order)
+    int S;                    // segments the stages are split into (grid.y of k_exc_block_mma; 1 for k_exc_block)
 };
 // ---- radiation look-ahead: the share of the resident history rows in the next kRbT steps' convolutions, one pass ----
 constexpr int kRbT = 8;            // steps per M-tile (rows of one DMMA tile); a block covers kRbT * m steps

@@ -5,9 +5,10 @@ python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_last.json').read())
 r=d['roofline']
-print('$TAG $ARGS', 'value %.2fM e2e %.2fM ms/step %.4f e2e ms %.4f' % (d['value']/1e6, d['e2e']['value']/1e6, d['ms_per_step'], d['e2e']['ms_per_step']), {k: round(v,4) for k,v in d['kernel_ms'].items()}, 'launch_ms', r.get('launch_ms'), 'frac %.3f' % r['frac'])"
+print('$TAG $ARGS', 'value %.2fM e2e %.2fM ms/step %.4f e2e ms %.4f' % (d['value']/1e6, d['e2e']['value']/1e6, d['ms_per_step'], d['e2e']['ms_per_step']), {k: round(v,4) for k,v in d['kernel_ms'].items()}, 'launch_ms', r.get('launch_ms'), 'frac %.3f' % r['frac'], 'exc frac %.3f' % r['excitation']['frac'])"
 grep "hc trace" gpurun_out/bench_err.log | head -1; tail -2 gpurun_out/bench_err.log | grep -v "hc trace"
 }
-export HC_TRACE=1
-ARGS="--rad-lookahead 2" TAG="gated-waves" run
+ARGS="" TAG="default" run
+ARGS="--rad-lookahead 3" TAG="wholepass" run
+ARGS="--workload sphere_irregular_ensemble" TAG="sphere" run
 true
