@@ -614,16 +614,10 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
         return;
     }
-    if (rb_use) {
-        RadStepArgs sa{};
-        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
-        sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.total = d_rb_total.p; sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
-        CUDA_CHECK(launch_rad_step(sa, stream));
-    } else {
+    if (!rb_use) {
         CUDA_CHECK(launch_prestep(pa, 1, stream));
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
     }
-    if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
-
 
     FinalizeGroups fg{};
     if (wave_mode == 2)
@@ -640,7 +634,17 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.exc_cache = d_la_cache.p; fa.exc_S = la_S;
     fa.rb_total = d_rb_total.p;
     fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
-    CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
+    if (rb_use) {
+        // served by the radiation look-ahead: append + block partials + young rows + finalize in one kernel
+        RadStepArgs sa{};
+        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
+        sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.total = d_rb_total.p;
+        sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
+        CUDA_CHECK(launch_step12(sa, fa, hs, fg, stream));
+        if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
+    } else {
+        CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
+    }
     if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_END], stream));
 }
 
@@ -912,7 +916,7 @@ void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d
     launch_phase(2, d_pose_in, d_vel_in, d_force_out);
     CUDA_CHECK(cudaEventRecord(ev_force, stream));
     if (rb_use) rb_launch_slices(1, true);        // this step's share of the next block's pass
-    prof.kernel_launches += phase1_launches + 2;
+    prof.kernel_launches += phase1_launches + (rb_use ? 1 : 2);
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
     force_valid = true;

@@ -616,7 +616,14 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
 // One CTA = 32 instances x 12 DoF; thread (b, d).
 constexpr int kRsInst = 32;
 constexpr int kRsLags = 8;                           // young lags staged per pass
-__global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) {
+struct FinalizeArgs;
+__device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                                             const StepHeader& h, const int d, const int b, const bool have_fr,
+                                             const double fr_block);
+
+template <bool kFinalize>
+__device__ __forceinline__ void rad_step_body(const RadStepArgs& a, const FinalizeArgs* fa, const HydrostaticTables* hs,
+                                              const FinalizeGroups* eg) {
     constexpr int D = 12;
     __shared__ double s_K[kRsLags * D * D];          // (K w)[lag][col][row]
     __shared__ double s_v[kRsLags][D][kRsInst];      // young rows, [lag][col][instance]
@@ -633,6 +640,13 @@ __global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) 
     {
         const double* p = a.partial[h.rb_buf] + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
         int ch = 0;
+        for (; ch + 8 <= h.rb_nchunk; ch += 8) {              // 8 independent loads in flight, summed in order
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(p + (size_t)(ch + i) * row_stride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fr = __dadd_rn(fr, v[i]);
+        }
         for (; ch + 4 <= h.rb_nchunk; ch += 4) {
             const double p0 = p[(size_t)ch * row_stride], p1 = p[(size_t)(ch + 1) * row_stride];
             const double p2 = p[(size_t)(ch + 2) * row_stride], p3 = p[(size_t)(ch + 3) * row_stride];
@@ -667,7 +681,23 @@ __global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) 
             fr = __dadd_rn(fr, acc);
         }
     }
-    a.total[(size_t)d * a.Bp + b] = fr;
+    if (kFinalize) {
+        if (b < a.B) finalize_one(*fa, *hs, *eg, h, d, b, true, fr);
+    } else {
+        a.total[(size_t)d * a.Bp + b] = fr;
+    }
+}
+
+__global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) {
+    rad_step_body<false>(a, nullptr, nullptr, nullptr);
+}
+
+// k_step12: phase 2 of a step served by the radiation look-ahead in ONE kernel = k_rad_step + k_finalize
+// (append, block partials + young rows, hydrostatics, waves, total).
+__global__ void __launch_bounds__(kRsInst * 12) k_step12(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
+                                                         const __grid_constant__ HydrostaticTables hs,
+                                                         const __grid_constant__ FinalizeGroups eg) {
+    rad_step_body<true>(a, &fa, &hs, &eg);
 }
 
 cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st) {
@@ -686,6 +716,12 @@ cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st)
 
 cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st) {
     k_rad_step<<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step12(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                          cudaStream_t st) {
+    k_step12<<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a, fa, hs, eg);
     return cudaGetLastError();
 }
 
@@ -1053,14 +1089,10 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
 // k_finalize: one thread per instance.
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const HydrostaticTables hs,
-                                                  const FinalizeGroups eg) {
-    // one thread per (dof, instance); instances fastest so the partial reads are coalesced
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = tid / a.Bp;
-    const int b = tid - d * a.Bp;
-    if (d >= a.D || b >= a.B) return;
-    const StepHeader h = *a.hdr;
+// Force of (dof d, instance b).  fr_block: the radiation force when the caller already holds it (k_step12).
+__device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                                             const StepHeader& h, const int d, const int b, const bool have_fr,
+                                             const double fr_block) {
     const int D = a.D;
     const int body = d / 6, i = d - 6 * body;
     const double gx = h.g[0], gy = h.g[1], gz = h.g[2];
@@ -1094,7 +1126,9 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
     }
     // ---- radiation: fixed-order sum of lag-chunk partials ----
     double fr = 0.0;
-    if (!a.waves_only && h.rad_src == 1) {
+    if (!a.waves_only && have_fr) {
+        fr = fr_block;                                                   // k_rad_block12 + this kernel (k_step12)
+    } else if (!a.waves_only && h.rad_src == 1) {
         fr = a.rb_total[(size_t)d * a.Bp + b];                           // k_rad_block12 + k_rad_step
     } else if (!a.waves_only) {
         const double* p = a.rad_partial + (size_t)d * a.Bp + b;
@@ -1127,7 +1161,14 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         // precomputed by k_exc_block(_mma): slot = buffer * T + block step; S row-segment partials in fixed order
         const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
         const double* p = a.exc_cache + (((size_t)buf * a.exc_S * kLaT + pos) * D + d) * a.Bp + b;
-        for (int sg = 0; sg < a.exc_S; ++sg) fw = __dadd_rn(fw, p[(size_t)sg * kLaT * D * a.Bp]);
+        const size_t sstride = (size_t)kLaT * D * a.Bp;
+        int sg = 0;
+        for (; sg + 4 <= a.exc_S; sg += 4) {                     // 4 independent loads in flight, summed in order
+            const double p0 = __ldg(p + (size_t)sg * sstride), p1 = __ldg(p + (size_t)(sg + 1) * sstride);
+            const double p2 = __ldg(p + (size_t)(sg + 2) * sstride), p3 = __ldg(p + (size_t)(sg + 3) * sstride);
+            fw = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fw, p0), p1), p2), p3);
+        }
+        for (; sg < a.exc_S; ++sg) fw = __dadd_rn(fw, p[(size_t)sg * sstride]);
     } else if (a.wave_mode == 2) {
         for (int g = 0; g < a.exc_ngroups; ++g) {
             if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
@@ -1152,6 +1193,17 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const Hy
         a.comp[BD + o] = fr;
         a.comp[2 * BD + o] = fw;
     }
+}
+
+__global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
+                                                  const __grid_constant__ FinalizeGroups eg) {
+    // one thread per (dof, instance); instances fastest so the partial reads are coalesced
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = tid / a.Bp;
+    const int b = tid - d * a.Bp;
+    if (d >= a.D || b >= a.B) return;
+    const StepHeader h = *a.hdr;
+    finalize_one(a, hs, eg, h, d, b, false, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -209,6 +209,8 @@ size_t rad_block_smem_bytes(int, int R);
 cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st);
 inline int rad_block_items(const RadBlockArgs& a) { return ((a.Bp + kRbTileInst - 1) / kRbTileInst) * a.nchunk_used * a.m; }
 cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st);
+cudaError_t launch_step12(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                          cudaStream_t st);
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
 cudaError_t measure_dmma_peak(double seconds_budget, double* tflops);
 cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);

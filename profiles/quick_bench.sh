@@ -1,4 +1,5 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 run() {
 python bench.py --steps 960 --warmup 10 --no-cpu $ARGS 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_last.json
 python -c "
@@ -9,6 +10,5 @@ print('$TAG $ARGS', 'value %.2fM e2e %.2fM ms/step %.4f e2e ms %.4f' % (d['value
 grep "hc trace" gpurun_out/bench_err.log | head -1; tail -2 gpurun_out/bench_err.log | grep -v "hc trace"
 }
 ARGS="" TAG="default" run
-ARGS="--rad-lookahead 3" TAG="wholepass" run
-ARGS="--workload sphere_irregular_ensemble" TAG="sphere" run
+HC_TRACE=1 ARGS="" TAG="default-trace" run
 true

@@ -244,10 +244,10 @@ def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la):
     assert st["steps_served"] == 699, st                # every step but the first (empty history)
     # rad_la = 2 plans one block ahead (one more pass started than blocks served)
     assert st["launches"] == nblocks + (1 if rad_la == 2 else 0), st
-    if exc_la == 1 and rad_la == 3:     # step 0 per-step (5), then 699 steps of 4 kernels + one whole pass per block
-        assert launches == 1 + 5 + 4 * 699 + nblocks, launches
+    if exc_la == 1 and rad_la == 3:     # step 0 per-step (5), then 699 steps of 3 kernels + one whole pass per block
+        assert launches == 1 + 5 + 3 * 699 + nblocks, launches
     elif exc_la == 1:                   # + one slice of the next block's pass after every step
-        assert launches <= 1 + 5 + 4 * 699 + 1 + 699, launches
+        assert launches <= 1 + 5 + 3 * 699 + 1 + 699, launches
 
 
 @pytest.mark.parametrize("rad_la,snap", [(1, 0.0), (1, 1e-8), (2, 1e-8)])
