@@ -451,7 +451,10 @@ def main():
                         "algorithmic_flops_per_launch": blk_flops, "launch_ms": blk_ms, "steps_per_launch": rb_T,
                         "history_bytes_per_launch": hist_bytes,
                         "kernel_ms": kms["radiation"],
-                        "kernel_ms_note": "radiation per step = k_rad_block12 launch / %d + k_rad_step" % rb_T,
+                        "kernel_ms_note": "launch_ms = one whole pass, extrapolated from the per-step slices timed in "
+                                          "the profiling pass (a pass launched whole, --rad-lookahead 3, measures "
+                                          "6.4 ms = 0.95 of the peak: profiles/r01d_radblock.summary.txt); radiation "
+                                          "per step = launch_ms / %d + k_step12" % rb_T,
                         "hbm_view": {"algorithmic_bytes_per_step": rad_bytes, "gbs": ach, "hbm_peak": peak, "frac": ach / peak,
                                      "note": "SURVEY 8(d) bytes of the per-step formulation over the measured radiation "
                                              "time per step: the block pass reads each history row once per %d steps, "
@@ -508,10 +511,12 @@ def main():
                                       "the measured step time; the step needs both resources at once"},
             "kernel_ms": kms,
             "kernel_ms_note": "isolated kernel durations (the profiling pass runs every kernel back-to-back in one "
-                              "stream; excitation = look-ahead block time / 8; radiation = look-ahead block time / "
-                              "steps per block + k_rad_step when the radiation look-ahead is on).  In the timed region the look-ahead "
-                              "block of the NEXT 8 steps runs on a low-priority side stream underneath the per-step "
-                              "kernels, so ms_per_step < sum(kernel_ms)",
+                              "stream).  excitation = look-ahead block time / 8.  With the radiation look-ahead on: "
+                              "radiation = this step's slice of the next block's k_rad_block12 pass + k_step12 (append, "
+                              "block partials, rows appended since the snapshot AND finalize, fused), finalize ~ 0.  "
+                              "In the timed region the excitation block of the next 8 steps and the slices of the next "
+                              "radiation block run on side streams underneath the per-step kernels and the host <-> "
+                              "device copies, so ms_per_step < sum(kernel_ms)",
             "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},
             "checksum": checksum,
             "faithful_bracketing": faithful,
