@@ -182,7 +182,6 @@ struct hc_ensemble {
     int phase1_launches = 0;
     bool phase_uses_lookahead = false;    // set per step: phase 1 skips the per-step excitation kernels
     bool skip_radiation = false;          // wave-only evaluation (hc_waves_force_at_time)
-    bool graph1_la = false;               // what the captured phase-1 graph contains
     cudaEvent_t ev[EV_COUNT] = {};
     hc_profile_stats prof{};
     double acc_ms[4] = {0, 0, 0, 0};
@@ -709,7 +708,7 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
         CUDA_CHECK(cudaStreamEndCapture(stream, &g));
         CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
         graph_key[phase] = key;
-        if (phase == 1) { graph1_valid = true; graph1_la = phase_uses_lookahead; }
+        if (phase == 1) { graph1_valid = true; }
         else { graph_valid = true; graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out; }
     }
     CUDA_CHECK(cudaGraphLaunch(ge, stream));
@@ -984,8 +983,6 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     // up slower (0.319 ms vs 0.274 ms), so auto selects the FMA-pipe kernel
     e->rad_mma = (D == 12) && (opts->rad_kernel == 2);
     e->rad_hybrid = (D == 12) && (opts->rad_kernel == 3);
-    const int lane_tile0 = 32 * kIPT;
-    (void)lane_tile0;
     e->setup_radiation_block();
     e->stage_kernel();
     e->d_rirf_t.upload(t->rirf_t);

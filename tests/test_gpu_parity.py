@@ -508,3 +508,65 @@ def test_large_ensemble_properties(rm3):
         e2.step(t, pose, 2.0 * vel)
     r1, r2 = e1.components()[1], e2.components()[1]
     np.testing.assert_array_equal(2.0 * r1, r2)
+
+
+@pytest.mark.gpu
+def test_large_ensemble_lookahead_paths(rm3):
+    """The bench configuration's kernels at the bench batch size: 16384 instances, dt = 0.01 (6 history rows per RIRF
+    lag), snapped brackets -> radiation look-ahead blocks (k_rad_block12 / k_step12) and excitation look-ahead blocks
+    (k_exc_block_mma) are selected automatically.  Replicated seeds must agree bit for bit, sampled instances must
+    match the oracle, and the radiation term must stay exactly linear in the velocity history."""
+    import torch
+    T, O = rm3
+    B, D, dt = 16384, 12, 0.01
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, bracket_snap=1e-8)
+    assert ens.rad_lookahead_steps() == 48
+    kw = dict(dt=dt, duration=4.0, ramp=1.0, Hs=2.5, Tp=8.0, nfreq=32, gamma=3.3)
+    seeds = np.concatenate([np.arange(1, B // 2 + 1), np.arange(1, B // 2 + 1)]).astype(np.int32)
+    ens.set_waves_irregular(seeds=seeds, **kw)
+    amp, om = synth.prescribed_motion(D)
+    half = B // 2
+    ph = (0.01 * np.arange(half))[:, None]
+    sample = [0, 1, 15, 16, 63, 64, 4095, half - 1]
+    insts = []
+    for b in sample:
+        i = orc.Instance(O)
+        i.set_irregular(seed=int(seeds[b]), share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    nsteps = 260
+    times = _acc_times(nsteps, dt)
+    dev = torch.device("cuda", 0)
+    d_pose = torch.empty((B, D), dtype=torch.float64, device=dev)
+    d_vel = torch.empty_like(d_pose)
+    d_force = torch.empty_like(d_pose)
+    got, want = [], []
+    for n, t in enumerate(times):
+        p = amp * np.sin(om * t + ph)
+        v = amp * om * np.cos(om * t + ph)
+        pose = np.concatenate([p, p])
+        vel = np.concatenate([v, v])
+        d_pose.copy_(torch.from_numpy(pose))
+        d_vel.copy_(torch.from_numpy(vel))
+        torch.cuda.synchronize()
+        ens.step_device(t, d_pose, d_vel, d_force)
+        ens.sync()
+        F = d_force.cpu().numpy()
+        assert np.array_equal(F[:half], F[half:])           # replicas agree bit for bit
+        ref = np.array([i.force(t, pose[b], vel[b], G981) for b, i in zip(sample, insts)])
+        got.append(F[sample].copy()); want.append(ref)
+    _assert_parity(np.array(got), np.array(want), "sampled instances")
+    st = ens.rad_block_stats()
+    assert st["steps_served"] == nsteps - 1, st
+    launches = ens.profile()["kernel_launches"]
+    assert launches < 1 + 5 + 2 * nsteps + 3 * (nsteps // 8 + 2) + 8, launches     # k_step12 + slice per step, blocks
+    ens.close()
+    # exact linearity of the block path in the velocity history
+    e1 = hc.Ensemble(T, batch=64, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
+    e2 = hc.Ensemble(T, batch=64, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
+    for t in _acc_times(120, dt):
+        pose, vel = _motion(D, 64, t)
+        e1.step(t, pose, vel)
+        e2.step(t, pose, 2.0 * vel)
+    assert e1.rad_block_stats()["steps_served"] == 119
+    r1, r2 = e1.components()[1], e2.components()[1]
+    np.testing.assert_array_equal(2.0 * r1, r2)
