@@ -434,7 +434,7 @@ def main():
                     "fp64_tflops": rad_tf, "fp64_peak_tflops": fp64_peak,
                     "fp64_frac": rad_tf / fp64_peak if fp64_peak else None}
         if rb_on:
-            # k_rad_block12: one launch = the resident rows' share of rb_T steps; lags served by the block at block
+            # k_rad_block<12>: one launch = the resident rows' share of rb_T steps; lags served by the block at block
             # step j: (L - 1) - floor(j / m)  (the younger lags belong to k_rad_step)
             m = rb_T // 8
             lag_steps = sum((RIRF_STEPS - 1) - (j // m) for j in range(rb_T))
@@ -442,8 +442,8 @@ def main():
             blk_ms = rb_stats["avg_ms"]
             blk_tf = blk_flops / (blk_ms * 1e-3) / 1e12
             hist_bytes = 8.0 * DOFS * B * m * (RIRF_STEPS - 1)         # every resident row once per block
-            rad_roof = {"bound": "tensor", "kernel": "k_rad_block12 (radiation look-ahead: %d steps per pass over the "
-                                                     "history, FP64 tensor cores, DMMA m8n8k4)" % rb_T,
+            rad_roof = {"bound": "tensor", "kernel": "k_rad_block<%d> (radiation look-ahead: %d steps per pass over the "
+                                                     "history, FP64 tensor cores, DMMA m8n8k4)" % (DOFS, rb_T),
                         "achieved": blk_tf, "peak": mma_peak, "unit": "TFLOP/s", "frac": blk_tf / mma_peak,
                         "traffic": (traffic or {}).get("rad_block_dram_bytes_per_launch"),
                         "peak_source": "FP64 tensor-core peak measured in this run (hc_measure_fp64_mma_peak, DMMA m8n8k4 "
@@ -454,7 +454,7 @@ def main():
                         "kernel_ms_note": "launch_ms = one whole pass, extrapolated from the per-step slices timed in "
                                           "the profiling pass (a pass launched whole, --rad-lookahead 3, measures "
                                           "6.4 ms = 0.95 of the peak: profiles/r01d_radblock.summary.txt); radiation "
-                                          "per step = launch_ms / %d + k_step12" % rb_T,
+                                          "per step = launch_ms / %d + k_step<12>" % rb_T,
                         "hbm_view": {"algorithmic_bytes_per_step": rad_bytes, "gbs": ach, "hbm_peak": peak, "frac": ach / peak,
                                      "note": "SURVEY 8(d) bytes of the per-step formulation over the measured radiation "
                                              "time per step: the block pass reads each history row once per %d steps, "
@@ -512,7 +512,7 @@ def main():
             "kernel_ms": kms,
             "kernel_ms_note": "isolated kernel durations (the profiling pass runs every kernel back-to-back in one "
                               "stream).  excitation = look-ahead block time / 8.  With the radiation look-ahead on: "
-                              "radiation = this step's slice of the next block's k_rad_block12 pass + k_step12 (append, "
+                              "radiation = this step's slice of the next block's k_rad_block<12> pass + k_step<12> (append, "
                               "block partials, rows appended since the snapshot AND finalize, fused), finalize ~ 0.  "
                               "In the timed region the excitation block of the next 8 steps and the slices of the next "
                               "radiation block run on side streams underneath the per-step kernels and the host <-> "

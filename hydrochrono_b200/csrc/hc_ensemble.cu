@@ -94,10 +94,11 @@ struct hc_ensemble {
     DevBuf<int> d_pr_lead;
     int rad_chunk = 0, rad_nchunk = 0;
 
-    // radiation look-ahead (D = 12): resident rows' share of the next kRbT steps in one pass (k_rad_block12)
+    // radiation look-ahead (D = 12): resident rows' share of the next kRbT steps in one pass (k_rad_block<12>)
     bool rb_enabled = false, rb_use = false;      // configured / serving the current step
     int rb_R = 0, rb_nchunk = 0, rb_m = 1;        // rows per chunk, chunks, history rows per RIRF lag
-    DevBuf<double> d_Kpad, d_rb_partial[2], d_rb_total;
+    int rb_occ = 3;
+    DevBuf<double> d_Kpad, d_rb_partial[2];
     DevBuf<int> d_rb_smax[2];
     std::vector<double> rb_scratch;
     struct RbBlock {
@@ -278,13 +279,15 @@ void hc_ensemble::stage_kernel() {
         d_Khyb.upload(Kh);
     }
     if (rb_enabled) {
-        // [lag][row][col] with lag stride kRbStride, zero beyond lag L - 1 (rows older than the kernel's support)
+        // [lag][row][col padded to a multiple of 4], lag stride rb_stride(D), zero beyond lag L - 1 (rows older
+        // than the kernel's support)
         const int lags = rb_nchunk * rb_R + 2 * kRbT + 1;
-        std::vector<double> Kp(size_t(lags) * kRbStride, 0.0);
+        const int stride = rb_stride(D), dp = rb_dp(D);
+        std::vector<double> Kp(size_t(lags) * stride, 0.0);
         for (int s = 0; s < L; ++s)
             for (int r = 0; r < D; ++r)
                 for (int c = 0; c < D; ++c)
-                    Kp[size_t(s) * kRbStride + r * D + c] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+                    Kp[size_t(s) * stride + r * dp + c] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
         d_Kpad.upload(Kp);
     }
 }
@@ -361,7 +364,7 @@ void hc_ensemble::setup_radiation_chunks() {
 void hc_ensemble::setup_radiation_block() {
     rb_enabled = false; rb_invalidate();
     const int want = opts.rad_lookahead;
-    if (want == 1 || D != 12 || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
+    if (want == 1 || (D != 6 && D != 12 && D != 18) || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
     for (int s = 1; s < L; ++s) if (!(T->rirf_t[s] > T->rirf_t[s - 1])) return;     // lags must ascend
     const double lag_dt = (T->rirf_t.back() - T->rirf_t.front()) / (L - 1);
     const long long m = std::llround(lag_dt / opts.dt_hint);
@@ -369,14 +372,15 @@ void hc_ensemble::setup_radiation_block() {
     const int tiles = Bp / kRbTileInst;
     if (want == 0 && (tiles < sm_count || !(opts.bracket_snap > 0.0))) return;       // auto: large ensembles only
     rb_m = int(m);
-    rb_R = pick_chunk(L - 1, tiles * rb_m, sm_count, 3, size_t(74) * 1024, rad_block_smem_bytes, D, 8);
+    rb_occ = (D <= 12) ? 3 : 2;                                    // resident CTAs per SM of k_rad_block<D> (registers)
+    rb_R = pick_chunk(L - 1, tiles * rb_m, sm_count, rb_occ, size_t(rb_occ == 3 ? 74 : 110) * 1024, rad_block_smem_bytes,
+                      D, 8);
     rb_nchunk = (L - 1 + rb_R - 1) / rb_R;
     rb_ahead = (want != 3);                                        // 3 = whole pass at the block's first step
     for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) {
         d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
         d_rb_smax[i].alloc(kRbT * kRbMaxM);
     }
-    d_rb_total.alloc(size_t(D) * Bp);
     if (!ev_rb[0]) { CUDA_CHECK(cudaEventCreate(&ev_rb[0])); CUDA_CHECK(cudaEventCreate(&ev_rb[1])); }
     if (rb_ahead && !rb_stream) {
         int lo = 0, hi = 0;
@@ -470,7 +474,7 @@ void hc_ensemble::rb_setup_pass(int buf) {
     ba = RadBlockArgs{};
     ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p; ba.smax = d_rb_smax[buf].p;
     ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));
-    ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
+    ba.D = D; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
     ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;
     rb_pass.items = rad_block_items(ba);
     rb_items_per_pass = rb_pass.items;
@@ -490,7 +494,7 @@ void hc_ensemble::rb_launch_slices(int count, bool side) {
     // Device-resident stepping (hc_step_device) queues steps back to back: slice boundaries on whole waves of
     // resident CTAs (3 per SM), so that no slice ends in a nearly empty wave.  Host-buffer stepping (hc_step) leaves
     // the GPU a window of copies + caller turnaround after every step: equal slices fit that window best.
-    const long long N = rb_pass.items, n = rb_pass.nslices, wave = host_stepping ? 1 : (long long)sm_count * 3;
+    const long long N = rb_pass.items, n = rb_pass.nslices, wave = host_stepping ? 1 : (long long)sm_count * rb_occ;
     auto cut = [&](int sl) -> int {
         if (sl >= n) return int(N);
         const long long x = N * sl / n;
@@ -631,15 +635,14 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
     fa.exc_cache = d_la_cache.p; fa.exc_S = la_S;
-    fa.rb_total = d_rb_total.p;
     fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
     if (rb_use) {
         // served by the radiation look-ahead: append + block partials + young rows + finalize in one kernel
         RadStepArgs sa{};
         sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
-        sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.total = d_rb_total.p;
+        sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.D = D;
         sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
-        CUDA_CHECK(launch_step12(sa, fa, hs, fg, stream));
+        CUDA_CHECK(launch_step(sa, fa, hs, fg, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
     } else {
         CUDA_CHECK(launch_finalize(fa, hs, fg, stream));

@@ -508,27 +508,29 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
 }
 
 // ------------------------------------------------------------------------------------------
-// Radiation look-ahead (D = 12).  When the step times are predictable (t, t + dt, ...) and every lag of every step
-// lands exactly on one history row -- lag s on row m s, m = RIRF lag spacing / dt an integer; the host verifies this
-// per step with the same bracket arithmetic as k_prestep, see hc_ensemble::rb_step_plan -- the steps j = rho + m g
+// Radiation look-ahead (D = 6, 12, 18).  When the step times are predictable (t, t + dt, ...) and every lag of every
+// step lands exactly on one history row -- lag s on row m s, m = RIRF lag spacing / dt an integer; the host verifies
+// this per step with the same bracket arithmetic as k_prestep, see hc_ensemble::rb_step_plan -- the steps j = rho + m g
 // (g = 0..7) of a block of 8 m steps all read the resident rows r = m u + (m - 1 - rho), and
 //     F_j = sum_{u >= 0} (K w)[u + g + 1] v_res[m u + m - 1 - rho]     (rows resident at the snapshot, r = 0 newest)
 //         + sum_{l <= j / m} (K w)[l] v_young[j - m l]                  (rows appended since the snapshot)
-// (j counts steps from the snapshot of the history the block works on; a block evaluated in the background one block
-// ahead has j = 8 m + its own step index, i.e. g runs over 8..15: RadBlockArgs::g0)
-// k_rad_block12 evaluates the first sum for all 8 m steps in ONE pass over the history (work item = instance tile x row
-// chunk x residue class rho; a pass can be launched in slices of consecutive items): per row and
-// warp a (96 x 12) x (12 x 16) product on the FP64 tensor cores.  M-tile d = the 8 steps of force row d:
+// (j counts steps from the snapshot of the history the block works on; a block evaluated one block ahead has
+// j = 8 m + its own step index, i.e. g runs over 8..15: RadBlockArgs::g0)
+// k_rad_block<D> evaluates the first sum for all 8 m steps in ONE pass over the history (work item = instance tile x
+// row chunk x residue class rho; a pass can be launched in slices of consecutive items): per row and warp a
+// (8 D x D) x (D x 16) product on the FP64 tensor cores.  M-tile d = the 8 steps of force row d:
 // A[g][c] = (K w)[u + g + 1][d][c], read from a shared-memory tile of R + 7 lags with one conflict-free LDS.64 per
-// fragment (lag stride 148 doubles); B = the history row, one 16-byte load per lane and k-step feeding two N-tiles.
-// HBM traffic per step falls to 1/8 of the per-step kernel's; the kernel is bound by the FP64 tensor pipe.
-// k_rad_step (phase 2 of every step) appends the step's velocities, sums the row-chunk partials in fixed order and
-// adds the second sum (at most 8 rows).
+// fragment (lag stride = 4 mod 16 doubles, columns padded to a multiple of 4 with zeros); B = the history row, one
+// 16-byte load per lane and k-step feeding two N-tiles.  HBM traffic per step falls to 1/8 of the per-step kernel's;
+// the kernel is bound by the FP64 tensor pipe.
+// k_step<D> (phase 2 of every step served by a block) appends the step's velocities, sums the row-chunk partials in
+// fixed order, adds the second sum (at most 16 rows) and finishes the step like k_finalize.
 // ------------------------------------------------------------------------------------------
-size_t rad_block_smem_bytes(int, int R) { return 16 + size_t(R + kRbT - 1) * kRbStride * sizeof(double); }
+size_t rad_block_smem_bytes(int D, int R) { return 16 + size_t(R + kRbT - 1) * rb_stride(D) * sizeof(double); }
 
-__global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
-    constexpr int D = 12;
+template <int D>
+__global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadBlockArgs a) {
+    constexpr int KS = (D + 3) / 4, DP = 4 * KS, STRIDE = rb_stride(D);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const double* Ks = reinterpret_cast<const double*>(smem_raw + 16);
@@ -542,9 +544,9 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
     const int nr = min(a.R, nu - r0);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        const uint32_t bytes = (uint32_t)(a.R + kRbT - 1) * kRbStride * sizeof(double);
+        const uint32_t bytes = (uint32_t)(a.R + kRbT - 1) * STRIDE * sizeof(double);
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(const_cast<double*>(Ks), a.Kpad + (size_t)(r0 + 1 + a.g0) * kRbStride, bytes, bar);
+        bulk_g2s(const_cast<double*>(Ks), a.Kpad + (size_t)(r0 + 1 + a.g0) * STRIDE, bytes, bar);
     }
     __syncthreads();
 
@@ -563,45 +565,48 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
     for (int d = 0; d < D; ++d) { C[d][0][0] = C[d][0][1] = C[d][1][0] = C[d][1][1] = 0.0; }
 
     const size_t row_stride = (size_t)D * a.Bp;
-    const double* hl = a.hist + (size_t)q * a.Bp + (active ? b0 + 2 * g : 0);
+    const double* hl = a.hist + (active ? b0 + 2 * g : 0);
     auto load_row = [&](int u, double2* dst) {
         int slot = (a.head0 - 1 - off - a.m * u) % a.cap;
         if (slot < 0) slot += a.cap;
         const double* p = hl + (size_t)slot * row_stride;
 #pragma unroll
-        for (int ks = 0; ks < 3; ++ks) dst[ks] = __ldg(reinterpret_cast<const double2*>(p + (size_t)(ks * 4) * a.Bp));
+        for (int ks = 0; ks < KS; ++ks) {
+            const int c = min(ks * 4 + q, D - 1);            // padded columns: any finite value (their A is zero)
+            dst[ks] = __ldg(reinterpret_cast<const double2*>(p + (size_t)c * a.Bp));
+        }
     };
-    double2 cur[3], nxt[3];
+    double2 cur[KS], nxt[KS];
     if (active && nr > 0) load_row(r0, cur);
     mbar_wait(bar, 0);
     if (active) {
-        const double* kl = Ks + (size_t)g * kRbStride + q;
+        const double* kl = Ks + (size_t)g * STRIDE + q;
         for (int i = 0; i < nr; ++i) {
             const int r = r0 + i;
             if (i + 1 < nr) load_row(r + 1, nxt);
-            const double* kr = kl + (size_t)i * kRbStride;       // lag (r + g0 + g + 1) = tile lag i + g
+            const double* kr = kl + (size_t)i * STRIDE;          // lag (r + g0 + g + 1) = tile lag i + g
             if (r <= rmax_min) {
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
+                for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        const double av = kr[d * 12 + ks * 4];
+                        const double av = kr[d * DP + ks * 4];
                         dmma8x8x4(C[d][0][0], C[d][0][1], av, cur[ks].x);
                         dmma8x8x4(C[d][1][0], C[d][1][1], av, cur[ks].y);
                     }
             } else {
                 const bool on = r <= rmax_g;
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
+                for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        const double av = on ? kr[d * 12 + ks * 4] : 0.0;
+                        const double av = on ? kr[d * DP + ks * 4] : 0.0;
                         dmma8x8x4(C[d][0][0], C[d][0][1], av, cur[ks].x);
                         dmma8x8x4(C[d][1][0], C[d][1][1], av, cur[ks].y);
                     }
             }
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks) cur[ks] = nxt[ks];
+            for (int ks = 0; ks < KS; ++ks) cur[ks] = nxt[ks];
         }
         // C[d][par][e]: step j = rho + m g, force row d, instance b0 + 2 (2 q + e) + par
 #pragma unroll
@@ -613,20 +618,21 @@ __global__ void __launch_bounds__(128, 3) k_rad_block12(const RadBlockArgs a) {
     }
 }
 
-// One CTA = 32 instances x 12 DoF; thread (b, d).
+// k_step<D>: phase 2 of a step served by the radiation look-ahead in ONE kernel (append, block partials + young rows,
+// then hydrostatics, waves and the total as k_finalize).  One CTA = 32 instances x D DoF; thread (b, d).
 constexpr int kRsInst = 32;
-constexpr int kRsLags = 8;                           // young lags staged per pass
 struct FinalizeArgs;
 __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                                              const StepHeader& h, const int d, const int b, const bool have_fr,
                                              const double fr_block);
 
-template <bool kFinalize>
-__device__ __forceinline__ void rad_step_body(const RadStepArgs& a, const FinalizeArgs* fa, const HydrostaticTables* hs,
-                                              const FinalizeGroups* eg) {
-    constexpr int D = 12;
-    __shared__ double s_K[kRsLags * D * D];          // (K w)[lag][col][row]
-    __shared__ double s_v[kRsLags][D][kRsInst];      // young rows, [lag][col][instance]
+template <int D>
+__global__ void __launch_bounds__(kRsInst * D) k_step(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
+                                                      const __grid_constant__ HydrostaticTables hs,
+                                                      const __grid_constant__ FinalizeGroups eg) {
+    constexpr int LAGS = (D <= 12) ? 8 : 4;          // young lags staged per pass
+    __shared__ double s_K[LAGS * D * D];             // (K w)[lag][col][row]
+    __shared__ double s_v[LAGS][D][kRsInst];         // young rows, [lag][col][instance]
     const StepHeader h = *a.hdr;
     const int j = h.rb_j;
     const int nl = min(min(h.rb_jj / a.m, h.rb_smax), a.L - 1) + 1;   // young lags 0 .. nl - 1
@@ -654,13 +660,13 @@ __device__ __forceinline__ void rad_step_body(const RadStepArgs& a, const Finali
         }
         for (; ch < h.rb_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * row_stride]);
     }
-    for (int l0 = ((nl - 1) / kRsLags) * kRsLags; l0 >= 0; l0 -= kRsLags) {     // oldest lag group first
-        const int n = min(kRsLags, nl - l0);
+    for (int l0 = ((nl - 1) / LAGS) * LAGS; l0 >= 0; l0 -= LAGS) {     // oldest lag group first
+        const int n = min(LAGS, nl - l0);
         __syncthreads();
         for (int i = tid; i < n * D * D; i += blockDim.x) s_K[i] = a.K[(size_t)l0 * D * D + i];
         for (int l = 0; l < n; ++l) {
             if (l0 + l == 0) {
-                // this step's sample: the CTA's [32][12] tile of vel is contiguous
+                // this step's sample: the CTA's [32][D] tile of vel is contiguous
                 const int lb = tid / D, c = tid - lb * D;
                 s_v[0][c][lb] = (b0 + lb < a.B) ? a.vel[(size_t)(b0 + lb) * D + c] : 0.0;
             } else {                                               // lag l: the row appended m l steps ago
@@ -681,47 +687,41 @@ __device__ __forceinline__ void rad_step_body(const RadStepArgs& a, const Finali
             fr = __dadd_rn(fr, acc);
         }
     }
-    if (kFinalize) {
-        if (b < a.B) finalize_one(*fa, *hs, *eg, h, d, b, true, fr);
-    } else {
-        a.total[(size_t)d * a.Bp + b] = fr;
-    }
+    if (b < a.B) finalize_one(fa, hs, eg, h, d, b, true, fr);
 }
 
-__global__ void __launch_bounds__(kRsInst * 12) k_rad_step(const RadStepArgs a) {
-    rad_step_body<false>(a, nullptr, nullptr, nullptr);
-}
-
-// k_step12: phase 2 of a step served by the radiation look-ahead in ONE kernel = k_rad_step + k_finalize
-// (append, block partials + young rows, hydrostatics, waves, total).
-__global__ void __launch_bounds__(kRsInst * 12) k_step12(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
-                                                         const __grid_constant__ HydrostaticTables hs,
-                                                         const __grid_constant__ FinalizeGroups eg) {
-    rad_step_body<true>(a, &fa, &hs, &eg);
-}
-
-cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st) {
+template <int D>
+static cudaError_t launch_rad_block_t(const RadBlockArgs& a, int nitems, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_rad_block12, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_rad_block<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
     if (nitems <= 0) return cudaSuccess;
-    k_rad_block12<<<nitems, 128, rad_block_smem_bytes(12, a.R), st>>>(a);
+    k_rad_block<D><<<nitems, 128, rad_block_smem_bytes(D, a.R), st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st) {
-    k_rad_step<<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a);
-    return cudaGetLastError();
+cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st) {
+    switch (a.D) {
+        case 6: return launch_rad_block_t<6>(a, nitems, st);
+        case 12: return launch_rad_block_t<12>(a, nitems, st);
+        case 18: return launch_rad_block_t<18>(a, nitems, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
-cudaError_t launch_step12(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                          cudaStream_t st) {
-    k_step12<<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a, fa, hs, eg);
+cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                        cudaStream_t st) {
+    switch (a.D) {
+        case 6: k_step<6><<<a.Bp / kRsInst, kRsInst * 6, 0, st>>>(a, fa, hs, eg); break;
+        case 12: k_step<12><<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a, fa, hs, eg); break;
+        case 18: k_step<18><<<a.Bp / kRsInst, kRsInst * 18, 0, st>>>(a, fa, hs, eg); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
 // k_finalize: one thread per instance.
 // ------------------------------------------------------------------------------------------
 
-// Force of (dof d, instance b).  fr_block: the radiation force when the caller already holds it (k_step12).
+// Force of (dof d, instance b).  fr_block: the radiation force when the caller already holds it (k_step).
 __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                                              const StepHeader& h, const int d, const int b, const bool have_fr,
                                              const double fr_block) {
@@ -1127,9 +1127,7 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
     // ---- radiation: fixed-order sum of lag-chunk partials ----
     double fr = 0.0;
     if (!a.waves_only && have_fr) {
-        fr = fr_block;                                                   // k_rad_block12 + this kernel (k_step12)
-    } else if (!a.waves_only && h.rad_src == 1) {
-        fr = a.rb_total[(size_t)d * a.Bp + b];                           // k_rad_block12 + k_rad_step
+        fr = fr_block;                                                   // k_rad_block + this kernel (k_step)
     } else if (!a.waves_only) {
         const double* p = a.rad_partial + (size_t)d * a.Bp + b;
         const size_t stride = (size_t)D * a.Bp;

@@ -23,7 +23,7 @@ struct StepHeader {
     int flags;
     int exc_src;       // 0: irregular wave force = sum of this step's lag-chunk partials; 1: look-ahead cache slot
     int exc_slot;
-    int rad_src;       // 0: radiation = this step's lag-chunk partials + head-row share; 1: radiation block (rb_total)
+    int rad_src;       // 0: radiation = this step's lag-chunk partials + head-row share; 1: radiation block (k_step)
     int rb_j;          // position of this step inside the radiation block
     int rb_smax;       // largest lag with a bracket at this step
     int rb_nchunk;     // row chunks of the block that hold data
@@ -97,7 +97,6 @@ struct FinalizeArgs {
     const double* pr_head;
     int L;
     int waves_only;           // 1: write only the wave force (WaveBase::GetForceAtTime), no state needed
-    const double* rb_total;   // [D][Bp] radiation force of this step when hdr->rad_src == 1
 };
 
 struct EtaArgs {
@@ -181,12 +180,17 @@ struct LookaheadArgs {
 // ---- radiation look-ahead: the share of the resident history rows in the next kRbT steps' convolutions, one pass ----
 constexpr int kRbT = 8;            // steps per M-tile (rows of one DMMA tile); a block covers kRbT * m steps
 constexpr int kRbMaxM = 8;         // largest supported ratio m = RIRF lag spacing / step size
-constexpr int kRbStride = 148;     // doubles per lag of the padded kernel table ([row][col] + 4: conflict-free LDS.64)
-constexpr int kRbTileInst = 64;    // instances per CTA of k_rad_block12
+// doubles per lag of the padded kernel table: [row][col padded to a multiple of 4], lag stride = 4 (mod 16) so that
+// the 8 lags x 4 columns of one DMMA A fragment fall into 32 different 8-byte banks
+__host__ __device__ constexpr int rb_dp(int D) { return 4 * ((D + 3) / 4); }
+__host__ __device__ constexpr int rb_stride(int D) { return D * rb_dp(D) + (4 - (D * rb_dp(D)) % 16 + 16) % 16; }
+static_assert(rb_stride(12) == 148 && rb_stride(6) == 52 && rb_stride(18) % 16 == 4, "bank-conflict-free lag stride");
+constexpr int kRbTileInst = 64;    // instances per CTA of k_rad_block
 struct RadBlockArgs {
-    const double* hist;       // [cap][12][Bp]
-    const double* Kpad;       // [lags + pad][kRbStride]  (K w)[lag][row][col], zero beyond the last lag
-    double* partial;          // [kRbT * m][nchunk][12][Bp]
+    const double* hist;       // [cap][D][Bp]
+    const double* Kpad;       // [lags + pad][rb_stride(D)]  (K w)[lag][row][col], zero beyond the last lag
+    double* partial;          // [kRbT * m][nchunk][D][Bp]
+    int D;
     const int* smax;          // [kRbT * m] per block step: largest lag with a bracket
     int head0;                // ring slot of the block's first step (resident row r lives in slot head0 - 1 - r)
     int cap, n_res, Bp, R, nchunk;
@@ -197,20 +201,18 @@ struct RadBlockArgs {
 };
 struct RadStepArgs {
     const StepHeader* hdr;
-    const double* vel;        // [B][12]
+    const double* vel;        // [B][D]
     double* hist;
     double* times;
     const double* K;          // [L][col][row]
-    const double* partial[2]; // [kRbT * m][nchunk][12][Bp], double-buffered
-    double* total;            // [12][Bp]
-    int B, Bp, nchunk, L, m;
+    const double* partial[2]; // [kRbT * m][nchunk][D][Bp], double-buffered
+    int D, B, Bp, nchunk, L, m;
 };
-size_t rad_block_smem_bytes(int, int R);
+size_t rad_block_smem_bytes(int D, int R);
 cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st);
 inline int rad_block_items(const RadBlockArgs& a) { return ((a.Bp + kRbTileInst - 1) / kRbTileInst) * a.nchunk_used * a.m; }
-cudaError_t launch_rad_step(const RadStepArgs& a, cudaStream_t st);
-cudaError_t launch_step12(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                          cudaStream_t st);
+cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                        cudaStream_t st);
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
 cudaError_t measure_dmma_peak(double seconds_budget, double* tflops);
 cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);

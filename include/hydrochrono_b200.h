@@ -160,7 +160,7 @@ typedef struct hc_ensemble_opts {
                                  2 = FP64 tensor cores (DMMA m8n8k4; 12 rows padded to 16: lower power, slower),
                                  3 = both engines: rows 0..7 on the tensor cores, rows 8..11 on the FMA pipe.
                                  Other body counts always use the FMA-pipe kernels. */
-    int rad_lookahead;        /* radiation look-ahead for 6N = 12: the share of the resident history rows in the next 8
+    int rad_lookahead;        /* radiation look-ahead for 6N = 6, 12, 18: the share of the resident history rows in the next 8
                                  (predicted) steps' convolutions is evaluated in one pass over the history on the FP64
                                  tensor cores, 1/8 of the per-step HBM traffic.  Served only for steps whose plan puts
                                  every lag exactly on one history row (uniform stepping on the RIRF grid, within
@@ -271,7 +271,7 @@ HC_API hc_status hc_get_kernel_ms(hc_ensemble* e, double* prestep_ms, double* ra
                                   double* finalize_ms, int reset);
 
 /* Radiation look-ahead (hc_ensemble_opts.rad_lookahead): steps per block (8 m, m = RIRF lag spacing / dt_hint), 0 when
-   the path is not configured or switched itself off.  hc_get_rad_block_stats: k_rad_block12 launches so far, how many
+   the path is not configured or switched itself off.  hc_get_rad_block_stats: k_rad_block<12> launches so far, how many
    steps they served, and the average launch duration in ms over the launches timed while profiling was on. */
 HC_API int hc_ensemble_rad_lookahead_steps(const hc_ensemble* e);
 HC_API hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, long long* steps_served, double* avg_ms,

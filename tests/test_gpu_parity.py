@@ -208,17 +208,21 @@ def test_rm3_irregular_ensemble(rm3, snap, lookahead, rad_kernel):
         assert launches == 1 + 5 * 700, launches
 
 
-@pytest.mark.parametrize("snap,exc_la,m,rad_la", [(1e-8, 5, 6, 2), (1e-8, 1, 6, 3), (1e-8, 1, 6, 2), (0.0, 1, 6, 2),
-                                                   (1e-8, 1, 1, 2), (1e-8, 4, 2, 3), (1e-8, 1, 2, 2)])
-def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la):
-    """Radiation look-ahead (k_rad_block12 + k_rad_step): the resident rows' share of 8 m steps per pass over the
+@pytest.mark.parametrize("snap,exc_la,m,rad_la,nb", [(1e-8, 5, 6, 2, 2), (1e-8, 1, 6, 3, 2), (1e-8, 1, 6, 2, 2),
+                                                      (0.0, 1, 6, 2, 2), (1e-8, 1, 1, 2, 2), (1e-8, 4, 2, 3, 2),
+                                                      (1e-8, 1, 2, 2, 2), (1e-8, 1, 1, 2, 1), (1e-8, 5, 2, 2, 1),
+                                                      (1e-8, 1, 2, 2, 3), (1e-8, 5, 1, 3, 3)])
+def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la, nb):
+    """Radiation look-ahead (k_rad_block<12> + k_rad_step): the resident rows' share of 8 m steps per pass over the
     history, m = RIRF lag spacing / dt.  With snap = 0 and dt = 0.01 the lags are true interpolations, so every step
     must fall back to the per-step kernel.  rad_la = 2: blocks evaluated one block ahead on a side stream; 3: in-stream."""
     if m == 6:
         T, O = rm3
-    else:   # lag spacing 0.01 (m = 1) / 0.02 (m = 2): history window shorter than the run, so rows get pruned
-        raw = synth.make_tables(num_bodies=2, rirf_steps=401 if m == 1 else 201, rirf_duration=4.0)
+    else:   # lag spacing 0.01 (m = 1) / 0.02 (m = 2): history window shorter than the run, so rows get pruned;
+        #     nb = 1 / 2 / 3 bodies = the D = 6 / 12 / 18 instantiations of k_rad_block and k_step
+        raw = synth.make_tables(num_bodies=nb, rirf_steps=401 if m == 1 else 201, rirf_duration=4.0)
         T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    D = 6 * nb
     B = 5
     ens = hc.Ensemble(T, batch=B, dt_hint=0.01, bracket_snap=snap, exc_lookahead=exc_la, rad_lookahead=rad_la)
     seeds = list(range(3, B + 3))
@@ -229,7 +233,7 @@ def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la):
         i.set_irregular(seed=seeds[b], share_irf_from=insts[0] if insts else None, **IRR)
         insts.append(i)
     times = _acc_times(700, 0.01)
-    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, D)
     np.testing.assert_array_equal(hs, rhs)
     worst = _assert_parity(rad, rrad, "radiation")
     _assert_parity(wv, rwv, "irregular excitation")
@@ -237,17 +241,18 @@ def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la):
     assert worst < (1e-11 if snap == 0.0 else 1e-9), worst
     launches = ens.profile()["kernel_launches"]
     st = ens.rad_block_stats()
+    ngroups = 3 if nb == 3 else 1       # excitation IRF groups: bodies merged for D = 6 / 12, one per body otherwise
     nblocks = -(-699 // (8 * m))
     if snap == 0.0:
-        assert launches == 1 + 5 * 700 and st["steps_served"] == 0, (launches, st)
+        assert launches == 1 + (4 + ngroups) * 700 and st["steps_served"] == 0, (launches, st)
         return
     assert st["steps_served"] == 699, st                # every step but the first (empty history)
     # rad_la = 2 plans one block ahead (one more pass started than blocks served)
     assert st["launches"] == nblocks + (1 if rad_la == 2 else 0), st
     if exc_la == 1 and rad_la == 3:     # step 0 per-step (5), then 699 steps of 3 kernels + one whole pass per block
-        assert launches == 1 + 5 + 3 * 699 + nblocks, launches
+        assert launches == 1 + (4 + ngroups) + (2 + ngroups) * 699 + nblocks, launches
     elif exc_la == 1:                   # + one slice of the next block's pass after every step
-        assert launches <= 1 + 5 + 3 * 699 + 1 + 699, launches
+        assert launches <= 1 + (4 + ngroups) + (2 + ngroups) * 699 + 1 + 699, launches
 
 
 @pytest.mark.parametrize("rad_la,snap", [(1, 0.0), (1, 1e-8), (2, 1e-8)])
@@ -513,7 +518,7 @@ def test_large_ensemble_properties(rm3):
 @pytest.mark.gpu
 def test_large_ensemble_lookahead_paths(rm3):
     """The bench configuration's kernels at the bench batch size: 16384 instances, dt = 0.01 (6 history rows per RIRF
-    lag), snapped brackets -> radiation look-ahead blocks (k_rad_block12 / k_step12) and excitation look-ahead blocks
+    lag), snapped brackets -> radiation look-ahead blocks (k_rad_block<12> / k_step<12>) and excitation look-ahead blocks
     (k_exc_block_mma) are selected automatically.  Replicated seeds must agree bit for bit, sampled instances must
     match the oracle, and the radiation term must stay exactly linear in the velocity history."""
     import torch
@@ -558,7 +563,7 @@ def test_large_ensemble_lookahead_paths(rm3):
     st = ens.rad_block_stats()
     assert st["steps_served"] == nsteps - 1, st
     launches = ens.profile()["kernel_launches"]
-    assert launches < 1 + 5 + 2 * nsteps + 3 * (nsteps // 8 + 2) + 8, launches     # k_step12 + slice per step, blocks
+    assert launches < 1 + 5 + 2 * nsteps + 3 * (nsteps // 8 + 2) + 8, launches     # k_step<12> + slice per step, blocks
     ens.close()
     # exact linearity of the block path in the velocity history
     e1 = hc.Ensemble(T, batch=64, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
