@@ -98,6 +98,10 @@ struct hc_ensemble {
     bool rb_enabled = false, rb_use = false;      // configured / serving the current step
     int rb_R = 0, rb_nchunk = 0, rb_m = 1;        // rows per chunk, chunks, history rows per RIRF lag
     int rb_occ = 3;
+    bool rb_general = false;                      // RIRF lag spacing is not a multiple of dt: row-grid kernel (below)
+    int rb_Lk = 0;                                // lags of the kernel the block path convolves with (L, or row grid)
+    std::vector<double> rb_pnom;                  // [L] nominal position of every lag in history rows (rirf_t / dt)
+    DevBuf<double> d_Kyoung;                      // first 2 kRbT lags of that kernel, [lag][col][row] (k_step)
     DevBuf<double> d_Kpad, d_rb_partial[2];
     DevBuf<int> d_rb_smax[2];
     std::vector<double> rb_scratch;
@@ -279,16 +283,41 @@ void hc_ensemble::stage_kernel() {
         d_Khyb.upload(Kh);
     }
     if (rb_enabled) {
-        // [lag][row][col padded to a multiple of 4], lag stride rb_stride(D), zero beyond lag L - 1 (rows older
-        // than the kernel's support)
+        // The kernel the block path convolves the history ROWS with, Krow[i][r][c], i = rows back.  Lag spacing a
+        // multiple of dt: Krow = (K w) on the lag grid (row m s <-> lag s).  Otherwise the linear interpolation of the
+        // velocity between rows i and i + 1 at the nominal position x_s = t_rirf[s] / dt = i + wo is folded into the
+        // kernel:  (K w)[s] (wn v_i + wo v_{i+1})  ->  Krow[i] += wn (K w)[s],  Krow[i + 1] += wo (K w)[s].
+        std::vector<double> Krow(size_t(rb_Lk) * D * D, 0.0);
+        for (int s = 0; s < L; ++s) {
+            int i = s;
+            double wn = 1.0, wo = 0.0;
+            if (rb_general) {
+                i = int(std::floor(rb_pnom[s]));
+                wo = rb_pnom[s] - double(i);
+                wn = 1.0 - wo;
+            }
+            for (int r = 0; r < D; ++r)
+                for (int c = 0; c < D; ++c) {
+                    const double kw = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+                    if (i < rb_Lk) Krow[(size_t(i) * D + r) * D + c] += wn * kw;
+                    if (wo != 0.0 && i + 1 < rb_Lk) Krow[(size_t(i + 1) * D + r) * D + c] += wo * kw;
+                }
+        }
+        // device copies: [lag][row][col padded to a multiple of 4] with lag stride rb_stride(D), zero beyond the last
+        // lag (rows older than the kernel's support), and the first lags as [lag][col][row] for k_step
         const int lags = rb_nchunk * rb_R + 2 * kRbT + 1;
         const int stride = rb_stride(D), dp = rb_dp(D);
         std::vector<double> Kp(size_t(lags) * stride, 0.0);
-        for (int s = 0; s < L; ++s)
+        for (int i = 0; i < rb_Lk; ++i)
             for (int r = 0; r < D; ++r)
-                for (int c = 0; c < D; ++c)
-                    Kp[size_t(s) * stride + r * dp + c] = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
+                for (int c = 0; c < D; ++c) Kp[size_t(i) * stride + r * dp + c] = Krow[(size_t(i) * D + r) * D + c];
         d_Kpad.upload(Kp);
+        const int ny = 2 * kRbT;
+        std::vector<double> Ky(size_t(ny) * D * D, 0.0);
+        for (int i = 0; i < std::min(ny, rb_Lk); ++i)
+            for (int r = 0; r < D; ++r)
+                for (int c = 0; c < D; ++c) Ky[(size_t(i) * D + c) * D + r] = Krow[(size_t(i) * D + r) * D + c];
+        d_Kyoung.upload(Ky);
     }
 }
 
@@ -359,23 +388,36 @@ void hc_ensemble::setup_radiation_chunks() {
     d_rad_partial.alloc(size_t(rad_nchunk) * D * Bp);
 }
 
-// Radiation look-ahead configuration: m = RIRF lag spacing / step size (an integer), row chunks of R rows per
-// residue class such that (instance tiles x chunks x m) fills whole waves of 3 resident CTAs per SM.
+// Radiation look-ahead configuration.  RIRF lag spacing = m dt with an integer m: the block works on the lag grid,
+// one residue class of history rows per step (rb_m = m).  Any other ratio: the block works on a row-grid kernel with
+// the interpolation weights folded in (rb_general, rb_m = 1; stage_kernel).  Row chunks of R rows per residue class
+// such that (instance tiles x chunks x m) fills whole waves of resident CTAs.
 void hc_ensemble::setup_radiation_block() {
     rb_enabled = false; rb_invalidate();
     const int want = opts.rad_lookahead;
     if (want == 1 || (D != 6 && D != 12 && D != 18) || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
     for (int s = 1; s < L; ++s) if (!(T->rirf_t[s] > T->rirf_t[s - 1])) return;     // lags must ascend
-    const double lag_dt = (T->rirf_t.back() - T->rirf_t.front()) / (L - 1);
-    const long long m = std::llround(lag_dt / opts.dt_hint);
-    if (m < 1 || m > kRbMaxM || std::fabs(lag_dt - double(m) * opts.dt_hint) > 1e-6 * opts.dt_hint) return;
+    if (T->rirf_t[0] < 0.0) return;
     const int tiles = Bp / kRbTileInst;
     if (want == 0 && (tiles < sm_count || !(opts.bracket_snap > 0.0))) return;       // auto: large ensembles only
-    rb_m = int(m);
+    const double dt = opts.dt_hint;
+    const double lag_dt = (T->rirf_t.back() - T->rirf_t.front()) / (L - 1);
+    const long long m = std::llround(lag_dt / dt);
+    rb_pnom.assign(L, 0.0);
+    if (m >= 1 && m <= kRbMaxM && std::fabs(lag_dt - double(m) * dt) <= 1e-6 * dt && T->rirf_t[0] == 0.0) {
+        rb_general = false; rb_m = int(m); rb_Lk = L;
+        for (int s = 0; s < L; ++s) rb_pnom[s] = double(m) * s;
+    } else {
+        for (int s = 0; s < L; ++s) rb_pnom[s] = T->rirf_t[s] / dt;
+        const double rows = std::floor(rb_pnom[L - 1]) + 2.0;
+        // FP64 work of the row-grid kernel (rows x D^2) against the HBM traffic of the per-step kernel (2 L rows)
+        if (rows < 2 * kRbT || rows * D > 64.0 * L) return;
+        rb_general = true; rb_m = 1; rb_Lk = int(rows);
+    }
     rb_occ = (D <= 12) ? 3 : 2;                                    // resident CTAs per SM of k_rad_block<D> (registers)
-    rb_R = pick_chunk(L - 1, tiles * rb_m, sm_count, rb_occ, size_t(rb_occ == 3 ? 74 : 110) * 1024, rad_block_smem_bytes,
-                      D, 8);
-    rb_nchunk = (L - 1 + rb_R - 1) / rb_R;
+    rb_R = pick_chunk(rb_Lk - 1, tiles * rb_m, sm_count, rb_occ, size_t(rb_occ == 3 ? 74 : 110) * 1024,
+                      rad_block_smem_bytes, D, 8);
+    rb_nchunk = (rb_Lk - 1 + rb_R - 1) / rb_R;
     rb_ahead = (want != 3);                                        // 3 = whole pass at the block's first step
     for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) {
         d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
@@ -393,40 +435,38 @@ void hc_ensemble::setup_radiation_block() {
 }
 
 // The radiation plan of one step (k_prestep's bracket arithmetic, same IEEE operations) reduced to the question the
-// block kernel needs answered: does every lag s that has a bracket resolve to exactly history row m s with weight 1?
-// tm[0 .. len) = the time history as it will be at that step, newest first.  smax = the largest lag with a bracket.
+// block kernel needs answered: does every lag s that has a bracket sit at its nominal position rb_pnom[s] (in history
+// rows back from the step, bracket index + weight of the older row) to within bracket_snap?  tm[0 .. len) = the time
+// history as it will be at that step, newest first.  smax = the largest lag with a bracket; the row-grid kernel
+// needs all of them (full window).
 bool hc_ensemble::rb_step_plan(const double* tm, int len, double snap, int& smax) const {
     smax = -1;
     if (len <= 1) return false;
     const double* rt = T->rirf_t.data();
-    const int m = rb_m;
     const double oldest = tm[len - 1];
     for (int s = 0; s < L; ++s) {
         const double q = tm[0] - rt[s];
         if (!(oldest <= q)) break;                           // no bracket; none for the later (older) lags either
-        auto is_bracket = [&](int i) {                       // smallest i with tm[i+1] <= q
-            return i >= 0 && i + 1 < len && tm[i + 1] <= q && (i == 0 || !(tm[i] <= q));
-        };
-        const int want = m * s;
-        int i;
-        if (is_bracket(want - 1)) i = want - 1;
-        else if (is_bracket(want)) i = want;
-        else return false;
+        // AdvanceToBracket: smallest i with tm[i+1] <= q; it can only be next to the nominal position
+        const double pn = rb_pnom[s];
+        int i = std::min(std::max(int(std::floor(pn)), 0), len - 2);
+        int moves = 0;
+        while (i > 0 && tm[i] <= q && moves < 4) { --i; ++moves; }
+        while (i + 1 < len - 1 && !(tm[i + 1] <= q) && moves < 4) { ++i; ++moves; }
+        if (!(tm[i + 1] <= q) || (i > 0 && tm[i] <= q)) return false;
         const double newer = tm[i], older = tm[i + 1];
-        int row;
-        if (q == older) row = i + 1;
-        else if (q == newer) row = i;
+        double pa;                                           // InterpolateVelocity6D's cases
+        if (q == older) pa = double(i + 1);
+        else if (q == newer) pa = double(i);
         else if (q > older && q < newer) {
             const double delta = newer - older;
             const double wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
-            const double wn = 1.0 - wo;
-            if (snap > 0.0 && wo <= snap) row = i;
-            else if (snap > 0.0 && wn <= snap) row = i + 1;
-            else return false;
+            pa = double(i) + wo;
         } else return false;
-        if (row != want) return false;
+        if (!(std::fabs(pa - pn) <= snap)) return false;
         smax = s;
     }
+    if (rb_general && smax != L - 1) return false;
     return smax >= 0;
 }
 
@@ -456,10 +496,10 @@ int hc_ensemble::rb_plan_block(RbBlock& Bk, double t, int base) {
         if (jj < base) continue;                                            // steps of the block being served
         int smax = -1;
         if (!rb_step_plan(tm, len, snap, smax)) break;
-        Bk.times[jj - base] = tp; Bk.smax[jj - base] = smax; Bk.len = jj - base + 1;
+        Bk.times[jj - base] = tp; Bk.smax[jj - base] = rb_general ? rb_Lk - 1 : smax; Bk.len = jj - base + 1;
     }
     for (int j = Bk.len; j < TT; ++j) { Bk.times[j] = Bk.len ? Bk.times[Bk.len - 1] : t; Bk.smax[j] = -1; }
-    const int n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));      // rows resident before this step's append
+    const int n_res = std::min(int(times.size()) - 1, rb_m * (rb_Lk - 1));  // rows resident before this step's append
     const int nu = (n_res + rb_m - 1) / rb_m;                               // rows of the fullest residue class
     Bk.nchunk_used = std::max(1, std::min(rb_nchunk, (nu + rb_R - 1) / rb_R));
     return Bk.len;
@@ -473,7 +513,7 @@ void hc_ensemble::rb_setup_pass(int buf) {
     RadBlockArgs& ba = rb_pass.args;
     ba = RadBlockArgs{};
     ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p; ba.smax = d_rb_smax[buf].p;
-    ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (L - 1));
+    ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (rb_Lk - 1));
     ba.D = D; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
     ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;
     rb_pass.items = rad_block_items(ba);
@@ -551,6 +591,8 @@ int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
     }
     // miss: first steps, end of a block that has no successor, or a time the prediction did not foresee
     rb_invalidate();
+    // row-grid kernel: needs the full window, i.e. a bracket for the oldest lag (k_prestep's test)
+    if (rb_general && !(times.back() <= t - T->rirf_t.back())) return -1;
     if (rb_builds > 0 && rb_hits_this_block < 2) {
         if (++rb_poor_blocks >= 3) { rb_enabled = false; return -1; }      // unpredictable stepping: stop trying
     } else {
@@ -639,9 +681,9 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
     if (rb_use) {
         // served by the radiation look-ahead: append + block partials + young rows + finalize in one kernel
         RadStepArgs sa{};
-        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_K.p;
+        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_Kyoung.p;
         sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.D = D;
-        sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = L; sa.m = rb_m;
+        sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = rb_Lk; sa.m = rb_m;
         CUDA_CHECK(launch_step(sa, fa, hs, fg, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
     } else {

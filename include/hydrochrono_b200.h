@@ -160,14 +160,17 @@ typedef struct hc_ensemble_opts {
                                  2 = FP64 tensor cores (DMMA m8n8k4; 12 rows padded to 16: lower power, slower),
                                  3 = both engines: rows 0..7 on the tensor cores, rows 8..11 on the FMA pipe.
                                  Other body counts always use the FMA-pipe kernels. */
-    int rad_lookahead;        /* radiation look-ahead for 6N = 6, 12, 18: the share of the resident history rows in the next 8
-                                 (predicted) steps' convolutions is evaluated in one pass over the history on the FP64
-                                 tensor cores, 1/8 of the per-step HBM traffic.  Served only for steps whose plan puts
-                                 every lag exactly on one history row (uniform stepping on the RIRF grid, within
-                                 bracket_snap) and whose time matches the prediction bitwise; other steps run the per-
-                                 step kernel.  0 = auto (on for large ensembles with bracket_snap > 0), 1 = off, 2 = on (each
-                                 block is evaluated one block ahead on a low-priority side stream), 3 = on, blocks
-                                 evaluated in the main stream at their first step */
+    int rad_lookahead;        /* radiation look-ahead for 6N = 6, 12, 18: the share of the resident history rows in the
+                                 next (predicted) steps' convolutions is evaluated in one pass over the history on the
+                                 FP64 tensor cores, 1/8 of the per-step HBM traffic.  RIRF lag spacing = m dt_hint with
+                                 an integer m <= 8: blocks of 8 m steps on the lag grid.  Any other ratio: blocks of 8
+                                 steps with a row-grid kernel (the velocity interpolation weights at the nominal lag
+                                 positions t_rirf / dt_hint folded into K), used once the history window is full.
+                                 A step is served from a block only if its time matches the prediction bitwise and
+                                 every lag sits within bracket_snap (in rows) of its nominal position; other steps run
+                                 the per-step kernel.  0 = auto (on for large ensembles with bracket_snap > 0), 1 = off,
+                                 2 = on (each block is evaluated one block ahead, one slice per step on a side
+                                 stream), 3 = on, whole pass in the main stream at the block's first step */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;
 

@@ -409,22 +409,27 @@ def test_gravity_vector_and_body_count_generic_path():
     # BASELINE.json configs 2..4 as parity cases (their .h5 files are stripped from the reference snapshot, so the
     # tables are synthetic with the demos' shapes and step sizes)
     ("oswec_jonswap", dict(tables=dict(num_bodies=2, rirf_steps=601, rirf_duration=30.0, exc_irf_steps=401,
-                                       exc_half_window=24.0), dt=0.03, steps=1100,
+                                       exc_half_window=24.0), dt=0.03, steps=1400,
                            sea=dict(Hs=1.5, Tp=10.0, gamma=3.3, nfreq=150, ramp=3.0))),     # demos/oswec: N = 2, dt = 0.03
     ("deepcwind_long_rirf", dict(tables=dict(num_bodies=1, rirf_steps=4001, rirf_duration=320.0, exc_irf_steps=601,
                                              exc_half_window=48.0), dt=0.08, steps=4100,
                                  sea=dict(Hs=6.0, Tp=12.0, gamma=2.2, nfreq=120, ramp=8.0))),  # demos/DeepCWind: N = 1, dt = 0.08
     ("f3of_three_bodies", dict(tables=dict(num_bodies=3, rirf_steps=401, rirf_duration=20.0, exc_irf_steps=301,
-                                           exc_half_window=15.0), dt=0.02, steps=1050,
+                                           exc_half_window=15.0), dt=0.02, steps=1300,
                                sea=dict(Hs=1.0, Tp=6.0, gamma=1.0, nfreq=100, ramp=0.0))),   # demos/f3of: N = 3, D = 18
 ])
-def test_baseline_config_shapes(name, cfg):
+@pytest.mark.parametrize("rad_la", [1, 2])
+def test_baseline_config_shapes(name, cfg, rad_la):
+    """rad_la = 2: radiation look-ahead blocks.  DeepCWind's lag spacing equals dt (lag-grid blocks from the second
+    step on); OSWEC's and F3OF's ratios are 5/3 and 5/2, so their blocks convolve the rows with the row-grid kernel
+    (interpolation weights folded in) once the history window is full (1000 steps)."""
     raw = synth.make_tables(**cfg["tables"])
     T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
     N = cfg["tables"]["num_bodies"]
     D, dt, steps = 6 * N, cfg["dt"], cfg["steps"]
     B = 3
-    ens = hc.Ensemble(T, batch=B, dt_hint=dt, exc_lookahead=5 if N <= 2 else 0)
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, exc_lookahead=5 if N <= 2 else 0, rad_lookahead=rad_la,
+                      bracket_snap=1e-8 if rad_la == 2 else 0.0)
     kw = dict(dt=dt, duration=steps * dt + 1.0, **cfg["sea"])
     seeds = [3, 4, 5]
     ens.set_waves_irregular(seeds=seeds, **kw)
@@ -445,6 +450,10 @@ def test_baseline_config_shapes(name, cfg):
             ref.append(r)
     _assert_parity(np.array(got), np.array(ref), name)
     assert ens.history_len() == insts[0].history_len()
+    if rad_la == 2:
+        served = ens.rad_block_stats()["steps_served"]
+        full_window = int(round(cfg["tables"]["rirf_duration"] / dt))
+        assert served >= (steps - 8 if name.startswith("deepcwind") else steps - full_window - 24), served
 
 
 def test_added_mass_mv(rm3):
