@@ -584,3 +584,43 @@ def test_large_ensemble_lookahead_paths(rm3):
     assert e1.rad_block_stats()["steps_served"] == 119
     r1, r2 = e1.components()[1], e2.components()[1]
     np.testing.assert_array_equal(2.0 * r1, r2)
+
+
+@pytest.mark.gpu
+def test_radiation_lookahead_reset_and_wrong_hint(rm3):
+    """(a) hc_ensemble_reset in the middle of a block: the second run reproduces the first bit for bit.
+    (b) dt_hint twice the step actually used: every prediction misses, the per-step kernels serve all steps, the
+    history ring (sized from the hint) has to grow, and the results still match the oracle."""
+    T, O = rm3
+    B, D, dt = 4, 12, 0.01
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
+    times = _acc_times(131, dt)          # stops inside the third block of 48
+
+    def run():
+        out = []
+        for t in times:
+            pose, vel = _motion(D, B, t)
+            out.append(ens.step(t, pose, vel, G981).copy())
+        return np.array(out)
+
+    first = run()
+    assert ens.rad_block_stats()["steps_served"] == 130
+    ens.reset()
+    second = run()
+    assert ens.rad_block_stats()["steps_served"] == 130
+    np.testing.assert_array_equal(first, second)
+    ens.close()
+
+    ens = hc.Ensemble(T, batch=B, dt_hint=2 * dt, bracket_snap=1e-8, rad_lookahead=2)
+    insts = [orc.Instance(O) for _ in range(B)]
+    times = _acc_times(3300, dt)         # ring sized for 60 s / 0.02 = 3000 rows (+ slack)
+    got, want = [], []
+    for n, t in enumerate(times):
+        pose, vel = _motion(D, B, t)
+        F = ens.step(t, pose, vel, G981)
+        ref = np.array([i.force(t, pose[b], vel[b], G981) for b, i in enumerate(insts)])
+        if n % 97 == 0 or n > 3250:
+            got.append(F.copy()); want.append(ref)
+    _assert_parity(np.array(got), np.array(want), "wrong dt_hint")
+    assert ens.rad_block_stats()["steps_served"] <= 3        # at most the first step of a block that then misses
+    assert ens.history_len() == insts[0].history_len() > 3100
