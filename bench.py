@@ -486,6 +486,7 @@ def main():
             "e2e": {"value": e2e, "unit": "instance-steps/s", "h2d_bytes_per_step": 2 * B * DOFS * 8 + 64,
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(launches) * world,
+            "launches_before_timed_region": int(launches0),      # ncu --launch-skip for a launch list of the timed steps
             "clocks": clocks,
             "roofline": {**rad_roof,
                          "excitation": ({"kernel": ("k_exc_block_mma<%d> (look-ahead, 8 steps per eta pass, DMMA m8n8k4)" % DOFS
