@@ -76,7 +76,7 @@ def parse():
     ap.add_argument("--rad-chunk", type=int, default=0)
     ap.add_argument("--exc-chunk", type=int, default=0)
     ap.add_argument("--cpu-instances", type=int, default=32)
-    ap.add_argument("--cpu-steps", type=int, default=200)
+    ap.add_argument("--cpu-steps", type=int, default=600)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="per-step excitation kernel only")
