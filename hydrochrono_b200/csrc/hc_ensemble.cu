@@ -1502,6 +1502,8 @@ hc_status hc_ensemble_refresh_rirf(hc_ensemble* e) {
     HC_GUARD_BEGIN
     e->use_device();
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->rb_stream) CUDA_CHECK(cudaStreamSynchronize(e->rb_stream));
+    e->rb_invalidate();              // blocks evaluated with the old kernel
     e->stage_kernel();
     return HC_OK;
     HC_GUARD_END

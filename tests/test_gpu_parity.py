@@ -304,16 +304,20 @@ def test_regular_waves_two_bodies_phase_quirk(rm3):
         ens.set_waves_regular([1.0], [50.0])       # omega beyond the frequency table
 
 
-def test_tapered_direct_mode(rm3):
+@pytest.mark.parametrize("rad_la", [1, 2])
+def test_tapered_direct_mode(rm3, rad_la):
+    """TaperedDirect preprocessing of the kernel (one-off, host); the look-ahead blocks convolve with the same
+    processed table."""
     raw = synth.rm3_like()
     T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
     T.set_convolution_mode("TaperedDirect", taper_start_percent=0.5, taper_end_percent=0.9)
     O.set_tapered(start=0.5, end=0.9)
-    ens = hc.Ensemble(T, batch=2, dt_hint=0.01)
+    ens = hc.Ensemble(T, batch=2, dt_hint=0.01, rad_lookahead=rad_la, bracket_snap=1e-8 if rad_la == 2 else 0.0)
     insts = [orc.Instance(O), orc.Instance(O)]
     times = _acc_times(400, 0.01)
     (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 12)
     _assert_parity(rad, rrad, "tapered radiation")
+    assert ens.rad_block_stats()["steps_served"] == (399 if rad_la == 2 else 0)
 
 
 # ---------------------------------------------------------------------------------------------
