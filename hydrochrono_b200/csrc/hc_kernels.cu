@@ -1059,17 +1059,30 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { C[mt][0][0] = C[mt][0][1] = C[mt][1][0] = C[mt][1][1] = 0.0; }
 
-    // lane's B element: eta row (k-step * 4 + q), instances b0 + 2 g + {0, 1}
+    // lane's B element: eta row (k-step * 4 + q), instances b0 + 2 g + {0, 1}.  eta is prefetched half a stage
+    // (KH k-steps) ahead: 2 x KH registers pairs instead of 2 x KS leave the compiler room to hoist the tap loads.
+    constexpr int KH = KS / 2;
     const double* eta_l = a.eta + (active ? b0 + 2 * g : 0);
-    auto load_stage = [&](int c, double2* dst) {
+    auto load_half = [&](int c, int h, double2* dst) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int row = min(a.row0 + c * kLaRows + ks * 4 + q, a.n_eta - 1);   // rows past the window: zero taps
-            dst[ks] = __ldg(reinterpret_cast<const double2*>(eta_l + (size_t)row * a.Bp));
+        for (int k = 0; k < KH; ++k) {
+            const int row = min(a.row0 + c * kLaRows + (h * KH + k) * 4 + q, a.n_eta - 1);   // past the window: zero taps
+            dst[k] = __ldg(reinterpret_cast<const double2*>(eta_l + (size_t)row * a.Bp));
         }
     };
-    double2 cur[KS], nxt[KS];
-    if (active && c0 < c1) load_stage(c0, cur);
+    auto mma_half = [&](const double* tp, int h, const double2* v) {
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const double av = tp[((h * KH + k) * MT + mt) * 32];
+                dmma8x8x4(C[mt][0][0], C[mt][0][1], av, v[k].x);
+                dmma8x8x4(C[mt][1][0], C[mt][1][1], av, v[k].y);
+            }
+        }
+    };
+    double2 cur[KH], nxt[KH];
+    if (active && c0 < c1) load_half(c0, 0, cur);
 
     for (int c = c0; c < c1; ++c) {
         const int st = (c - c0) & 1;
@@ -1078,21 +1091,17 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
             bulk_g2s(stage0 + (st ^ 1) * kStageDoubles, a.taps + (size_t)(c + 1) * kStageDoubles, kStageBytes,
                      &bars[st ^ 1]);
         }
-        if (active && c + 1 < c1) load_stage(c + 1, nxt);                 // eta of the next stage is in flight
+        if (active) load_half(c, 1, nxt);                                 // second half of this stage in flight
         mbar_wait(&bars[st], ((c - c0) >> 1) & 1);
         if (active) {
             const double* tp = reinterpret_cast<const double*>(smem_raw + 16) + (size_t)st * kStageDoubles + lane;
+            mma_half(tp, 0, cur);
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
+            for (int k = 0; k < KH; ++k) cur[k] = nxt[k];
+            if (c + 1 < c1) load_half(c + 1, 0, nxt);                     // first half of the next stage in flight
+            mma_half(tp, 1, cur);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const double av = tp[(ks * MT + mt) * 32];
-                    dmma8x8x4(C[mt][0][0], C[mt][0][1], av, cur[ks].x);
-                    dmma8x8x4(C[mt][1][0], C[mt][1][1], av, cur[ks].y);
-                }
-            }
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) cur[ks] = nxt[ks];
+            for (int k = 0; k < KH; ++k) cur[k] = nxt[k];
         }
         __syncthreads();
     }
