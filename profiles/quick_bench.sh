@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "rm3_irregular or radiation_lookahead or large_ensemble or misprediction or sphere" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -x -q -k "rm3_irregular or large_ensemble" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 run() {
 python bench.py --steps 960 --warmup 10 --no-cpu $ARGS 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_last.json
 python -c "
@@ -9,5 +9,4 @@ print('$TAG $ARGS', 'value %.2fM e2e %.2fM ms/step %.4f e2e ms %.4f' % (d['value
 tail -2 gpurun_out/bench_err.log
 }
 ARGS="" TAG="default" run
-ARGS="--workload sphere_irregular_ensemble" TAG="sphere" run
 true
