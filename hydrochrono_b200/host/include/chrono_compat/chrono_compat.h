@@ -2,8 +2,9 @@
 // small rigid-body stepper, so that the host layer (hydroc/*.h) and the reference-style demo mains can be built
 // and run where Project Chrono is not installed.  It is NOT a multibody engine: bodies are free 6-DoF rigid
 // bodies, optionally locked to heave by a ChLinkLockPrismatic to a fixed body and damped by a ChLinkTSDA;
-// ChSystem::DoStepDynamics advances with the linearised-Euler scheme the reference's goldens were produced with
-// (force evaluated once at (t_n, x_n, v_n), v += dt (M + M_added)^-1 F, x += dt v).
+// ChSystem::DoStepDynamics advances with the linearised-Euler scheme the reference's sphere goldens were produced
+// with (force evaluated once at (t_n, x_n, v_n), v += dt (M + M_added)^-1 F, x += dt v), or, after
+// SetTimestepperType(HHT) as in the reference's YAML runs, with an HHT-alpha step (chrono_compat.cpp).
 //
 // With the real Chrono, compile the host layer with -DHYDROC_HAVE_CHRONO and this header is not used.
 #pragma once
@@ -313,7 +314,8 @@ class ChSystem {
     void SetGravitationalAcceleration(const ChVector3d& g) { g_ = g; }
     const ChVector3d& GetGravitationalAcceleration() const { return g_; }
     void SetSolverType(ChSolver::Type) {}
-    void SetTimestepperType(ChTimestepper::Type) {}
+    void SetTimestepperType(ChTimestepper::Type t) { stepper_ = t; }
+    ChTimestepper::Type GetTimestepperType() const { return stepper_; }
     ChSolver* GetSolver() { return &solver_; }
     void Add(std::shared_ptr<ChBody> b) { AddBody(std::move(b)); }
     void AddBody(std::shared_ptr<ChBody> b) { b->system_ = this; bodies_.push_back(std::move(b)); }
@@ -336,6 +338,12 @@ class ChSystem {
     int DoStepDynamics(double dt);
 
   private:
+    void Assemble(const std::vector<ChBody*>& act, std::vector<double>& F, std::vector<double>& M);
+    std::vector<double> SolveAccelerations(const std::vector<ChBody*>& act, const std::vector<double>& rhs,
+                                           const std::vector<double>& M);
+    int StepHHT(const std::vector<ChBody*>& act, double h);
+    ChTimestepper::Type stepper_ = ChTimestepper::Type::EULER_IMPLICIT_LINEARIZED;
+    std::vector<double> hht_F_, hht_a_;      // generalised force and accelerations at t_n (HHT)
     ChVector3d g_{0, 0, -9.81};
     ChSolver solver_;
     double time_ = 0.0, step_ = 0.0;

@@ -31,16 +31,11 @@ static void solve_dense(std::vector<double>& A, std::vector<double>& b, int n) {
     }
 }
 
-int ChSystem::DoStepDynamics(double dt) {
-    step_ = dt;
-    std::vector<ChBody*> act;
-    for (auto& b : bodies_)
-        if (!b->IsFixed()) act.push_back(b.get());
+// Generalised force (applied ChForces evaluated at the current time/state, gravity, spring-dampers) and mass matrix
+// (rigid-body inertia + the M Jacobians of stiff loads, i.e. ChLoadAddedMass) of the non-fixed bodies.
+void ChSystem::Assemble(const std::vector<ChBody*>& act, std::vector<double>& F, std::vector<double>& M) {
     const int n = 6 * int(act.size());
-    if (n == 0) { time_ += dt; return 1; }
-
-    // forces at (t_n, x_n, v_n): applied ChForces (world-aligned), gravity, spring-dampers
-    std::vector<double> F(n, 0.0);
+    F.assign(n, 0.0);
     for (size_t i = 0; i < act.size(); ++i) {
         ChBody* b = act[i];
         for (const auto& f : b->GetForces()) {
@@ -63,9 +58,7 @@ int ChSystem::DoStepDynamics(double dt) {
             for (int k = 0; k < 3; ++k) F[6 * i + k] += sgn * f * u[k];
         }
     }
-
-    // mass matrix: rigid-body inertia + the M Jacobians of stiff loads (ChLoadAddedMass)
-    std::vector<double> M(size_t(n) * n, 0.0);
+    M.assign(size_t(n) * n, 0.0);
     for (size_t i = 0; i < act.size(); ++i) {
         for (int k = 0; k < 3; ++k) {
             M[size_t(6 * i + k) * n + 6 * i + k] = act[i]->GetMass();
@@ -82,8 +75,12 @@ int ChSystem::DoStepDynamics(double dt) {
             for (int r = 0; r < m; ++r)
                 for (int cc = 0; cc < m; ++cc) M[size_t(r) * n + cc] += J(r, cc);
         }
+}
 
-    // eliminate locked DoFs, solve for the accelerations of the free ones
+// Accelerations of the free DoFs from M a = rhs (locked DoFs eliminated, their acceleration is zero).
+std::vector<double> ChSystem::SolveAccelerations(const std::vector<ChBody*>& act, const std::vector<double>& rhs_full,
+                                                 const std::vector<double>& M) {
+    const int n = 6 * int(act.size());
     std::vector<int> idx;
     for (size_t i = 0; i < act.size(); ++i)
         for (int k = 0; k < 6; ++k)
@@ -91,14 +88,37 @@ int ChSystem::DoStepDynamics(double dt) {
     const int nf = int(idx.size());
     std::vector<double> A(size_t(nf) * nf), rhs(nf);
     for (int r = 0; r < nf; ++r) {
-        rhs[r] = F[idx[r]];
+        rhs[r] = rhs_full[idx[r]];
         for (int c = 0; c < nf; ++c) A[size_t(r) * nf + c] = M[size_t(idx[r]) * n + idx[c]];
     }
     if (nf > 0) solve_dense(A, rhs, nf);
     std::vector<double> acc(n, 0.0);
     for (int r = 0; r < nf; ++r) acc[idx[r]] = rhs[r];
+    return acc;
+}
 
-    // v_{n+1} = v_n + dt a ; x_{n+1} = x_n + dt v_{n+1}
+static void rotate_by(ChBody* b, const ChVector3d& dtheta) {
+    const double a = dtheta.Length();
+    if (a > 0.0) {
+        ChQuaterniond q = QuatFromAngleAxis(a, dtheta * (1.0 / a)) * b->GetRot();
+        q.Normalize();
+        b->SetRot(q);
+    }
+}
+
+int ChSystem::DoStepDynamics(double dt) {
+    step_ = dt;
+    std::vector<ChBody*> act;
+    for (auto& b : bodies_)
+        if (!b->IsFixed()) act.push_back(b.get());
+    const int n = 6 * int(act.size());
+    if (n == 0) { time_ += dt; return 1; }
+    if (stepper_ == ChTimestepper::Type::HHT) return StepHHT(act, dt);
+
+    // linearised Euler: forces at (t_n, x_n, v_n);  v_{n+1} = v_n + dt a ; x_{n+1} = x_n + dt v_{n+1}
+    std::vector<double> F, M;
+    Assemble(act, F, M);
+    const std::vector<double> acc = SolveAccelerations(act, F, M);
     for (size_t i = 0; i < act.size(); ++i) {
         ChBody* b = act[i];
         ChVector3d v = b->GetPosDt(), w = b->GetAngVelParent();
@@ -110,14 +130,70 @@ int ChSystem::DoStepDynamics(double dt) {
         b->SetPosDt(v);
         b->SetAngVelParent(w);
         b->SetPos(b->GetPos() + v * dt);
-        const double wl = w.Length();
-        if (wl > 0.0) {
-            ChQuaterniond q = QuatFromAngleAxis(wl * dt, w * (1.0 / wl)) * b->GetRot();
-            q.Normalize();
-            b->SetRot(q);
-        }
+        rotate_by(b, w * dt);
     }
     time_ += dt;
+    return 1;
+}
+
+// HHT-alpha (alpha = -0.2, gamma = 1/2 - alpha, beta = (1 - alpha)^2 / 4), the stepper of the reference's YAML runs.
+// The applied forces are time-keyed callbacks (ChFunction::GetVal(t); TestHydro caches per time value), so within a
+// step they are evaluated exactly once, at t_{n+1} with the predictor state -- later iterations of Chrono's Newton
+// loop would read the cache.  The step is therefore:
+//   predictor   x* = x_n + h v_n + h^2/2 a_n,  v* = v_n + h a_n                       (a* = a_n)
+//   forces      F_{n+1} = F(t_{n+1}, x*, v*)
+//   balance     M a_{n+1} = (1 + alpha) F_{n+1} - alpha F_n
+//   corrector   x_{n+1} = x_n + h v_n + h^2 ((1/2 - beta) a_n + beta a_{n+1}),  v_{n+1} = v_n + h ((1 - gamma) a_n + gamma a_{n+1})
+int ChSystem::StepHHT(const std::vector<ChBody*>& act, double h) {
+    const double alpha = -0.2, gamma = 0.5 - alpha, beta = 0.25 * (1.0 - alpha) * (1.0 - alpha);
+    const int n = 6 * int(act.size());
+    std::vector<double> F, M;
+    if (int(hht_F_.size()) != n) {                       // first step: consistent initial accelerations M a_0 = F_0
+        Assemble(act, F, M);
+        hht_F_ = F;
+        hht_a_ = SolveAccelerations(act, F, M);
+    }
+    struct Saved { ChVector3d x, v, w; ChQuaterniond q; };
+    std::vector<Saved> s0(act.size());
+    for (size_t i = 0; i < act.size(); ++i) {
+        ChBody* b = act[i];
+        s0[i] = Saved{b->GetPos(), b->GetPosDt(), b->GetAngVelParent(), b->GetRot()};
+        const ChVector3d a(hht_a_[6 * i], hht_a_[6 * i + 1], hht_a_[6 * i + 2]);
+        const ChVector3d al(hht_a_[6 * i + 3], hht_a_[6 * i + 4], hht_a_[6 * i + 5]);
+        b->SetPos(s0[i].x + s0[i].v * h + a * (0.5 * h * h));
+        b->SetPosDt(s0[i].v + a * h);
+        rotate_by(b, s0[i].w * h + al * (0.5 * h * h));
+        b->SetAngVelParent(s0[i].w + al * h);
+    }
+    time_ += h;
+    Assemble(act, F, M);
+    std::vector<double> rhs(n);
+    for (int k = 0; k < n; ++k) rhs[k] = (1.0 + alpha) * F[k] - alpha * hht_F_[k];
+    const std::vector<double> an = SolveAccelerations(act, rhs, M);
+    for (size_t i = 0; i < act.size(); ++i) {
+        ChBody* b = act[i];
+        ChVector3d x = s0[i].x, v = s0[i].v, w = s0[i].w, dth;
+        for (int k = 0; k < 3; ++k) {
+            const double a0 = hht_a_[6 * i + k], a1 = an[6 * i + k];
+            const double l0 = hht_a_[6 * i + 3 + k], l1 = an[6 * i + 3 + k];
+            if (b->free_dof[k]) {
+                x[k] += h * s0[i].v[k] + h * h * ((0.5 - beta) * a0 + beta * a1);
+                v[k] += h * ((1.0 - gamma) * a0 + gamma * a1);
+            } else v[k] = 0.0;
+            if (b->free_dof[3 + k]) {
+                dth[k] = h * s0[i].w[k] + h * h * ((0.5 - beta) * l0 + beta * l1);
+                w[k] += h * ((1.0 - gamma) * l0 + gamma * l1);
+            } else { dth[k] = 0.0; w[k] = 0.0; }
+        }
+        b->SetPos(x);
+        b->SetPosDt(v);
+        b->SetRot(s0[i].q);
+        rotate_by(b, dth);
+        b->SetAngVelParent(w);
+        b->acc_ = ChVector3d(an[6 * i], an[6 * i + 1], an[6 * i + 2]);
+    }
+    hht_F_ = F;
+    hht_a_ = an;
     return 1;
 }
 

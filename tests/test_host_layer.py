@@ -41,6 +41,14 @@ def test_yaml_parser(host_build):
     assert "All hydro YAML parser tests passed" in out.stdout
 
 
+def test_compat_steppers_converge(host_build):
+    """chrono_compat's linearised-Euler (order 1) and HHT-alpha (order 2) steps against a closed-form oscillator whose
+    force comes from state-reading, time-keyed ChFunction callbacks (the way ComponentFunc feeds Chrono).  CPU only."""
+    out = subprocess.run([os.path.join(host_build, "test_stepper")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "stepper test passed" in out.stdout
+
+
 def test_host_layer_fails_loudly_without_gpu(host_build, sphere_h5, tmp_path):
     import hydrochrono_b200 as hc
     if hc.device_count() > 0:
