@@ -359,6 +359,7 @@ def main():
     for _ in range(K):
         dev_step()
     ev1.record(stream)
+    t_enq = time.perf_counter() - t0               # host time to enqueue the K steps (the GPU runs behind)
     ens.sync()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t0
@@ -517,9 +518,10 @@ def main():
                                                      .get(args.lookahead_mode, str(args.lookahead_mode))),
                        "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
                              % (8e-9 * DOFS * B * ens.history_len(), 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
-                       "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s); "
+                       "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s, "
+                                 "of which %.4f s to enqueue them); "
                                  "e2e: wall clock around K synchronous hc_step calls; per-kernel ms: CUDA events inside "
-                                 "the library on the same stream" % t_wall},
+                                 "the library on the same stream" % (t_wall, t_enq)},
             "e2e": {"value": e2e, "unit": "instance-steps/s", "h2d_bytes_per_step": 2 * B * DOFS * 8 + 64,
                     "d2h_bytes_per_step": B * DOFS * 8, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(launches) * world,

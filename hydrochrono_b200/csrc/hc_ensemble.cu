@@ -101,6 +101,8 @@ struct hc_ensemble {
     bool rb_general = false;                      // RIRF lag spacing is not a multiple of dt: row-grid kernel (below)
     int rb_Lk = 0;                                // lags of the kernel the block path convolves with (L, or row grid)
     std::vector<double> rb_pnom;                  // [L] nominal position of every lag in history rows (rirf_t / dt)
+    std::vector<int> rb_pi;                       // [L] its integer part (bracket index) ...
+    std::vector<double> rb_pw;                    // [L] ... and fraction (weight of the older row)
     DevBuf<double> d_Kyoung;                      // first 2 kRbT lags of that kernel, [lag][col][row] (k_step)
     DevBuf<double> d_Kpad, d_rb_partial[2];
     DevBuf<int> d_rb_smax[2];
@@ -414,6 +416,11 @@ void hc_ensemble::setup_radiation_block() {
         if (rows < 2 * kRbT || rows * D > 64.0 * L) return;
         rb_general = true; rb_m = 1; rb_Lk = int(rows);
     }
+    rb_pi.resize(L); rb_pw.resize(L);
+    for (int s = 0; s < L; ++s) {
+        rb_pi[s] = int(std::floor(rb_pnom[s]));
+        rb_pw[s] = rb_pnom[s] - double(rb_pi[s]);
+    }
     rb_occ = (D <= 12) ? 3 : 2;                                    // resident CTAs per SM of k_rad_block<D> (registers)
     rb_R = pick_chunk(rb_Lk - 1, tiles * rb_m, sm_count, rb_occ, size_t(rb_occ == 3 ? 74 : 110) * 1024,
                       rad_block_smem_bytes, D, 8);
@@ -443,31 +450,29 @@ bool hc_ensemble::rb_step_plan(const double* tm, int len, double snap, int& smax
     smax = -1;
     if (len <= 1) return false;
     const double* rt = T->rirf_t.data();
-    const double oldest = tm[len - 1];
-    for (int s = 0; s < L; ++s) {
-        const double q = tm[0] - rt[s];
-        if (!(oldest <= q)) break;                           // no bracket; none for the later (older) lags either
-        // AdvanceToBracket: smallest i with tm[i+1] <= q; it can only be next to the nominal position
-        const double pn = rb_pnom[s];
-        int i = std::min(std::max(int(std::floor(pn)), 0), len - 2);
-        int moves = 0;
-        while (i > 0 && tm[i] <= q && moves < 4) { --i; ++moves; }
-        while (i + 1 < len - 1 && !(tm[i + 1] <= q) && moves < 4) { ++i; ++moves; }
-        if (!(tm[i + 1] <= q) || (i > 0 && tm[i] <= q)) return false;
-        const double newer = tm[i], older = tm[i + 1];
-        double pa;                                           // InterpolateVelocity6D's cases
-        if (q == older) pa = double(i + 1);
-        else if (q == newer) pa = double(i);
-        else if (q > older && q < newer) {
-            const double delta = newer - older;
-            const double wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
-            pa = double(i) + wo;
-        } else return false;
-        if (!(std::fabs(pa - pn) <= snap)) return false;
-        smax = s;
+    const double t0 = tm[0], oldest = tm[len - 1];
+    // lags with a bracket: oldest <= t0 - rt[s] (k_prestep's test, same subtraction); rt ascends, so they are 0..smax
+    if (!(oldest <= t0 - rt[0])) return false;
+    int lo = 0, hi = L - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (oldest <= t0 - rt[mid]) lo = mid; else hi = mid - 1;
     }
-    if (rb_general && smax != L - 1) return false;
-    return smax >= 0;
+    if (rb_general && lo != L - 1) return false;
+    // every such lag at its nominal position i + w (rows back): |q - (tm[i] - w (tm[i] - tm[i+1]))| <= snap * spacing,
+    // i.e. bracket index + older-row weight within snap of the nominal ones (InterpolateVelocity6D's arithmetic)
+    const int* pi = rb_pi.data();
+    const double* pw = rb_pw.data();
+    for (int s = 0; s <= lo; ++s) {
+        const int i = pi[s];
+        const double w = pw[s];
+        if (i + (w > 0.0 ? 1 : 0) > len - 1) return false;
+        const double delta = (i + 1 < len) ? tm[i] - tm[i + 1] : tm[i - 1] - tm[i];
+        const double d = (t0 - rt[s]) - (tm[i] - w * delta);
+        if (!(std::fabs(d) <= snap * delta)) return false;
+    }
+    smax = lo;
+    return true;
 }
 
 // Plans the block whose first step comes `base` steps after the current one (time t, already on `times`): predicted
