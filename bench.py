@@ -102,8 +102,11 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th, self.nvml, self.proc = index, [], False, None, None, None
+        self.period = float(os.environ.get("HC_BENCH_CLOCK_PERIOD", "0.02"))
 
     def start(self):
+        if os.environ.get("HC_BENCH_NO_CLOCKS"):       # experiment switch: no sampling at all
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -140,7 +143,7 @@ class ClockSampler:
                 self.samples.append((sm, self.mx, [1.0 if (r & b) else 0.0 for b in bits]))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
