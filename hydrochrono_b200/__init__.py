@@ -212,6 +212,21 @@ class Tables:
         _check(lib.hc_added_mass(self._h, n, _dp(M)))
         return M
 
+    def rad_lookahead_plan(self, dt_hint):
+        """Host-side plan of the radiation look-ahead for a step size: (mode, rows_per_lag, kernel_lags); mode 0 =
+        not usable, 1 = lag grid, 2 = row grid (hc_rad_lookahead_plan)."""
+        mode, m, lk = C.c_int(), C.c_int(), C.c_int()
+        _check(lib.hc_rad_lookahead_plan(self._h, float(dt_hint), C.byref(mode), C.byref(m), C.byref(lk)))
+        return mode.value, m.value, lk.value
+
+    def rad_lookahead_check_step(self, dt_hint, bracket_snap, times_newest_first):
+        """smax (largest bracketed lag) if the look-ahead could serve a step with this time history, else -1."""
+        tm = _f64(times_newest_first)
+        smax = C.c_int()
+        _check(lib.hc_rad_lookahead_check_step(self._h, float(dt_hint), float(bracket_snap), _dp(tm), int(tm.size),
+                                               C.byref(smax)))
+        return smax.value
+
     def close(self):
         if getattr(self, "_h", None):
             lib.hc_tables_destroy(self._h)

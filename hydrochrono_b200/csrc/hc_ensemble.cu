@@ -101,8 +101,7 @@ struct hc_ensemble {
     bool rb_general = false;                      // RIRF lag spacing is not a multiple of dt: row-grid kernel (below)
     int rb_Lk = 0;                                // lags of the kernel the block path convolves with (L, or row grid)
     std::vector<double> rb_pnom;                  // [L] nominal position of every lag in history rows (rirf_t / dt)
-    std::vector<int> rb_pi;                       // [L] its integer part (bracket index) ...
-    std::vector<double> rb_pw;                    // [L] ... and fraction (weight of the older row)
+    RadPlan rb_plan;                              // the same + bracket index / older-row weight per lag (hc_plan.cpp)
     DevBuf<double> d_Kyoung;                      // first 2 kRbT lags of that kernel, [lag][col][row] (k_step)
     DevBuf<double> d_Kpad, d_rb_partial[2];
     DevBuf<int> d_rb_smax[2];
@@ -397,30 +396,12 @@ void hc_ensemble::setup_radiation_chunks() {
 void hc_ensemble::setup_radiation_block() {
     rb_enabled = false; rb_invalidate();
     const int want = opts.rad_lookahead;
-    if (want == 1 || (D != 6 && D != 12 && D != 18) || L < 2 * kRbT || opts.dt_hint <= 0.0) return;
-    for (int s = 1; s < L; ++s) if (!(T->rirf_t[s] > T->rirf_t[s - 1])) return;     // lags must ascend
-    if (T->rirf_t[0] < 0.0) return;
+    if (want == 1 || (D != 6 && D != 12 && D != 18) || opts.dt_hint <= 0.0) return;
     const int tiles = Bp / kRbTileInst;
     if (want == 0 && (tiles < sm_count || !(opts.bracket_snap > 0.0))) return;       // auto: large ensembles only
-    const double dt = opts.dt_hint;
-    const double lag_dt = (T->rirf_t.back() - T->rirf_t.front()) / (L - 1);
-    const long long m = std::llround(lag_dt / dt);
-    rb_pnom.assign(L, 0.0);
-    if (m >= 1 && m <= kRbMaxM && std::fabs(lag_dt - double(m) * dt) <= 1e-6 * dt && T->rirf_t[0] == 0.0) {
-        rb_general = false; rb_m = int(m); rb_Lk = L;
-        for (int s = 0; s < L; ++s) rb_pnom[s] = double(m) * s;
-    } else {
-        for (int s = 0; s < L; ++s) rb_pnom[s] = T->rirf_t[s] / dt;
-        const double rows = std::floor(rb_pnom[L - 1]) + 2.0;
-        // FP64 work of the row-grid kernel (rows x D^2) against the HBM traffic of the per-step kernel (2 L rows)
-        if (rows < 2 * kRbT || rows * D > 64.0 * L) return;
-        rb_general = true; rb_m = 1; rb_Lk = int(rows);
-    }
-    rb_pi.resize(L); rb_pw.resize(L);
-    for (int s = 0; s < L; ++s) {
-        rb_pi[s] = int(std::floor(rb_pnom[s]));
-        rb_pw[s] = rb_pnom[s] - double(rb_pi[s]);
-    }
+    rb_plan = make_rad_plan(*T, opts.dt_hint, kRbMaxM, 2 * kRbT);      // hc_plan.cpp
+    if (!rb_plan.usable) return;
+    rb_general = rb_plan.general; rb_m = rb_plan.m; rb_Lk = rb_plan.Lk; rb_pnom = rb_plan.pnom;
     rb_occ = (D <= 12) ? 3 : 2;                                    // resident CTAs per SM of k_rad_block<D> (registers)
     rb_R = pick_chunk(rb_Lk - 1, tiles * rb_m, sm_count, rb_occ, size_t(rb_occ == 3 ? 74 : 110) * 1024,
                       rad_block_smem_bytes, D, 8);
@@ -447,32 +428,7 @@ void hc_ensemble::setup_radiation_block() {
 // history as it will be at that step, newest first.  smax = the largest lag with a bracket; the row-grid kernel
 // needs all of them (full window).
 bool hc_ensemble::rb_step_plan(const double* tm, int len, double snap, int& smax) const {
-    smax = -1;
-    if (len <= 1) return false;
-    const double* rt = T->rirf_t.data();
-    const double t0 = tm[0], oldest = tm[len - 1];
-    // lags with a bracket: oldest <= t0 - rt[s] (k_prestep's test, same subtraction); rt ascends, so they are 0..smax
-    if (!(oldest <= t0 - rt[0])) return false;
-    int lo = 0, hi = L - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (oldest <= t0 - rt[mid]) lo = mid; else hi = mid - 1;
-    }
-    if (rb_general && lo != L - 1) return false;
-    // every such lag at its nominal position i + w (rows back): |q - (tm[i] - w (tm[i] - tm[i+1]))| <= snap * spacing,
-    // i.e. bracket index + older-row weight within snap of the nominal ones (InterpolateVelocity6D's arithmetic)
-    const int* pi = rb_pi.data();
-    const double* pw = rb_pw.data();
-    for (int s = 0; s <= lo; ++s) {
-        const int i = pi[s];
-        const double w = pw[s];
-        if (i + (w > 0.0 ? 1 : 0) > len - 1) return false;
-        const double delta = (i + 1 < len) ? tm[i] - tm[i + 1] : tm[i - 1] - tm[i];
-        const double d = (t0 - rt[s]) - (tm[i] - w * delta);
-        if (!(std::fabs(d) <= snap * delta)) return false;
-    }
-    smax = lo;
-    return true;
+    return rad_plan_step(*T, rb_plan, tm, len, snap, smax);                // hc_plan.cpp
 }
 
 // Plans the block whose first step comes `base` steps after the current one (time t, already on `times`): predicted

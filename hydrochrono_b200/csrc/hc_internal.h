@@ -76,6 +76,19 @@ struct ExcIrfBody {       // resampled excitation IRF for one body (:572-628)
 };
 std::vector<ExcIrfBody> resample_excitation_irf(const hc_tables& T, double dt);
 
+// Radiation look-ahead planning (hc_plan.cpp): positions of the RIRF lags on the history-row grid
+struct RadPlan {
+    bool usable = false;
+    bool general = false;     // lag spacing is not a multiple of dt: row-grid kernel with the lerp weights folded in
+    int m = 1;                // history rows per lag (lag-grid path), 1 on the row grid
+    int Lk = 0;               // lags of the kernel the block path convolves with (L, or rows of the row grid)
+    dvec pnom;                // [L] nominal position of every lag, in rows back from the step
+    std::vector<int> pi;      // [L] its integer part (bracket index)
+    dvec pw;                  // [L] its fraction (weight of the older row)
+};
+RadPlan make_rad_plan(const hc_tables& T, double dt, int max_m, int min_lags);
+bool rad_plan_step(const hc_tables& T, const RadPlan& P, const double* tm, int len, double snap, int& smax);
+
 // H5 reader (hc_h5.cpp)
 hc_tables* load_bemio_h5(const char* path, int num_bodies);
 hc_tables* tables_from_desc(const hc_tables_desc& d);

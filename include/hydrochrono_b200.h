@@ -280,6 +280,16 @@ HC_API int hc_ensemble_rad_lookahead_steps(const hc_ensemble* e);
 HC_API hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, long long* steps_served, double* avg_ms,
                                         int reset);
 
+/* Host-side planning of the radiation look-ahead, exposed for testing (no device needed).
+   hc_rad_lookahead_plan: mode = 0 (the look-ahead cannot serve this step size), 1 (lag grid: RIRF lag spacing =
+   rows_per_lag * dt_hint) or 2 (row grid: interpolation weights folded into a kernel of kernel_lags rows).
+   hc_rad_lookahead_check_step: times_newest_first[0 .. n) = the time history at a step (element 0 = the step's time);
+   smax = the largest lag with a bracket when every bracketed lag sits within bracket_snap rows of its nominal
+   position (and, for mode 2, all lags are bracketed), else -1: the step would run the per-step kernel. */
+HC_API hc_status hc_rad_lookahead_plan(const hc_tables* t, double dt_hint, int* mode, int* rows_per_lag, int* kernel_lags);
+HC_API hc_status hc_rad_lookahead_check_step(const hc_tables* t, double dt_hint, double bracket_snap,
+                                             const double* times_newest_first, int n, int* smax);
+
 /* Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator for the FP64-bound kernels). */
 HC_API hc_status hc_measure_fp64_peak(int device, double* tflops);
 /* The same on the FP64 tensor cores (DMMA m8n8k4 loop). */

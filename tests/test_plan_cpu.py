@@ -1,0 +1,101 @@
+"""Host-side planning of the radiation look-ahead (hc_plan.cpp) against a restatement of the reference's bracket
+logic (TestHydro::AdvanceToBracket / InterpolateVelocity6D, src/hydro_forces.cpp:343-381,601-610).  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+import hydrochrono_b200 as hc
+from hydrochrono_b200 import synth
+
+
+def reference_plan(times, rirf_t):
+    """Per lag: None (no bracket) or the position of the query in history rows back from the step
+    (bracket index + weight of the older row), from the reference's own arithmetic."""
+    tm = list(times)
+    out = []
+    for ts in rirf_t:
+        q = tm[0] - ts
+        if not (tm[-1] <= q):
+            out.append(None)
+            continue
+        i = 0
+        while not (tm[i + 1] <= q):          # AdvanceToBracket: smallest i with time(i+1) <= q
+            i += 1
+        newer, older = tm[i], tm[i + 1]
+        if q == older:
+            out.append(float(i + 1))
+        elif q == newer:
+            out.append(float(i))
+        else:
+            out.append(i + (newer - q) / (newer - older))
+    return out
+
+
+def history(n, dt, window):
+    """Time history at step n of a run t += dt from 0, newest first, pruned like PruneHistory (:327-340)."""
+    t, ts = 0.0, [0.0]
+    for _ in range(n):
+        t += dt
+        ts.append(t)
+    tm = ts[::-1]
+    t_min = tm[0] - window
+    while len(tm) > 1 and tm[len(tm) - 2] < t_min:
+        tm.pop()
+    return tm
+
+
+def expected(tm, rirf_t, pnom, snap, need_all):
+    plan = reference_plan(tm, rirf_t)
+    smax = -1
+    for s, p in enumerate(plan):
+        if p is None:
+            break
+        if abs(p - pnom[s]) > snap:
+            return -1
+        smax = s
+    if need_all and smax != len(rirf_t) - 1:
+        return -1
+    return smax
+
+
+@pytest.mark.parametrize("nb,steps,duration,dt,mode,m", [
+    (2, 1001, 60.0, 0.01, 1, 6),       # the headline workload: lag spacing 0.06 = 6 dt
+    (1, 401, 4.0, 0.01, 1, 1),         # lag spacing = dt
+    (2, 601, 30.0, 0.03, 2, 1),        # OSWEC shape: ratio 5/3 -> row grid
+    (3, 401, 20.0, 0.02, 2, 1),        # F3OF shape: ratio 5/2 -> row grid
+])
+def test_plan_and_step_check(nb, steps, duration, dt, mode, m):
+    raw = synth.make_tables(num_bodies=nb, rirf_steps=steps, rirf_duration=duration)
+    T = hc.Tables.from_raw(raw)
+    rirf_t = np.linspace(0.0, duration, steps)
+    got_mode, got_m, lk = T.rad_lookahead_plan(dt)
+    assert (got_mode, got_m) == (mode, m)
+    pnom = (m * np.arange(steps)).astype(float) if mode == 1 else rirf_t / dt
+    assert lk == (steps if mode == 1 else math.floor(pnom[-1]) + 2)
+    full = int(round(duration / dt))
+    for n in (1, 2, 7, full // 3, full - 1, full, full + 1, full + 57):
+        tm = history(n, dt, duration)
+        for snap in (1e-8, 0.0):
+            want = expected(tm, rirf_t, pnom, snap, need_all=(mode == 2))
+            got = T.rad_lookahead_check_step(dt, snap, tm)
+            # snap = 0 asks for exact hits: the device snaps nothing either, both sides must agree lag by lag
+            assert got == want, (n, snap, got, want)
+    # with the window full and snapped brackets every step is served
+    assert T.rad_lookahead_check_step(dt, 1e-8, history(full + 5, dt, duration)) == steps - 1
+
+
+def test_irregular_steps_are_rejected():
+    raw = synth.rm3_like()
+    T = hc.Tables.from_raw(raw)
+    rng = np.random.default_rng(3)
+    ts = np.concatenate([[0.0], np.cumsum(rng.uniform(0.004, 0.012, size=400))])
+    assert T.rad_lookahead_check_step(0.01, 1e-8, ts[::-1].copy()) == -1
+    # one perturbed row in an otherwise uniform history: the lags that land on it are off by 3e-3 rows
+    tm = np.array(history(300, 0.01, 60.0))
+    assert T.rad_lookahead_check_step(0.01, 1e-8, tm) >= 0
+    tm[120] += 3e-5
+    assert T.rad_lookahead_check_step(0.01, 1e-8, tm) == -1
+    # a step size the plan was not made for
+    assert T.rad_lookahead_check_step(0.02, 1e-8, np.array(history(300, 0.01, 60.0))) == -1
+    assert T.rad_lookahead_plan(0.0007)[0] == 0          # 86 rows per lag: neither grid pays off
