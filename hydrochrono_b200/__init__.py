@@ -219,6 +219,14 @@ class Tables:
         _check(lib.hc_rad_lookahead_plan(self._h, float(dt_hint), C.byref(mode), C.byref(m), C.byref(lk)))
         return mode.value, m.value, lk.value
 
+    def rad_lookahead_row_kernel(self, dt_hint):
+        """[kernel_lags][6N][6N] kernel the look-ahead blocks convolve the history rows with."""
+        _, _, lk = self.rad_lookahead_plan(dt_hint)
+        D = 6 * self.num_bodies
+        out = np.empty((lk, D, D))
+        _check(lib.hc_rad_lookahead_row_kernel(self._h, float(dt_hint), _dp(out)))
+        return out
+
     def rad_lookahead_check_step(self, dt_hint, bracket_snap, times_newest_first):
         """smax (largest bracketed lag) if the look-ahead could serve a step with this time history, else -1."""
         tm = _f64(times_newest_first)

@@ -288,22 +288,7 @@ void hc_ensemble::stage_kernel() {
         // multiple of dt: Krow = (K w) on the lag grid (row m s <-> lag s).  Otherwise the linear interpolation of the
         // velocity between rows i and i + 1 at the nominal position x_s = t_rirf[s] / dt = i + wo is folded into the
         // kernel:  (K w)[s] (wn v_i + wo v_{i+1})  ->  Krow[i] += wn (K w)[s],  Krow[i + 1] += wo (K w)[s].
-        std::vector<double> Krow(size_t(rb_Lk) * D * D, 0.0);
-        for (int s = 0; s < L; ++s) {
-            int i = s;
-            double wn = 1.0, wo = 0.0;
-            if (rb_general) {
-                i = int(std::floor(rb_pnom[s]));
-                wo = rb_pnom[s] - double(i);
-                wn = 1.0 - wo;
-            }
-            for (int r = 0; r < D; ++r)
-                for (int c = 0; c < D; ++c) {
-                    const double kw = t->Keff[(size_t(r) * D + c) * L + s] * t->rirf_w[s];
-                    if (i < rb_Lk) Krow[(size_t(i) * D + r) * D + c] += wn * kw;
-                    if (wo != 0.0 && i + 1 < rb_Lk) Krow[(size_t(i + 1) * D + r) * D + c] += wo * kw;
-                }
-        }
+        const std::vector<double> Krow = rad_plan_row_kernel(*t, rb_plan);     // hc_plan.cpp, [rb_Lk][D][D]
         // device copies: [lag][row][col padded to a multiple of 4] with lag stride rb_stride(D), zero beyond the last
         // lag (rows older than the kernel's support), and the first lags as [lag][col][row] for k_step
         const int lags = rb_nchunk * rb_R + 2 * kRbT + 1;

@@ -3,6 +3,7 @@
 // would compute for one step (hydro_forces.cpp:343-381,601-610; k_prestep on the device) keeps every lag there.
 #include "hc_internal.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace hc {
@@ -71,6 +72,31 @@ bool rad_plan_step(const hc_tables& T, const RadPlan& P, const double* tm, int l
     return true;
 }
 
+// The kernel the block path convolves the history ROWS with, Krow[i][r][c], i = rows back from the step.  Lag grid:
+// Krow = (K w) (row m s <-> lag s, stored per lag).  Row grid: the linear interpolation of the velocity between rows
+// i and i + 1 at the nominal position x_s = i + wo is folded into the kernel,
+//   (K w)[s] (wn v_i + wo v_{i+1})   ->   Krow[i] += wn (K w)[s],   Krow[i + 1] += wo (K w)[s].
+dvec rad_plan_row_kernel(const hc_tables& T, const RadPlan& P) {
+    const int L = T.L, D = T.D;
+    dvec Krow(size_t(P.Lk) * D * D, 0.0);
+    for (int s = 0; s < L; ++s) {
+        int i = s;
+        double wn = 1.0, wo = 0.0;
+        if (P.general) {
+            i = P.pi[s];
+            wo = P.pw[s];
+            wn = 1.0 - wo;
+        }
+        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) {
+                const double kw = T.Keff[(size_t(r) * D + c) * L + s] * T.rirf_w[s];
+                if (i < P.Lk) Krow[(size_t(i) * D + r) * D + c] += wn * kw;
+                if (wo != 0.0 && i + 1 < P.Lk) Krow[(size_t(i + 1) * D + r) * D + c] += wo * kw;
+            }
+    }
+    return Krow;
+}
+
 }  // namespace hc
 
 extern "C" {
@@ -81,6 +107,15 @@ hc_status hc_rad_lookahead_plan(const hc_tables* t, double dt_hint, int* mode, i
     if (mode) *mode = !P.usable ? 0 : (P.general ? 2 : 1);
     if (rows_per_lag) *rows_per_lag = P.usable ? P.m : 0;
     if (kernel_lags) *kernel_lags = P.usable ? P.Lk : 0;
+    return HC_OK;
+}
+
+hc_status hc_rad_lookahead_row_kernel(const hc_tables* t, double dt_hint, double* out) {
+    if (!t || !out) { hc::set_last_error("null argument"); return HC_ERR_INVALID; }
+    const hc::RadPlan P = hc::make_rad_plan(*t, dt_hint, 8, 16);
+    if (!P.usable) { hc::set_last_error("the radiation look-ahead cannot serve this step size"); return HC_ERR_INVALID; }
+    const hc::dvec K = hc::rad_plan_row_kernel(*t, P);
+    std::copy(K.begin(), K.end(), out);
     return HC_OK;
 }
 

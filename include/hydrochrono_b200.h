@@ -287,6 +287,8 @@ HC_API hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, lon
    smax = the largest lag with a bracket when every bracketed lag sits within bracket_snap rows of its nominal
    position (and, for mode 2, all lags are bracketed), else -1: the step would run the per-step kernel. */
 HC_API hc_status hc_rad_lookahead_plan(const hc_tables* t, double dt_hint, int* mode, int* rows_per_lag, int* kernel_lags);
+/* The kernel the block path convolves the history rows with: out[kernel_lags][6N][6N] (row, column). */
+HC_API hc_status hc_rad_lookahead_row_kernel(const hc_tables* t, double dt_hint, double* out);
 HC_API hc_status hc_rad_lookahead_check_step(const hc_tables* t, double dt_hint, double bracket_snap,
                                              const double* times_newest_first, int n, int* smax);
 

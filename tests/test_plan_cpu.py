@@ -99,3 +99,39 @@ def test_irregular_steps_are_rejected():
     # a step size the plan was not made for
     assert T.rad_lookahead_check_step(0.02, 1e-8, np.array(history(300, 0.01, 60.0))) == -1
     assert T.rad_lookahead_plan(0.0007)[0] == 0          # 86 rows per lag: neither grid pays off
+
+
+@pytest.mark.parametrize("nb,steps,duration,dt", [(2, 601, 30.0, 0.03), (1, 401, 4.0, 0.01), (2, 1001, 60.0, 0.01)])
+def test_row_kernel_reproduces_the_reference_convolution(nb, steps, duration, dt):
+    """sum_s K[:, :, s] w[s] lerp(v, t - t_s)  (hydro_forces.cpp:586-647)  ==  sum_i Krow[i] v[row i]  for a history on a
+    uniform grid: the row-grid kernel folds the interpolation weights in, the lag-grid kernel is (K w) itself."""
+    raw = synth.make_tables(num_bodies=nb, rirf_steps=steps, rirf_duration=duration)
+    T = hc.Tables.from_raw(raw)
+    D = 6 * nb
+    mode, m, lk = T.rad_lookahead_plan(dt)
+    Krow = T.rad_lookahead_row_kernel(dt)
+    assert Krow.shape == (lk, D, D)
+    K = T.rirf()                      # [D][D][L], what GetRIRFval returns
+    w = T.rirf_width()
+    rirf_t = T.rirf_time()
+    n = int(round(duration / dt)) + 9
+    tm = np.array(history(n, dt, duration))
+    rng = np.random.default_rng(8)
+    v = rng.standard_normal((len(tm), D))              # row i = velocity sample at tm[i]
+    plan = reference_plan(tm, rirf_t)
+    ref = np.zeros(D)
+    for s, p in enumerate(plan):
+        assert p is not None
+        i = int(math.floor(p))
+        wo = p - i
+        vq = v[i] if wo == 0.0 else (1.0 - wo) * v[i] + wo * v[i + 1]
+        ref += K[:, :, s] @ (vq * w[s])
+    rows = m * np.arange(lk) if mode == 1 else np.arange(lk)
+    rows = rows[rows < len(tm)]
+    got = np.einsum("irc,ic->r", Krow[: len(rows)], v[rows])
+    # the reference gives the neighbouring row a weight of the size of the rounding noise of the accumulated times
+    # (|p - p_nominal| ~ 1e-11 rows at t ~ 60 s); with white-noise rows that is the whole difference.  The block path
+    # is only used when that offset is below bracket_snap (1e-8 in bench.py), the bound asserted here.
+    dev = max(abs(p - q) for p, q in zip(plan, (m * np.arange(steps)).astype(float) if mode == 1 else rirf_t / dt))
+    assert dev < 1e-8
+    assert np.abs(got - ref).max() <= max(1e-12, 50 * dev) * np.abs(ref).max()
