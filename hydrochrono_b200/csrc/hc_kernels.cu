@@ -8,6 +8,11 @@
 //                                                        src/hydro_forces.cpp:586-647
 //   k_excitation  batched excitation-IRF convolution over the precomputed free-surface elevation
 //                                                        src/wave_types.cpp:552-570,776-844
+//   k_rad_block<D> / k_step<D>      radiation look-ahead: the resident history rows' share of the next 8 m steps in
+//                 one pass on the FP64 tensor cores (DMMA m8n8k4), and the per-step kernel that completes a step
+//                 served that way (append, partial sums, rows appended since the snapshot, finalize)
+//   k_la_brackets / k_la_taps / k_exc_block(_mma)<ND>   excitation look-ahead: the wave force of the next 8 predicted
+//                 step times in one pass over eta (state-independent, wave_types.cpp:776-844)
 //   k_finalize    reduces the lag-chunk partials in fixed order, adds hydrostatics and regular-wave
 //                 excitation, forms total = hydrostatic - radiation + waves
 //                                                        src/hydro_forces.cpp:263-322,758-760; src/wave_types.cpp:315-327
