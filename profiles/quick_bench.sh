@@ -1,1 +1,6 @@
-python -m pytest tests -m gpu -x -q -k "baseline_config_shapes and (oswec or f3of) or test_rm3_radiation_lookahead and 1e-08-5-6" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --no-cpu 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_final.json
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_final.json'))
+print('value %.2fM e2e %.2fM ms/step %.4f launches %d' % (d['value']/1e6, d['e2e']['value']/1e6, d['ms_per_step'], d['gpu_launches']), d['clocks']['sm_mhz'], d['roofline']['frac'], d['roofline']['traffic'])"
