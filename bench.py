@@ -519,8 +519,10 @@ def main():
                                                      {0: "background stream, DMMA", 2: "in-stream", 3: "background stream", 4: "in-stream, DMMA",
                                                       5: "background stream, DMMA"}
                                                      .get(args.lookahead_mode, str(args.lookahead_mode))),
-                       "l2": "inputs larger than L2: %.1f GB history window + %.1f GB eta per GPU, ~%.2f GB touched per step"
-                             % (8e-9 * DOFS * B * ens.history_len(), 8e-9 * B * n_eta, 1e-9 * (rad_bytes + exc_bytes)),
+                       "l2": "inputs larger than L2 (126 MB), no flush needed: %.1f GB history window + %.1f GB eta per "
+                             "GPU, streamed once per %d / 8 steps (~%.2f GB of them touched per step)"
+                             % (8e-9 * DOFS * B * ens.history_len(), 8e-9 * B * n_eta, rb_T if rb_on else 1,
+                                1e-9 * step_bytes),
                        "timing": "value: CUDA events on the ensemble's stream around K hc_step_device calls (wall %.4f s, "
                                  "of which %.4f s to enqueue them); "
                                  "e2e: wall clock around K synchronous hc_step calls; per-kernel ms: CUDA events inside "
