@@ -135,3 +135,38 @@ def test_row_kernel_reproduces_the_reference_convolution(nb, steps, duration, dt
     dev = max(abs(p - q) for p, q in zip(plan, (m * np.arange(steps)).astype(float) if mode == 1 else rirf_t / dt))
     assert dev < 1e-8
     assert np.abs(got - ref).max() <= max(1e-12, 50 * dev) * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nb,steps,duration,dt", [(2, 1001, 60.0, 0.01), (2, 601, 30.0, 0.03)])
+@pytest.mark.parametrize("base_blocks", [0, 1])
+def test_block_decomposition_is_the_full_convolution(nb, steps, duration, dt, base_blocks):
+    """The identity k_rad_block<D> / k_step<D> are built on, written out with numpy on the
+    library's own row kernel: for a block whose snapshot of the history was taken `base` steps before its first step,
+        F_j = sum_u Krow[u + g + 1] v_res[m u + m - 1 - rho]  +  sum_{l <= jj / m} Krow[l] v_young[jj - m l],
+    jj = base + j = rho + m g, equals the convolution of all rows with the row kernel."""
+    raw = synth.make_tables(num_bodies=nb, rirf_steps=steps, rirf_duration=duration)
+    T = hc.Tables.from_raw(raw)
+    D = 6 * nb
+    mode, m, lk = T.rad_lookahead_plan(dt)
+    K = T.rad_lookahead_row_kernel(dt)                      # [lk][D][D], one entry per lag (lag grid) or row (row grid)
+    TT = 8 * m
+    base = base_blocks * TT
+    n0 = m * (lk - 1) + 40                                  # snapshot step: the window is full
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((n0 + 2 * TT + 1, D))           # v[n] = velocity sample of step n
+    for j in (0, 1, m - 1 if m > 1 else 2, TT // 2, TT - 1):
+        jj = base + j
+        n = n0 + jj                                         # this step
+        # direct: lag s (lag grid) or row i (row grid) reads the sample m s (or i) steps back
+        direct = sum(K[s] @ v[n - m * s] for s in range(lk))
+        rho, g = jj % m, jj // m
+        # resident rows: r = 0 is the newest sample before the snapshot step, i.e. step n0 - 1 - r
+        resident = np.zeros(D)
+        u = 0
+        while u + g + 1 < lk:
+            r = m * u + (m - 1 - rho)
+            resident += K[u + g + 1] @ v[n0 - 1 - r]
+            u += 1
+        # young rows: appended by the snapshot step and after it, k = jj - m l steps after the snapshot
+        young = sum(K[l] @ v[n0 + jj - m * l] for l in range(min(g, lk - 1) + 1))
+        assert np.abs(resident + young - direct).max() <= 1e-12 * np.abs(direct).max(), (j, jj)
