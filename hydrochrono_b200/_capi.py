@@ -120,6 +120,8 @@ SIGNATURES = {
     "hc_measure_fp64_peak": (C.c_int, [C.c_int, dp]),
     "hc_measure_fp64_mma_peak": (C.c_int, [C.c_int, dp]),
     "hc_rad_lookahead_plan": (C.c_int, [vp, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hc_rad_pass_next": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.c_int, C.c_longlong,
+                                   C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hc_rad_lookahead_row_kernel": (C.c_int, [vp, C.c_double, dp]),
     "hc_rad_lookahead_check_step": (C.c_int, [vp, C.c_double, C.c_double, dp, C.c_int, C.POINTER(C.c_int)]),
     "hc_ensemble_rad_lookahead_steps": (C.c_int, [vp]),

@@ -112,7 +112,12 @@ struct hc_ensemble {
     } rbk[2];                                     // double-buffered: the block being served / the one evaluated ahead
     int rb_cur = 0, rb_pos = 0;
     bool rb_ahead = false;                        // next block evaluated one block ahead, one slice after every step
-    struct RbPass { RadBlockArgs args{}; int items = 0, next_slice = 0, nslices = 0; bool active = false; } rb_pass;
+    struct RbPass {
+        RadBlockArgs args{};
+        int items = 0, next_slice = 0, nslices = 0;
+        long long next_item = 0;                  // where the next slice starts
+        bool active = false;
+    } rb_pass;
     cudaStream_t rb_stream = nullptr;             // slices run here, each gated by its step's phase 2
     cudaEvent_t ev_rb_side = nullptr;             // last slice enqueued on rb_stream
     bool rb_side_pending = false;
@@ -464,7 +469,7 @@ void hc_ensemble::rb_setup_pass(int buf) {
     ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;
     rb_pass.items = rad_block_items(ba);
     rb_items_per_pass = rb_pass.items;
-    rb_pass.next_slice = 0; rb_pass.nslices = TT; rb_pass.active = true;
+    rb_pass.next_slice = 0; rb_pass.next_item = 0; rb_pass.nslices = TT; rb_pass.active = true;
     ++rb_launches;
     Bk.valid = true;
 }
@@ -476,26 +481,21 @@ void hc_ensemble::rb_launch_slices(int count, bool side) {
     if (!rb_pass.active) return;
     side = side && !profiling && rb_stream;
     cudaStream_t st = side ? rb_stream : stream;
-    const int s0 = rb_pass.next_slice, s1 = std::min(rb_pass.nslices, s0 + count);
     // Device-resident stepping (hc_step_device) queues steps back to back: slice boundaries on whole waves of
     // resident CTAs (3 per SM), so that no slice ends in a nearly empty wave.  Host-buffer stepping (hc_step) leaves
-    // the GPU a window of copies + caller turnaround after every step: equal slices fit that window best.
-    const long long N = rb_pass.items, n = rb_pass.nslices, wave = host_stepping ? 1 : (long long)sm_count * rb_occ;
-    auto cut = [&](int sl) -> int {
-        if (sl >= n) return int(N);
-        const long long x = N * sl / n;
-        return int(std::min(N, (x + wave / 2) / wave * wave));
-    };
-    const int i0 = cut(s0), i1 = cut(s1);
-    rb_pass.next_slice = s1;
-    if (s1 >= rb_pass.nslices) rb_pass.active = false;
-    if (i1 <= i0) return;
+    // the GPU a window of copies + caller turnaround after every step: equal slices fit that window best.  A range
+    // always starts where the previous one ended (hc_plan.cpp), so a caller may mix the two inside a block.
+    const long long wave = host_stepping ? 1 : (long long)sm_count * rb_occ;
+    long long i0 = 0, i1 = 0;
+    const bool any = rad_pass_next(rb_pass.items, rb_pass.nslices, rb_pass.next_slice, rb_pass.next_item, count, wave, i0, i1);
+    if (rb_pass.next_slice >= rb_pass.nslices) rb_pass.active = false;
+    if (!any) return;
     RadBlockArgs ba = rb_pass.args;
-    ba.item0 = i0;
+    ba.item0 = int(i0);
     if (side) CUDA_CHECK(cudaStreamWaitEvent(rb_stream, ev_force, 0));
     if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], st));
-    CUDA_CHECK(launch_rad_block(ba, i1 - i0, st));
-    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], st)); rb_events_pending = true; rb_items_pending = i1 - i0; }
+    CUDA_CHECK(launch_rad_block(ba, int(i1 - i0), st));
+    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], st)); rb_events_pending = true; rb_items_pending = int(i1 - i0); }
     if (side) { CUDA_CHECK(cudaEventRecord(ev_rb_side, rb_stream)); rb_side_pending = true; }
     prof.kernel_launches += 1;
 }

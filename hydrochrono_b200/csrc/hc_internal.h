@@ -89,6 +89,8 @@ struct RadPlan {
 RadPlan make_rad_plan(const hc_tables& T, double dt, int max_m, int min_lags);
 bool rad_plan_step(const hc_tables& T, const RadPlan& P, const double* tm, int len, double snap, int& smax);
 dvec rad_plan_row_kernel(const hc_tables& T, const RadPlan& P);
+bool rad_pass_next(long long N, int nslices, int& next_slice, long long& next_item, int count, long long wave,
+                   long long& i0, long long& i1);
 
 // H5 reader (hc_h5.cpp)
 hc_tables* load_bemio_h5(const char* path, int num_bodies);

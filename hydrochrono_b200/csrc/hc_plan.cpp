@@ -97,6 +97,26 @@ dvec rad_plan_row_kernel(const hc_tables& T, const RadPlan& P) {
     return Krow;
 }
 
+// Next range of work items of a pass that is launched in `nslices` slices: [i0, i1) for the `count` slices after
+// `next_slice`.  Nominal boundaries N s / nslices are rounded to multiples of `wave` (whole waves of resident CTAs;
+// 1 = equal slices).  The range always starts where the previous one ended, whatever `wave` was then, and the last
+// slice always ends at N, so the slices of a pass cover [0, N) exactly once even if the policy changes on the way.
+bool rad_pass_next(long long N, int nslices, int& next_slice, long long& next_item, int count, long long wave,
+                   long long& i0, long long& i1) {
+    const int s1 = std::min(nslices, next_slice + std::max(count, 0));
+    if (wave < 1) wave = 1;
+    long long end = N;
+    if (s1 < nslices) {
+        const long long x = N * s1 / nslices;
+        end = std::min(N, (x + wave / 2) / wave * wave);
+    }
+    i0 = next_item;
+    i1 = std::max(i0, end);
+    next_slice = s1;
+    next_item = i1;
+    return i1 > i0;
+}
+
 }  // namespace hc
 
 extern "C" {
@@ -108,6 +128,11 @@ hc_status hc_rad_lookahead_plan(const hc_tables* t, double dt_hint, int* mode, i
     if (rows_per_lag) *rows_per_lag = P.usable ? P.m : 0;
     if (kernel_lags) *kernel_lags = P.usable ? P.Lk : 0;
     return HC_OK;
+}
+
+int hc_rad_pass_next(long long items, int nslices, int* next_slice, long long* next_item, int count, long long wave,
+                     long long* i0, long long* i1) {
+    return hc::rad_pass_next(items, nslices, *next_slice, *next_item, count, wave, *i0, *i1) ? 1 : 0;
 }
 
 hc_status hc_rad_lookahead_row_kernel(const hc_tables* t, double dt_hint, double* out) {

@@ -287,6 +287,11 @@ HC_API hc_status hc_get_rad_block_stats(hc_ensemble* e, long long* launches, lon
    smax = the largest lag with a bracket when every bracketed lag sits within bracket_snap rows of its nominal
    position (and, for mode 2, all lags are bracketed), else -1: the step would run the per-step kernel. */
 HC_API hc_status hc_rad_lookahead_plan(const hc_tables* t, double dt_hint, int* mode, int* rows_per_lag, int* kernel_lags);
+/* Slicing of a look-ahead pass of `items` work items into `nslices` launches (test hook of the launcher's arithmetic):
+   advances the cursor (next_slice, next_item) by `count` slices with boundaries rounded to multiples of `wave` and
+   returns 1 with the range [i0, i1) to launch, 0 when the range is empty.  The ranges of a pass tile [0, items). */
+HC_API int hc_rad_pass_next(long long items, int nslices, int* next_slice, long long* next_item, int count, long long wave,
+                            long long* i0, long long* i1);
 /* The kernel the block path convolves the history rows with: out[kernel_lags][6N][6N] (row, column). */
 HC_API hc_status hc_rad_lookahead_row_kernel(const hc_tables* t, double dt_hint, double* out);
 HC_API hc_status hc_rad_lookahead_check_step(const hc_tables* t, double dt_hint, double bracket_snap,

@@ -1,6 +1,1 @@
-python bench.py --no-cpu --steps 300 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_final2.json
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_final2.json'))
-print('value %.2fM e2e %.2fM' % (d['value']/1e6, d['e2e']['value']/1e6), d['config']['l2'])"
-tail -2 gpurun_out/bench_err.log
+python -m pytest tests -m gpu -x -q -k "mixing_host_and_device" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log

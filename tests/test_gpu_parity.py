@@ -628,3 +628,37 @@ def test_radiation_lookahead_reset_and_wrong_hint(rm3):
     _assert_parity(np.array(got), np.array(want), "wrong dt_hint")
     assert ens.rad_block_stats()["steps_served"] <= 3        # at most the first step of a block that then misses
     assert ens.history_len() == insts[0].history_len() > 3100
+
+
+@pytest.mark.gpu
+def test_mixing_host_and_device_stepping_inside_a_block():
+    """hc_step (equal pass slices) and hc_step_device (wave-aligned pass slices) alternate in the middle of look-ahead
+    blocks: the slices of every pass must still cover all of its work items.  Batch large enough (2304 instances = 36
+    instance tiles x 2 chunks x 6 classes = 432+ items) for the two slicings to differ."""
+    import torch
+    raw = synth.make_tables(num_bodies=2, rirf_steps=101, rirf_duration=6.0)       # lag spacing 0.06 = 6 dt
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    B, D, dt = 2304, 12, 0.01
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
+    assert ens.rad_lookahead_steps() == 48
+    sample = [0, 63, 64, 1000, B - 1]
+    insts = [orc.Instance(O) for _ in sample]
+    dev = torch.device("cuda", 0)
+    d_pose = torch.empty((B, D), dtype=torch.float64, device=dev)
+    d_vel = torch.empty_like(d_pose)
+    d_force = torch.empty_like(d_pose)
+    got, want = [], []
+    for n, t in enumerate(_acc_times(700, dt)):
+        pose, vel = _motion(D, B, t)
+        if (n // 19) % 2 == 0:                      # switch the API every 19 steps: never aligned with the 48-step blocks
+            F = ens.step(t, pose, vel, G981)
+        else:
+            d_pose.copy_(torch.from_numpy(pose)); d_vel.copy_(torch.from_numpy(vel))
+            torch.cuda.synchronize()
+            ens.step_device(t, d_pose, d_vel, d_force, G981)
+            ens.sync()
+            F = d_force.cpu().numpy()
+        ref = np.array([i.force(t, pose[b], vel[b], G981) for b, i in zip(sample, insts)])
+        got.append(F[sample].copy()); want.append(ref)
+    _assert_parity(np.array(got), np.array(want), "mixed stepping")
+    assert ens.rad_block_stats()["steps_served"] == 699

@@ -170,3 +170,44 @@ def test_block_decomposition_is_the_full_convolution(nb, steps, duration, dt, ba
         # young rows: appended by the snapshot step and after it, k = jj - m l steps after the snapshot
         young = sum(K[l] @ v[n0 + jj - m * l] for l in range(min(g, lk - 1) + 1))
         assert np.abs(resident + young - direct).max() <= 1e-12 * np.abs(direct).max(), (j, jj)
+
+
+def test_pass_slices_tile_the_work_items_whatever_the_policy():
+    """The slices a look-ahead pass is launched in (hc_plan.cpp::rad_pass_next) cover [0, N) exactly once, also when
+    the rounding of the boundaries (whole waves for device-resident stepping, equal slices for host-buffer stepping)
+    changes in the middle of the pass."""
+    import ctypes as C
+    from hydrochrono_b200._capi import lib
+    rng = np.random.default_rng(12)
+    for N, nsl in ((27648, 48), (1536, 48), (59904, 8), (7, 48), (444 * 5, 16)):
+        for trial in range(20):
+            ns, ni = C.c_int(0), C.c_longlong(0)
+            covered, launches = [], 0
+            while ns.value < nsl:
+                wave = int(rng.choice([1, 444, 296]))
+                count = int(rng.choice([1, 1, 1, 4]))
+                i0, i1 = C.c_longlong(), C.c_longlong()
+                any_ = lib.hc_rad_pass_next(N, nsl, C.byref(ns), C.byref(ni), count, wave, C.byref(i0), C.byref(i1))
+                if any_:
+                    assert i1.value > i0.value
+                    covered.append((i0.value, i1.value))
+                    launches += 1
+                else:
+                    assert i1.value == i0.value
+            assert covered[0][0] == 0 and covered[-1][1] == N
+            assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    # one policy throughout: wave-aligned boundaries (except the end), equal slices with wave = 1
+    ns, ni = C.c_int(0), C.c_longlong(0)
+    ends = []
+    for _ in range(48):
+        i0, i1 = C.c_longlong(), C.c_longlong()
+        lib.hc_rad_pass_next(27648, 48, C.byref(ns), C.byref(ni), 1, 444, C.byref(i0), C.byref(i1))
+        ends.append(i1.value)
+    assert all(e % 444 == 0 for e in ends[:-1]) and ends[-1] == 27648
+    ns, ni = C.c_int(0), C.c_longlong(0)
+    ends = []
+    for _ in range(48):
+        i0, i1 = C.c_longlong(), C.c_longlong()
+        lib.hc_rad_pass_next(27648, 48, C.byref(ns), C.byref(ni), 1, 1, C.byref(i0), C.byref(i1))
+        ends.append(i1.value)
+    assert ends == [576 * (k + 1) for k in range(48)]
