@@ -1450,6 +1450,7 @@ hc_status hc_ensemble_refresh_rirf(hc_ensemble* e) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     if (e->rb_stream) CUDA_CHECK(cudaStreamSynchronize(e->rb_stream));
     e->rb_invalidate();              // blocks evaluated with the old kernel
+    e->drop_graph();                 // the captured kernels hold the addresses of the old tables
     e->stage_kernel();
     return HC_OK;
     HC_GUARD_END
