@@ -248,7 +248,7 @@ class Ensemble:
     """B lock-stepped TestHydro instances on one GPU."""
 
     def __init__(self, tables, batch=1, device=0, dt_hint=0.0, bracket_snap=0.0, rad_chunk=0, exc_chunk=0,
-                 use_graph=True, stream=None, exc_lookahead=0, rad_kernel=0, rad_lookahead=0):
+                 use_graph=True, stream=None, exc_lookahead=0, rad_kernel=0, rad_lookahead=0, rad_pass_mode=0):
         self.tables = tables  # keep alive
         o = _capi.EnsembleOpts()
         lib.hc_ensemble_default_opts(C.byref(o))
@@ -257,6 +257,7 @@ class Ensemble:
         o.exc_lookahead = int(exc_lookahead)
         o.rad_kernel = int(rad_kernel)
         o.rad_lookahead = int(rad_lookahead)
+        o.rad_pass_mode = int(rad_pass_mode)
         o.stream = stream
         h = C.c_void_p()
         _check(lib.hc_ensemble_create(tables._h, C.byref(o), C.byref(h)))
@@ -356,6 +357,15 @@ class Ensemble:
 
     def sync(self):
         _check(lib.hc_sync(self._h))
+
+    def join(self):
+        """Orders the ensemble's stream after all look-ahead work enqueued so far on the library's side streams."""
+        _check(lib.hc_ensemble_join(self._h))
+
+    def lookahead_state(self):
+        r, x = C.c_int(), C.c_int()
+        _check(lib.hc_ensemble_lookahead_state(self._h, C.byref(r), C.byref(x)))
+        return {"radiation": r.value, "excitation": x.value}
 
     def reset(self):
         _check(lib.hc_ensemble_reset(self._h))

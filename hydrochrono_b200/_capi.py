@@ -41,7 +41,7 @@ class TaperedOpts(C.Structure):
 class EnsembleOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("batch", C.c_int), ("dt_hint", C.c_double), ("bracket_snap", C.c_double),
                 ("rad_chunk", C.c_int), ("exc_chunk", C.c_int), ("use_graph", C.c_int), ("exc_lookahead", C.c_int),
-                ("rad_kernel", C.c_int), ("rad_lookahead", C.c_int), ("stream", vp)]
+                ("rad_kernel", C.c_int), ("rad_lookahead", C.c_int), ("rad_pass_mode", C.c_int), ("stream", vp)]
 
 
 class IrregularParams(C.Structure):
@@ -111,6 +111,8 @@ SIGNATURES = {
     "hc_waves_force_at_time": (C.c_int, [vp, C.c_double, dp]),
     "hc_ensemble_refresh_rirf": (C.c_int, [vp]),
     "hc_sync": (C.c_int, [vp]),
+    "hc_ensemble_join": (C.c_int, [vp]),
+    "hc_ensemble_lookahead_state": (C.c_int, [vp, ip, ip]),
     "hc_ensemble_history_len": (C.c_int, [vp]),
     "hc_added_mass_mv": (C.c_int, [vp, C.c_int, C.c_double, vp, vp]),
     "hc_added_mass_mv_device": (C.c_int, [vp, C.c_int, C.c_double, vp, vp]),

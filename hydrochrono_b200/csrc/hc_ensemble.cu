@@ -104,7 +104,6 @@ struct hc_ensemble {
     RadPlan rb_plan;                              // the same + bracket index / older-row weight per lag (hc_plan.cpp)
     DevBuf<double> d_Kyoung;                      // first 2 kRbT lags of that kernel, [lag][col][row] (k_step)
     DevBuf<double> d_Kpad, d_rb_partial[2];
-    DevBuf<int> d_rb_smax[2];
     std::vector<double> rb_scratch;
     struct RbBlock {
         double times[kRbT * kRbMaxM]; int smax[kRbT * kRbMaxM];
@@ -118,9 +117,16 @@ struct hc_ensemble {
         long long next_item = 0;                  // where the next slice starts
         bool active = false;
     } rb_pass;
-    cudaStream_t rb_stream = nullptr;             // slices run here, each gated by its step's phase 2
+    cudaStream_t rb_stream = nullptr;             // the pass of the block evaluated ahead runs here
     cudaEvent_t ev_rb_side = nullptr;             // last slice enqueued on rb_stream
+    cudaEvent_t ev_rb_snap = nullptr;             // main stream at the block's snapshot of the history
     bool rb_side_pending = false;
+    int rb_pass_mode = 1;                         // 1 slice per step gated by the step's forces, 2 slice per step
+                                                  // ungated, 3 whole pass at the block's first step
+    bool last_step_fast = false;                  // the previous step had an empty phase 1 (both look-aheads served it)
+    bool inputs_on_copy_stream = false;           // hc_step: the state upload of this step is on copy_stream (ev_inputs)
+    StepHeader hdr_h{};                           // header of the step being enqueued (k_step takes it by value)
+    bool hdr_on_device = false;                   // ... and whether this step also needs it in d_hdr
     bool host_stepping = false;                   // the current step came through hc_step (host buffers)
     int rb_builds = 0, rb_hits_this_block = 0, rb_poor_blocks = 0;
     long long rb_launches = 0, rb_steps_served = 0, rb_items_timed = 0;
@@ -177,6 +183,7 @@ struct hc_ensemble {
     int la_S = 1;                     // eta-row segments of the DMMA block kernel (partials summed by k_finalize)
     cudaStream_t la_stream = nullptr;
     cudaEvent_t ev_la_done[2] = {nullptr, nullptr}, ev_la_free[2] = {nullptr, nullptr}, ev_la_build = nullptr;
+    cudaEvent_t ev_la_join = nullptr;
     int la_builds = 0, la_hits_this_block = 0, la_poor_blocks = 0;
     DevBuf<double> d_la_cache, d_la_times;
     cudaEvent_t ev_la[2] = {nullptr, nullptr};
@@ -188,7 +195,6 @@ struct hc_ensemble {
     bool graph_valid = false, graph1_valid = false;
     cudaStream_t copy_stream = nullptr;                     // H2D of pose/vel overlaps phase 1
     cudaEvent_t ev_inputs = nullptr, ev_force = nullptr;   // state uploaded / forces of the step ready
-    const double* graph_pose = nullptr; const double* graph_vel = nullptr; double* graph_force = nullptr;
     bool profiling = false;
     int phase1_launches = 0;
     bool phase_uses_lookahead = false;    // set per step: phase 1 skips the per-step excitation kernels
@@ -217,9 +223,11 @@ struct hc_ensemble {
         for (auto& x : ev_la_done) if (x) cudaEventDestroy(x);
         for (auto& x : ev_la_free) if (x) cudaEventDestroy(x);
         if (ev_la_build) cudaEventDestroy(ev_la_build);
+        if (ev_la_join) cudaEventDestroy(ev_la_join);
         for (auto& x : ev_rb) if (x) cudaEventDestroy(x);
         if (rb_stream) { cudaStreamSynchronize(rb_stream); cudaStreamDestroy(rb_stream); }
         if (ev_rb_side) cudaEventDestroy(ev_rb_side);
+        if (ev_rb_snap) cudaEventDestroy(ev_rb_snap);
     }
     void drop_graph() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -241,16 +249,17 @@ struct hc_ensemble {
     int rb_plan_block(RbBlock& Bk, double t, int base);
     void rb_setup_pass(int buf);
     void rb_launch_slices(int count, bool side);
+    void rb_join_side();
     void rb_begin_ahead(int buf, double t);
     void rb_invalidate() { rbk[0].valid = rbk[1].valid = false; rb_pos = 0; rb_pass.active = false; }
-    void enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out, bool with_events);
-    void launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
-    void begin_step(double t, const double* g);
+    void enqueue_phase(int phase, bool with_events);
+    void launch_phase(int phase);
+    void begin_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void setup_lookahead();
     int lookahead_slot(double t);
     int enqueue_lookahead_block(int buf, double t0, cudaStream_t st);
     void prefetch_lookahead(int buf);
-    void finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
+    void finish_step(double t);
     void collect_events();
 };
 
@@ -288,7 +297,7 @@ void hc_ensemble::stage_kernel() {
         }
         d_Khyb.upload(Kh);
     }
-    if (rb_enabled) {
+    if (rb_plan.usable && rb_nchunk > 0) {        // look-ahead CONFIGURED (it may be switched off at run time and back on)
         // The kernel the block path convolves the history ROWS with, Krow[i][r][c], i = rows back.  Lag spacing a
         // multiple of dt: Krow = (K w) on the lag grid (row m s <-> lag s).  Otherwise the linear interpolation of the
         // velocity between rows i and i + 1 at the nominal position x_s = t_rirf[s] / dt = i + wo is folded into the
@@ -385,6 +394,7 @@ void hc_ensemble::setup_radiation_chunks() {
 // such that (instance tiles x chunks x m) fills whole waves of resident CTAs.
 void hc_ensemble::setup_radiation_block() {
     rb_enabled = false; rb_invalidate();
+    rb_plan = RadPlan{}; rb_nchunk = 0;
     const int want = opts.rad_lookahead;
     if (want == 1 || (D != 6 && D != 12 && D != 18) || opts.dt_hint <= 0.0) return;
     const int tiles = Bp / kRbTileInst;
@@ -397,16 +407,17 @@ void hc_ensemble::setup_radiation_block() {
                       rad_block_smem_bytes, D, 8);
     rb_nchunk = (rb_Lk - 1 + rb_R - 1) / rb_R;
     rb_ahead = (want != 3);                                        // 3 = whole pass at the block's first step
-    for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) {
-        d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
-        d_rb_smax[i].alloc(kRbT * kRbMaxM);
-    }
+    for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+    rb_pass_mode = opts.rad_pass_mode >= 1 && opts.rad_pass_mode <= 3 ? opts.rad_pass_mode : 1;
     if (!ev_rb[0]) { CUDA_CHECK(cudaEventCreate(&ev_rb[0])); CUDA_CHECK(cudaEventCreate(&ev_rb[1])); }
     if (rb_ahead && !rb_stream) {
         int lo = 0, hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority (numerically largest)
-        CUDA_CHECK(cudaStreamCreateWithPriority(&rb_stream, cudaStreamNonBlocking, (lo + hi) / 2));
+        // gated slices: above the excitation block's stream (they are held back by the steps); ungated / whole pass:
+        // below it, or the pass would starve the excitation block that the steps need sooner
+        CUDA_CHECK(cudaStreamCreateWithPriority(&rb_stream, cudaStreamNonBlocking, rb_pass_mode == 1 ? (lo + hi) / 2 : lo));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_rb_side, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_rb_snap, cudaEventDisableTiming));
     }
     rb_builds = 0; rb_hits_this_block = 0; rb_poor_blocks = 0;
     rb_enabled = true;
@@ -460,10 +471,10 @@ int hc_ensemble::rb_plan_block(RbBlock& Bk, double t, int base) {
 void hc_ensemble::rb_setup_pass(int buf) {
     RbBlock& Bk = rbk[buf];
     const int TT = kRbT * rb_m;
-    CUDA_CHECK(cudaMemcpyAsync(d_rb_smax[buf].p, Bk.smax, TT * sizeof(int), cudaMemcpyHostToDevice, stream));
     RadBlockArgs& ba = rb_pass.args;
     ba = RadBlockArgs{};
-    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p; ba.smax = d_rb_smax[buf].p;
+    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p;
+    std::copy(Bk.smax, Bk.smax + TT, ba.smax);
     ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (rb_Lk - 1));
     ba.D = D; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
     ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;
@@ -474,30 +485,52 @@ void hc_ensemble::rb_setup_pass(int buf) {
     Bk.valid = true;
 }
 
-// Launches the next `count` slices of the pending pass (slice i = items [N i / n, N (i + 1) / n)): on the main stream,
-// or on the side stream behind the step's forces (ev_force) so that the pass never runs ahead of the steps it is
-// interleaved with and the main stream never queues behind it.
+// Launches the next `count` slices of the pending pass (slice i = items [N i / n, N (i + 1) / n)) on the main stream
+// (side = false: a block that must be complete before the step that asked for it) or on the side stream.  There the
+// pass of the block evaluated ahead is paced in one of three ways (rb_pass_mode):
+//   1  one slice per step, each gated by its step's forces (ev_force): the pass never runs ahead of the steps it is
+//      interleaved with, the steps never queue behind it (what a caller that synchronises every step wants);
+//   2  one slice per step, not gated: two driver calls per step instead of five;
+//   3  the whole pass at the block's first step: one launch per block.
+// In modes 2 and 3 the side stream ranks below the excitation block's stream.  Every pass is ordered after the main
+// stream's position at the block's snapshot (ev_rb_snap: the rows it reads, the partial buffer it overwrites).
 void hc_ensemble::rb_launch_slices(int count, bool side) {
     if (!rb_pass.active) return;
     side = side && !profiling && rb_stream;
     cudaStream_t st = side ? rb_stream : stream;
-    // Device-resident stepping (hc_step_device) queues steps back to back: slice boundaries on whole waves of
-    // resident CTAs (3 per SM), so that no slice ends in a nearly empty wave.  Host-buffer stepping (hc_step) leaves
-    // the GPU a window of copies + caller turnaround after every step: equal slices fit that window best.  A range
-    // always starts where the previous one ended (hc_plan.cpp), so a caller may mix the two inside a block.
+    const bool gated = side && rb_pass_mode == 1;
+    // Back-to-back stepping (hc_step_device): slice boundaries on whole waves of resident CTAs (3 per SM), so that no
+    // slice ends in a nearly empty wave.  Host-buffer stepping (hc_step) leaves the GPU a window of copies + caller
+    // turnaround after every step: equal slices fit that window best.  A range always starts where the previous one
+    // ended (hc_plan.cpp), so a caller may mix the two inside a block.
     const long long wave = host_stepping ? 1 : (long long)sm_count * rb_occ;
     long long i0 = 0, i1 = 0;
+    const bool first = rb_pass.next_slice == 0;
     const bool any = rad_pass_next(rb_pass.items, rb_pass.nslices, rb_pass.next_slice, rb_pass.next_item, count, wave, i0, i1);
-    if (rb_pass.next_slice >= rb_pass.nslices) rb_pass.active = false;
-    if (!any) return;
-    RadBlockArgs ba = rb_pass.args;
-    ba.item0 = int(i0);
-    if (side) CUDA_CHECK(cudaStreamWaitEvent(rb_stream, ev_force, 0));
-    if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], st));
-    CUDA_CHECK(launch_rad_block(ba, int(i1 - i0), st));
-    if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], st)); rb_events_pending = true; rb_items_pending = int(i1 - i0); }
-    if (side) { CUDA_CHECK(cudaEventRecord(ev_rb_side, rb_stream)); rb_side_pending = true; }
-    prof.kernel_launches += 1;
+    const bool last = rb_pass.next_slice >= rb_pass.nslices;
+    if (last) rb_pass.active = false;
+    if (side && first && !gated) CUDA_CHECK(cudaStreamWaitEvent(rb_stream, ev_rb_snap, 0));
+    if (any) {
+        RadBlockArgs ba = rb_pass.args;
+        ba.item0 = int(i0);
+        if (gated) {
+            CUDA_CHECK(cudaEventRecord(ev_force, stream));
+            CUDA_CHECK(cudaStreamWaitEvent(rb_stream, ev_force, 0));
+        }
+        if (profiling) CUDA_CHECK(cudaEventRecord(ev_rb[0], st));
+        CUDA_CHECK(launch_rad_block(ba, int(i1 - i0), st));
+        if (profiling) { CUDA_CHECK(cudaEventRecord(ev_rb[1], st)); rb_events_pending = true; rb_items_pending = int(i1 - i0); }
+        prof.kernel_launches += 1;
+        if (side) rb_side_pending = true;
+    }
+}
+
+// Main stream waits for everything enqueued on the side stream (block switch, or a miss that abandons a pass).
+void hc_ensemble::rb_join_side() {
+    if (!rb_side_pending) return;
+    CUDA_CHECK(cudaEventRecord(ev_rb_side, rb_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(stream, ev_rb_side, 0));
+    rb_side_pending = false;
 }
 
 // Look-ahead by one block: at the first step of a block, the NEXT block is planned from the same snapshot of the
@@ -512,6 +545,12 @@ void hc_ensemble::rb_begin_ahead(int buf, double t) {
     if (int(times.size()) + TT + 2 > cap) return;
     if (rb_plan_block(rbk[buf], t, TT) < TT / 2) return;
     rb_setup_pass(buf);
+    if (rb_stream && !profiling && rb_pass_mode != 1) {
+        // everything the pass reads (rows appended by earlier steps) or overwrites (partials of the block before the
+        // current one) is ordered before this point of the main stream
+        CUDA_CHECK(cudaEventRecord(ev_rb_snap, stream));
+        if (rb_pass_mode == 3) rb_launch_slices(TT, true);
+    }
 }
 
 // Position of the step at time t inside the current radiation block, switching to the block evaluated ahead or
@@ -531,7 +570,7 @@ int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
     RbBlock& Nxt = rbk[rb_cur ^ 1];
     if (rb_ahead && Cur.valid && rb_pos == TT && Nxt.valid && !rb_pass.active && Nxt.len > 0 && Nxt.times[0] == t) {
         rb_cur ^= 1; rb_pos = 0; rb_hits_this_block = 0; rb_poor_blocks = 0;
-        if (rb_side_pending) { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_rb_side, 0)); rb_side_pending = false; }
+        rb_join_side();
         rb_begin_ahead(rb_cur ^ 1, t);
         return fill(rb_pos++);
     }
@@ -548,7 +587,7 @@ int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
     if (times.size() < 2) return -1;
     ++rb_builds;
     if (rb_plan_block(rbk[rb_cur], t, 0) < TT / 2) return -1;              // not worth a block pass
-    if (rb_side_pending) { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_rb_side, 0)); rb_side_pending = false; }
+    rb_join_side();
     rb_setup_pass(rb_cur);
     rb_launch_slices(TT, false);                                           // the whole pass, now
     rb_pos = 0;
@@ -559,10 +598,9 @@ int hc_ensemble::radiation_block_slot(double t, StepHeader& hh) {
 // The per-step kernel sequence in two phases.  Phase 1 needs only the step header (time): interpolation plans +
 // excitation convolution.  Phase 2 needs the step's state: history append, radiation convolution, finalize.
 // hc_step overlaps the pose/velocity H2D copy with phase 1.
-void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out,
-                                bool with_events) {
+void hc_ensemble::enqueue_phase(int phase, bool with_events) {
     PrestepArgs pa{};
-    pa.hdr = d_hdr.p; pa.vel = d_vel_in; pa.hist = d_hist.p; pa.times = d_times.p;
+    pa.hdr = d_hdr.p; pa.hist = d_hist.p; pa.times = d_times.p;
     pa.rirf_t = d_rirf_t.p; pa.rirf_w = d_rirf_w.p;
     pa.pr_new = d_pr_new.p; pa.pr_old = d_pr_old.p; pa.pr_wn = d_pr_wn.p; pa.pr_wo = d_pr_wo.p; pa.pr_wd = d_pr_wd.p;
     pa.pr_head = d_pr_head.p; pa.pr_lead = d_pr_lead.p;
@@ -617,20 +655,21 @@ void hc_ensemble::enqueue_phase(int phase, const double* d_pose_in, const double
             fg.dof0[g] = G.dof0; fg.nd[g] = G.nd; fg.chunk0[g] = G.chunk0; fg.nchunk[g] = G.nchunk;
         }
     FinalizeArgs fa{};
-    fa.hdr = d_hdr.p; fa.pose = d_pose_in; fa.rad_partial = d_rad_partial.p; fa.exc_partial = d_exc_partial.p;
-    fa.force = d_force_out; fa.comp = d_comp.p;
+    fa.hdr = d_hdr.p; fa.rad_partial = d_rad_partial.p; fa.exc_partial = d_exc_partial.p;
+    fa.comp = d_comp.p;
     fa.reg_amp = d_reg_amp.p; fa.reg_omega = d_reg_omega.p; fa.reg_mag = d_reg_mag.p; fa.reg_phase = d_reg_phase.p;
     fa.B = B; fa.Bp = Bp; fa.D = D; fa.N = N; fa.rad_nchunk = rad_nchunk; fa.wave_mode = wave_mode;
     fa.exc_ngroups = (wave_mode == 2) ? int(groups.size()) : 0; fa.exc_ndmax = exc_ndmax;
     fa.exc_cache = d_la_cache.p; fa.exc_S = la_S;
-    fa.vel = d_vel_in; fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
+    fa.K = d_K.p; fa.pr_lead = d_pr_lead.p; fa.pr_wd = d_pr_wd.p; fa.pr_head = d_pr_head.p; fa.L = L;
     if (rb_use) {
-        // served by the radiation look-ahead: append + block partials + young rows + finalize in one kernel
+        // served by the radiation look-ahead: append + block partials + young rows + finalize in one kernel that
+        // takes the step header by value (launched directly, never part of a captured graph)
         RadStepArgs sa{};
-        sa.hdr = d_hdr.p; sa.vel = d_vel_in; sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_Kyoung.p;
+        sa.hist = d_hist.p; sa.times = d_times.p; sa.K = d_Kyoung.p;
         sa.partial[0] = d_rb_partial[0].p; sa.partial[1] = d_rb_partial[1].p; sa.D = D;
         sa.B = B; sa.Bp = Bp; sa.nchunk = rb_nchunk; sa.L = rb_Lk; sa.m = rb_m;
-        CUDA_CHECK(launch_step(sa, fa, hs, fg, stream));
+        CUDA_CHECK(launch_step(sa, fa, hs, fg, hdr_h, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
     } else {
         CUDA_CHECK(launch_finalize(fa, hs, fg, stream));
@@ -670,26 +709,26 @@ void hc_ensemble::collect_events() {
     prof.step_seconds += 1e-3 * (plan + app + rad + exc + fin);
 }
 
-void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
-    const bool want_graph = opts.use_graph && !profiling;
+void hc_ensemble::launch_phase(int phase) {
+    // phase 2 of a step served by the radiation look-ahead is the single kernel k_step: launched directly
+    const bool want_graph = opts.use_graph && !profiling && !(phase == 2 && rb_use);
     if (!want_graph) {
-        enqueue_phase(phase, d_pose_in, d_vel_in, d_force_out, profiling);
+        enqueue_phase(phase, profiling);
         if (phase == 2) events_pending = profiling;
         return;
     }
     cudaGraph_t& g = phase == 1 ? graph1 : graph;
     cudaGraphExec_t& ge = phase == 1 ? graph1_exec : graph_exec;
     const int key = (phase_uses_lookahead ? 1 : 0) | (rb_use ? 2 : 0) | (skip_radiation ? 4 : 0);
-    bool valid = phase == 1 ? (graph1_valid && graph_key[1] == key)
-                            : (graph_valid && graph_key[2] == key && graph_pose == d_pose_in && graph_vel == d_vel_in &&
-                               graph_force == d_force_out);
+    // (the step's pose / velocity / force pointers travel in the header, so the graphs do not depend on them)
+    const bool valid = (phase == 1 ? graph1_valid : graph_valid) && graph_key[phase] == key;
     if (!valid) {
         if (ge) cudaGraphExecDestroy(ge);
         if (g) cudaGraphDestroy(g);
         ge = nullptr; g = nullptr;
         CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         try {
-            enqueue_phase(phase, d_pose_in, d_vel_in, d_force_out, false);
+            enqueue_phase(phase, false);
         } catch (...) {
             cudaGraph_t tmp = nullptr;
             cudaStreamEndCapture(stream, &tmp);
@@ -699,29 +738,30 @@ void hc_ensemble::launch_phase(int phase, const double* d_pose_in, const double*
         CUDA_CHECK(cudaStreamEndCapture(stream, &g));
         CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
         graph_key[phase] = key;
-        if (phase == 1) { graph1_valid = true; }
-        else { graph_valid = true; graph_pose = d_pose_in; graph_vel = d_vel_in; graph_force = d_force_out; }
+        if (phase == 1) graph1_valid = true; else graph_valid = true;
     }
     CUDA_CHECK(cudaGraphLaunch(ge, stream));
 }
 
 // Host-side bookkeeping of one recompute (hydro_forces.cpp:746-760) + phase 1 launch.
-void hc_ensemble::begin_step(double t, const double* g) {
+void hc_ensemble::begin_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
     // --- ComputeForceRadiationDampingConv's host-side bookkeeping ---
     if (!times.empty() && t == times.front())
         fail(HC_ERR_DUPLICATE_TIME, "Tried to compute the radiation damping convolution twice within the same time step!");
     if (!times.empty() && t < times.front())
         fail(HC_ERR_TIME_ORDER, "Radiation convolution: interpolation error; query_time not bracketed by history.");
+    std::string eta_error;
     if (wave_mode == 2) {
         // ExcitationConvolution bounds (wave_types.cpp:800,833-840): every t - tau_j must lie inside the eta window
         const double tmin = eta_t_h.front(), tmax = eta_t_h.back();
         for (auto& G : groups) {
             const double hi = t - G->tau_first, lo = t - G->tau_last;
-            if (!(tmin <= lo && hi <= tmax))
-                fail(HC_ERR_ETA_WINDOW,
-                     "Excitation convolution: trying to find free surface elevation at a time out of bounds from the "
-                     "precomputed free surface elevation (" + std::to_string(hi > tmax ? hi : lo) + "not in [" +
-                     std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.");
+            if (!(tmin <= lo && hi <= tmax)) {
+                eta_error = "Excitation convolution: trying to find free surface elevation at a time out of bounds from the "
+                            "precomputed free surface elevation (" + std::to_string(hi > tmax ? hi : lo) + "not in [" +
+                            std::to_string(tmin) + ", " + std::to_string(tmax) + "]). Excitation force ignored at this time step.";
+                break;
+            }
         }
     }
     if (int(times.size()) >= cap) {
@@ -738,23 +778,48 @@ void hc_ensemble::begin_step(double t, const double* g) {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         collect_events();
     }
-    // Pageable source: the runtime stages small copies at call time, so the stack header can be reused at once.
-    StepHeader hh{};
+    StepHeader& hh = hdr_h;
+    hh = StepHeader{};
     hh.t = t; hh.g[0] = g[0]; hh.g[1] = g[1]; hh.g[2] = g[2];
     hh.snap = opts.bracket_snap; hh.head = head; hh.len = int(times.size()); hh.cap = cap; hh.flags = 0;
+    hh.pose = d_pose_in; hh.vel = d_vel_in; hh.force = d_force.p;
+    hh.force2 = (d_force_out != d_force.p) ? d_force_out : nullptr;   // the caller's buffer + the time-keyed cache
     phase_uses_lookahead = false;
+    rb_use = false;
+    if (!eta_error.empty()) {
+        // The reference throws from ComputeForceWaves (wave_types.cpp:833-840) AFTER ComputeForceRadiationDampingConv
+        // has pushed the step's sample and after prev_time was set (hydro_forces.cpp:747-756): the history keeps the
+        // sample, the force cache of this time holds the zeros it was reset to, and the caller sees the exception.
+        rb_invalidate();
+        la_blk[0].valid = la_blk[1].valid = false;
+        last_step_fast = false;
+        if (inputs_on_copy_stream) CUDA_CHECK(cudaStreamWaitEvent(stream, ev_inputs, 0));
+        CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
+        PrestepArgs pa{};
+        pa.hdr = d_hdr.p; pa.hist = d_hist.p; pa.times = d_times.p; pa.B = B; pa.Bp = Bp; pa.D = D; pa.L = L;
+        CUDA_CHECK(launch_prestep(pa, 1, stream));
+        CUDA_CHECK(cudaMemsetAsync(d_force.p, 0, d_force.n * sizeof(double), stream));
+        CUDA_CHECK(cudaMemsetAsync(d_comp.p, 0, d_comp.n * sizeof(double), stream));
+        prof.kernel_launches += 1;
+        prev_time = t;
+        force_valid = true;
+        fail(HC_ERR_ETA_WINDOW, eta_error);
+    }
     if (wave_mode == 2 && la_enabled) {
         const int slot = lookahead_slot(t);
         if (slot >= 0) { hh.exc_src = 1; hh.exc_slot = slot; phase_uses_lookahead = true; }
     }
-    rb_use = false;
     if (rb_enabled && !skip_radiation) rb_use = radiation_block_slot(t, hh) >= 0;
-    CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
     phase1_launches = 0;
     const bool per_step_exc = (wave_mode == 2) && !(la_enabled && phase_uses_lookahead);
-    if (rb_use && !per_step_exc && !profiling) return;          // phase 1 is empty
+    // k_step takes the header by value; every other kernel of a step reads it from d_hdr.  Pageable source: the runtime
+    // stages small copies at call time, so hdr_h can be rewritten by the next step at once.
+    hdr_on_device = !(rb_use && !per_step_exc) || profiling;
+    if (hdr_on_device) CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
+    last_step_fast = rb_use && !per_step_exc && !profiling;
+    if (last_step_fast) return;                                 // phase 1 is empty
     phase1_launches = (rb_use ? 0 : 1) + ((rb_use && !per_step_exc) ? 0 : 1) + (per_step_exc ? int(groups.size()) : 0);
-    launch_phase(1, nullptr, nullptr, nullptr);
+    launch_phase(1);
 }
 
 // ---- excitation look-ahead ---------------------------------------------------------------------
@@ -793,6 +858,7 @@ void hc_ensemble::setup_lookahead() {
         for (auto& x : ev_la_done) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         for (auto& x : ev_la_free) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_la_build, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_la_join, cudaEventDisableTiming));
     }
     for (auto& G : groups) {
         G->la_idx.alloc(size_t(kLaT) * G->Le);
@@ -823,22 +889,28 @@ int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
     }
     if (T == 0) return 0;
     for (int i = T; i < kLaT; ++i) Bk.times[i] = Bk.times[T - 1];    // unused warps recompute the last time
+    auto row_of = [&](double tt) {                            // largest i with eta_t[i] <= tt
+        auto it = std::upper_bound(eta_t_h.begin(), eta_t_h.end(), tt);
+        return int(it - eta_t_h.begin()) - 1;
+    };
+    // eta rows each group's taps cover; the capacity check for ALL groups comes before anything is enqueued
+    int row0s[kMaxBodies], nrowss[kMaxBodies];
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group& G = *groups[gi];
+        int row0 = row_of(Bk.times[0] - G.tau_last) - 1;
+        if (row0 < 0) row0 = 0;
+        const int row_hi = std::min(n_eta - 1, row_of(Bk.times[T - 1] - G.tau_first) + 1);
+        row0s[gi] = row0; nrowss[gi] = row_hi - row0 + 1;
+        if (nrowss[gi] > G.la_rows_cap - kLaRows) return 0;
+    }
     CUDA_CHECK(cudaStreamWaitEvent(st, ev_la_build, 0));
     double* d_times = d_la_times.p + size_t(buf) * kLaT;
     CUDA_CHECK(cudaMemcpyAsync(d_times, Bk.times.data(), kLaT * sizeof(double), cudaMemcpyHostToDevice, st));
     const bool timed = profiling;
     if (timed) CUDA_CHECK(cudaEventRecord(ev_la[0], st));
-    auto row_of = [&](double tt) {                            // largest i with eta_t[i] <= tt
-        auto it = std::upper_bound(eta_t_h.begin(), eta_t_h.end(), tt);
-        return int(it - eta_t_h.begin()) - 1;
-    };
-    for (auto& Gp : groups) {
-        Group& G = *Gp;
-        int row0 = row_of(Bk.times[0] - G.tau_last) - 1;
-        if (row0 < 0) row0 = 0;
-        const int row_hi = std::min(n_eta - 1, row_of(Bk.times[T - 1] - G.tau_first) + 1);
-        const int nrows = row_hi - row0 + 1;
-        if (nrows > G.la_rows_cap - kLaRows) return 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group& G = *groups[gi];
+        const int row0 = row0s[gi], nrows = nrowss[gi];
         LookaheadPlanArgs pa{};
         pa.times = d_times; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
         pa.idx = G.la_idx.p; pa.w1 = G.la_w1.p; pa.w2 = G.la_w2.p; pa.taps = G.la_taps.p;
@@ -902,10 +974,9 @@ int hc_ensemble::lookahead_slot(double t) {
     return la_cur * kLaT + la_pos++;
 }
 
-void hc_ensemble::finish_step(double t, const double* d_pose_in, const double* d_vel_in, double* d_force_out) {
-    launch_phase(2, d_pose_in, d_vel_in, d_force_out);
-    CUDA_CHECK(cudaEventRecord(ev_force, stream));
-    if (rb_use) rb_launch_slices(1, true);        // this step's share of the next block's pass
+void hc_ensemble::finish_step(double t) {
+    launch_phase(2);
+    if (rb_use && rb_pass_mode != 3) rb_launch_slices(1, true);    // this step's share of the next block's pass
     prof.kernel_launches += phase1_launches + (rb_use ? 1 : 2);
     prof.hydrostatics_calls++; prof.radiation_calls++; prof.waves_calls++;
     prev_time = t;
@@ -934,6 +1005,7 @@ void hc_ensemble_default_opts(hc_ensemble_opts* o) {
     std::memset(o, 0, sizeof(*o));
     o->device = 0; o->batch = 1; o->dt_hint = 0.0; o->bracket_snap = 0.0;
     o->rad_chunk = 0; o->exc_chunk = 0; o->use_graph = 1; o->exc_lookahead = 0; o->rad_kernel = 0; o->rad_lookahead = 0;
+    o->rad_pass_mode = 0;
     o->stream = nullptr;
 }
 
@@ -1025,6 +1097,12 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0;
     if (e->rb_stream) CUDA_CHECK(cudaStreamSynchronize(e->rb_stream));
     e->rb_invalidate(); e->rb_hits_this_block = 0; e->rb_builds = 0; e->rb_poor_blocks = 0;
+    // a new run: look-aheads that the misprediction heuristics switched off are armed again
+    if (e->d_Kpad.p && e->rb_plan.usable) e->rb_enabled = true;
+    e->rb_side_pending = false;
+    if (e->wave_mode == 2 && e->d_la_cache.p && !e->la_enabled) { e->la_enabled = true; e->drop_graph(); }
+    e->la_cur = 0; e->la_builds = 0; e->la_hits_this_block = 0; e->la_poor_blocks = 0;
+    e->last_step_fast = false;
     e->prev_time = -1.0;
     e->force_valid = false;
     CUDA_CHECK(cudaMemsetAsync(e->d_force.p, 0, e->d_force.n * sizeof(double), e->stream));
@@ -1330,10 +1408,10 @@ hc_status hc_step_device(hc_ensemble* e, double t, const double* d_pose, const d
         return HC_OK;
     }
     e->host_stepping = false;
-    e->begin_step(t, g);
-    e->finish_step(t, d_pose, d_vel, e->d_force.p);
-    if (d_force != e->d_force.p)
-        CUDA_CHECK(cudaMemcpyAsync(d_force, e->d_force.p, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    e->inputs_on_copy_stream = false;
+    // the kernels write the forces to the caller's buffer and to the ensemble's time-keyed cache
+    e->begin_step(t, g, d_pose, d_vel, d_force);
+    e->finish_step(t);
     if (recomputed) *recomputed = 1;
     return HC_OK;
     HC_GUARD_END
@@ -1349,30 +1427,36 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
     const bool tr = e->trace && t != e->prev_time;
     const auto h0 = std::chrono::steady_clock::now();
     if (t != e->prev_time) {
-        // state upload on the copy stream, overlapped with the state-independent phase 1 on the main stream
-        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[0], e->copy_stream));
-        CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, e->copy_stream));
-        CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, e->copy_stream));
-        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[1], e->copy_stream));
-        CUDA_CHECK(cudaEventRecord(e->ev_inputs, e->copy_stream));
+        // State upload.  A step served by both look-aheads has nothing to run before its state arrives (phase 1 is
+        // empty): everything goes down the main stream, no cross-stream events.  Otherwise the upload runs on the copy
+        // stream underneath the state-independent phase 1 (plans, per-step convolutions).  Which of the two this step
+        // will be is known only inside begin_step, so the previous step's answer decides where the copies go.
+        const bool on_copy = !e->last_step_fast;
+        cudaStream_t cs = on_copy ? e->copy_stream : e->stream;
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[0], cs));
+        CUDA_CHECK(cudaMemcpyAsync(e->d_vel.p, vel, bytes, cudaMemcpyHostToDevice, cs));
+        CUDA_CHECK(cudaMemcpyAsync(e->d_pose.p, pose, bytes, cudaMemcpyHostToDevice, cs));
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[1], cs));
+        if (on_copy) CUDA_CHECK(cudaEventRecord(e->ev_inputs, e->copy_stream));
+        e->inputs_on_copy_stream = on_copy;
         e->host_stepping = true;
         try {
-            e->begin_step(t, g);
+            e->begin_step(t, g, e->d_pose.p, e->d_vel.p, e->d_force.p);
         } catch (...) {
             cudaStreamSynchronize(e->copy_stream);
+            cudaStreamSynchronize(e->stream);
             throw;
         }
-        CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_inputs, 0));
+        if (on_copy) CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_inputs, 0));
+        e->inputs_on_copy_stream = false;
         if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[2], e->stream));
-        e->finish_step(t, e->d_pose.p, e->d_vel.p, e->d_force.p);
+        e->finish_step(t);
         re = 1;
     }
-    // forces back on the copy stream: the main stream is free to run look-ahead work queued behind the step
-    CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_force, 0));
-    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[3], e->copy_stream));
-    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->copy_stream));
-    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[4], e->copy_stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[3], e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[4], e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
     if (tr) {
         float a = 0, b = 0, c = 0, d = 0, f = 0;
         cudaEventElapsedTime(&a, e->ev_tr[0], e->ev_tr[1]);
@@ -1410,19 +1494,20 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
         }
     }
     if (e->events_pending) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); e->collect_events(); }
+    if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
     StepHeader hh{};
     hh.t = t; hh.snap = e->opts.bracket_snap; hh.head = e->head < 0 ? 0 : e->head; hh.len = 0; hh.cap = e->cap;
+    hh.force = e->d_wave_tmp.p;
     CUDA_CHECK(cudaMemcpyAsync(e->d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, e->stream));
     const bool saved_la = e->phase_uses_lookahead;
     const bool saved_rb = e->rb_use;
     e->phase_uses_lookahead = false;                 // always the per-step kernels here
     e->rb_use = false;
     e->skip_radiation = true;
-    e->enqueue_phase(1, nullptr, nullptr, nullptr, false);
+    e->enqueue_phase(1, false);
     e->skip_radiation = false;
     e->phase_uses_lookahead = saved_la;
     e->rb_use = saved_rb;
-    if (e->d_wave_tmp.n < n) e->d_wave_tmp.alloc(n);
     FinalizeGroups fg{};
     if (e->wave_mode == 2)
         for (size_t g = 0; g < e->groups.size(); ++g) {
@@ -1430,7 +1515,7 @@ hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* out) {
             fg.dof0[g] = G.dof0; fg.nd[g] = G.nd; fg.chunk0[g] = G.chunk0; fg.nchunk[g] = G.nchunk;
         }
     FinalizeArgs fa{};
-    fa.hdr = e->d_hdr.p; fa.exc_partial = e->d_exc_partial.p; fa.force = e->d_wave_tmp.p; fa.comp = nullptr;
+    fa.hdr = e->d_hdr.p; fa.exc_partial = e->d_exc_partial.p; fa.comp = nullptr;
     fa.reg_amp = e->d_reg_amp.p; fa.reg_omega = e->d_reg_omega.p; fa.reg_mag = e->d_reg_mag.p; fa.reg_phase = e->d_reg_phase.p;
     fa.B = e->B; fa.Bp = e->Bp; fa.D = e->D; fa.N = e->N; fa.rad_nchunk = 0; fa.wave_mode = e->wave_mode;
     fa.exc_ngroups = (e->wave_mode == 2) ? int(e->groups.size()) : 0; fa.exc_ndmax = e->exc_ndmax; fa.waves_only = 1;
@@ -1475,6 +1560,28 @@ hc_status hc_sync(hc_ensemble* e) {
     if (e->events_pending) e->collect_events();
     return HC_OK;
     HC_GUARD_END
+}
+
+hc_status hc_ensemble_join(hc_ensemble* e) {
+    HC_GUARD_BEGIN
+    e->use_device();
+    if (e->rb_stream) {
+        CUDA_CHECK(cudaEventRecord(e->ev_rb_side, e->rb_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_rb_side, 0));
+        if (!e->rb_pass.active) e->rb_side_pending = false;
+    }
+    if (e->la_stream) {
+        CUDA_CHECK(cudaEventRecord(e->ev_la_join, e->la_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_la_join, 0));
+    }
+    return HC_OK;
+    HC_GUARD_END
+}
+
+hc_status hc_ensemble_lookahead_state(const hc_ensemble* e, int* radiation, int* excitation) {
+    if (radiation) *radiation = (e->d_Kpad.p && e->rb_plan.usable) ? (e->rb_enabled ? 1 : 0) : -1;
+    if (excitation) *excitation = e->d_la_cache.p ? (e->la_enabled ? 1 : 0) : -1;
+    return HC_OK;
 }
 
 // ---- added mass ----------------------------------------------------------------------

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int 
         const int n = a.D * a.Bp;
         for (int i = tid; i < n; i += nth) {
             const int c = i / a.Bp, b = i - c * a.Bp;
-            row[i] = (b < a.B) ? a.vel[(size_t)b * a.D + c] : 0.0;
+            row[i] = (b < a.B) ? h.vel[(size_t)b * a.D + c] : 0.0;
         }
         if (tid == 0) a.times[h.head] = h.t;
     }
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
 size_t rad_block_smem_bytes(int D, int R) { return 16 + size_t(R + kRbT - 1) * rb_stride(D) * sizeof(double); }
 
 template <int D>
-__global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadBlockArgs a) {
+__global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const __grid_constant__ RadBlockArgs a) {
     constexpr int KS = (D + 3) / 4, DP = 4 * KS, STRIDE = rb_stride(D);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadB
     const int b0 = tile * kRbTileInst + warp * 16;
     const bool active = b0 < a.Bp;
     // row u feeds step rho + m g iff its lag u + g + 1 has a bracket at that step
-    const int rmax_g = __ldg(a.smax + rho + a.m * g) - (g + a.g0) - 1;
+    const int rmax_g = a.smax[rho + a.m * g] - (g + a.g0) - 1;
     int rmax_min = rmax_g;
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) rmax_min = min(rmax_min, __shfl_xor_sync(0xffffffffu, rmax_min, o));
@@ -635,11 +635,11 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
 template <int D>
 __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
                                                       const __grid_constant__ HydrostaticTables hs,
-                                                      const __grid_constant__ FinalizeGroups eg) {
+                                                      const __grid_constant__ FinalizeGroups eg,
+                                                      const __grid_constant__ StepHeader h) {
     constexpr int LAGS = (D <= 12) ? 8 : 4;          // young lags staged per pass
     __shared__ double s_K[LAGS * D * D];             // (K w)[lag][col][row]
     __shared__ double s_v[LAGS][D][kRsInst];         // young rows, [lag][col][instance]
-    const StepHeader h = *a.hdr;
     const int j = h.rb_j;
     const int nl = min(min(h.rb_jj / a.m, h.rb_smax), a.L - 1) + 1;   // young lags 0 .. nl - 1
     const int tid = threadIdx.x;
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
             const double* e = fa.exc_cache + (((size_t)buf * fa.exc_S * kLaT + pos) * D + d) * a.Bp + b;
             for (int sg = 0; sg < fa.exc_S; ++sg) prefetch_l2(e + (size_t)sg * kLaT * D * a.Bp);
         }
-        if (b < a.B && d % 6 == 0) prefetch_l2(fa.pose + (size_t)b * D + d);
+        if (b < a.B && d % 6 == 0) prefetch_l2(h.pose + (size_t)b * D + d);
     }
     // fixed-order sum of the row-chunk partials of block step j
     double fr = 0.0;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
             if (l0 + l == 0) {
                 // this step's sample: the CTA's [32][D] tile of vel is contiguous
                 const int lb = tid / D, c = tid - lb * D;
-                s_v[0][c][lb] = (b0 + lb < a.B) ? a.vel[(size_t)(b0 + lb) * D + c] : 0.0;
+                s_v[0][c][lb] = (b0 + lb < a.B) ? h.vel[(size_t)(b0 + lb) * D + c] : 0.0;
             } else {                                               // lag l: the row appended m l steps ago
                 int slot = (h.head - a.m * (l0 + l)) % h.cap;
                 if (slot < 0) slot += h.cap;
@@ -733,7 +733,7 @@ cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st)
 }
 
 cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                        cudaStream_t st) {
+                        const StepHeader& hdr, cudaStream_t st) {
     // 34 KB of static shared memory per CTA: ask for the large carve-out so that 4 CTAs of k_step<12> fit per SM and
     // the 512 CTAs of a 16384-instance ensemble run as a single wave
     static bool attr_set[64] = {};
@@ -746,9 +746,9 @@ cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const Hydr
         attr_set[dev & 63] = true;
     }
     switch (a.D) {
-        case 6: k_step<6><<<a.Bp / kRsInst, kRsInst * 6, 0, st>>>(a, fa, hs, eg); break;
-        case 12: k_step<12><<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a, fa, hs, eg); break;
-        case 18: k_step<18><<<a.Bp / kRsInst, kRsInst * 18, 0, st>>>(a, fa, hs, eg); break;
+        case 6: k_step<6><<<a.Bp / kRsInst, kRsInst * 6, 0, st>>>(a, fa, hs, eg, hdr); break;
+        case 12: k_step<12><<<a.Bp / kRsInst, kRsInst * 12, 0, st>>>(a, fa, hs, eg, hdr); break;
+        case 18: k_step<18><<<a.Bp / kRsInst, kRsInst * 18, 0, st>>>(a, fa, hs, eg, hdr); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1140,7 +1140,7 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
     const double rho_g = __dmul_rn(hs.rho, glen);
     double fh = 0.0;
     if (!a.waves_only) {
-    const double* pose = a.pose + (size_t)b * D + 6 * body;
+    const double* pose = h.pose + (size_t)b * D + 6 * body;
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 6; ++j)
@@ -1177,7 +1177,7 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
         }
         for (; ch < a.rad_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
         // share of this step's own velocity sample (leading lags whose newer bracket sample is "now")
-        const double* vel = a.vel + (size_t)b * D;
+        const double* vel = h.vel + (size_t)b * D;
         for (int s = 0; s < a.L && a.pr_lead[s]; ++s) {   // leading lags: contiguous from lag 0
             const double hw = a.pr_head[s];
             if (hw == 0.0 || a.pr_wd[s] == 0.0) continue;
@@ -1221,8 +1221,10 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
         }
     }
     const size_t o = (size_t)b * D + d;
-    if (a.waves_only) { a.force[o] = fw; return; }
-    a.force[o] = __dadd_rn(__dsub_rn(fh, fr), fw);                   // hs - rad + waves (:758-760)
+    if (a.waves_only) { h.force[o] = fw; return; }
+    const double total = __dadd_rn(__dsub_rn(fh, fr), fw);           // hs - rad + waves (:758-760)
+    h.force[o] = total;
+    if (h.force2) h.force2[o] = total;
     if (a.comp) {
         const size_t BD = (size_t)a.B * D;
         a.comp[o] = fh;

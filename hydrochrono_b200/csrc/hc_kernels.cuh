@@ -30,6 +30,12 @@ struct StepHeader {
     int rb_jj;         // steps since the block's snapshot of the history (rb_j, or rb_j + block length for a
                        // block that was evaluated in the background one block ahead)
     int rb_buf;        // which of the two partial buffers holds the block
+    // the step's state and result buffers travel in the header so that the captured graphs and the directly launched
+    // k_step stay valid when a caller rotates its device buffers from step to step
+    const double* pose;   // [B][D]
+    const double* vel;    // [B][D]
+    double* force;        // [B][D]
+    double* force2;       // second copy of the total (the caller's buffer when `force` is the ensemble's cache), or null
 };
 
 struct HydrostaticTables {
@@ -71,11 +77,9 @@ struct ExcitationArgs {
 };
 
 struct FinalizeArgs {
-    const StepHeader* hdr;
-    const double* pose;       // [B][D]
+    const StepHeader* hdr;    // pose / vel / force of the step come from the header
     const double* rad_partial;
     const double* exc_partial;
-    double* force;            // [B][D]
     double* comp;             // [3][B][D] hydrostatic, radiation, waves
     // regular waves (SoA over instances)
     const double* reg_amp;    // [Bp]
@@ -90,7 +94,6 @@ struct FinalizeArgs {
     const double* exc_cache;  // [2][S][T][D][Bp] look-ahead blocks of wave forces (hdr->exc_src == 1), S row segments
     int exc_S;
     // share of this step's own velocity sample in the radiation convolution
-    const double* vel;        // [B][D]
     const double* K;          // [L][D][D]  (K w)
     const int* pr_lead;
     const double* pr_wd;
@@ -111,7 +114,6 @@ struct EtaArgs {
 
 struct PrestepArgs {
     const StepHeader* hdr;
-    const double* vel;     // [B][D]
     double* hist;          // [cap][D][Bp]
     double* times;         // [cap]
     const double* rirf_t;  // [L]
@@ -191,7 +193,7 @@ struct RadBlockArgs {
     const double* Kpad;       // [lags + pad][rb_stride(D)]  (K w)[lag][row][col], zero beyond the last lag
     double* partial;          // [kRbT * m][nchunk][D][Bp]
     int D;
-    const int* smax;          // [kRbT * m] per block step: largest lag with a bracket
+    int smax[kRbT * kRbMaxM]; // per block step: largest lag with a bracket (by value: no copy per pass)
     int head0;                // ring slot of the block's first step (resident row r lives in slot head0 - 1 - r)
     int cap, n_res, Bp, R, nchunk;
     int m;                    // history rows per RIRF lag (lag s of a step = history row m s)
@@ -200,8 +202,6 @@ struct RadBlockArgs {
     int item0;                // first work item of this launch (a pass can be cut into slices of consecutive items)
 };
 struct RadStepArgs {
-    const StepHeader* hdr;
-    const double* vel;        // [B][D]
     double* hist;
     double* times;
     const double* K;          // [L][col][row]
@@ -212,7 +212,7 @@ size_t rad_block_smem_bytes(int D, int R);
 cudaError_t launch_rad_block(const RadBlockArgs& a, int nitems, cudaStream_t st);
 inline int rad_block_items(const RadBlockArgs& a) { return ((a.Bp + kRbTileInst - 1) / kRbTileInst) * a.nchunk_used * a.m; }
 cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                        cudaStream_t st);
+                        const StepHeader& hdr, cudaStream_t st);
 cudaError_t measure_dfma_peak(double seconds_budget, double* tflops);
 cudaError_t measure_dmma_peak(double seconds_budget, double* tflops);
 cudaError_t launch_lookahead_plan(const LookaheadPlanArgs& a, cudaStream_t st);

@@ -171,6 +171,10 @@ typedef struct hc_ensemble_opts {
                                  the per-step kernel.  0 = auto (on for large ensembles with bracket_snap > 0), 1 = off,
                                  2 = on (each block is evaluated one block ahead, one slice per step on a side
                                  stream), 3 = on, whole pass in the main stream at the block's first step */
+    int rad_pass_mode;        /* how the pass of the radiation block evaluated ahead is paced on its side stream: 0 = auto
+                                 (= 1), 1 = one slice per step, each gated by its step's forces, 2 = one slice per step,
+                                 not gated (two driver calls per step), 3 = the whole pass at the block's first step (one
+                                 launch per block; k_step competes with resident pass CTAs for SM slots) */
     void* stream;             /* cudaStream_t to run on (NULL = ensemble creates its own non-blocking stream) */
 } hc_ensemble_opts;
 
@@ -247,6 +251,14 @@ HC_API hc_status hc_waves_force_at_time(hc_ensemble* e, double t, double* waves)
 /* Re-stage the radiation kernel after hc_tables_set_convolution_mode() changed the ensemble's tables. */
 HC_API hc_status hc_ensemble_refresh_rirf(hc_ensemble* e);
 HC_API hc_status hc_sync(hc_ensemble* e);
+/* Orders the ensemble's stream after every look-ahead pass enqueued so far on the library's side streams (no host
+ * wait).  A caller that times device-resident stepping with events on the ensemble's stream calls this before each
+ * event so that the interval contains all the work the steps in between gave rise to. */
+HC_API hc_status hc_ensemble_join(hc_ensemble* e);
+/* Whether the radiation / excitation look-ahead paths are armed (1), configured but switched off by the misprediction
+ * heuristic (0: irregular step sizes; hc_ensemble_reset or hc_ensemble_set_bracket_snap arm them again) or not
+ * configured at all (-1). */
+HC_API hc_status hc_ensemble_lookahead_state(const hc_ensemble* e, int* radiation, int* excitation);
 HC_API int hc_ensemble_history_len(const hc_ensemble* e);
 
 /* ChLoadAddedMass::LoadIntLoadResidual_Mv (src/chloadaddedmass.cpp:55-71), batched: R[b] += c * M_sys * w[b]

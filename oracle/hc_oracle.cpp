@@ -1058,4 +1058,52 @@ double orc_bench_steps(OrcInstance** inst, int count, int nsteps, double t0, dou
     return el;
 }
 
+// Test/bench infrastructure (not a restatement of reference code): loads a velocity history as if the instance had
+// been stepped through `n` earlier evaluations (times newest first, vel[n][D]); what hydro_forces.cpp:559-577 would
+// have left behind, without paying for n convolutions.  The next orc_force call continues from there.
+int orc_set_history(OrcInstance* o, int n, const double* times_newest_first, const double* vel) {
+    ORC_TRY
+    Instance& I = o->I;
+    const int N = I.T->N, D = I.T->D;
+    I.time_history.assign(times_newest_first, times_newest_first + n);
+    for (int b = 0; b < N; ++b) {
+        I.vel_hist[b].resize(n);
+        for (int i = 0; i < n; ++i) I.vel_hist[b][i].assign(vel + size_t(i) * D + 6 * b, vel + size_t(i) * D + 6 * b + 6);
+    }
+    I.prev_time = n > 0 ? times_newest_first[0] : -1.0;
+    return 0;
+    ORC_CATCH
+}
+
+// CPU baseline driver with the GPU arm's exact inputs: step n (time times[n]) takes pose/vel from buffer
+// (buf0 + n) % nbuf of pose[nbuf][count][D] / vel[nbuf][count][D].  mode as orc_bench_steps.  When forces != null the
+// totals of every step are stored as forces[nsteps][count][D].
+double orc_bench_lockstep(OrcInstance** inst, int count, int nsteps, const double* times, int nbuf, int buf0,
+                          const double* pose, const double* vel, int mode, const double* gvec, double* forces,
+                          double* checksum) {
+    if (count <= 0) return 0.0;
+    const int D = inst[0]->I.T->D;
+    double cs = 0.0;
+    const double tstart = now_s();
+    auto one = [&](int i, int n) {
+        const size_t off = (size_t((buf0 + n) % nbuf) * count + i) * D;
+        EvaluateAtTime(inst[i]->I, times[n], pose + off, vel + off, gvec);
+        if (forces) std::copy(inst[i]->I.f_total.begin(), inst[i]->I.f_total.end(), forces + (size_t(n) * count + i) * D);
+        return inst[i]->I.f_total[2];
+    };
+    if (mode == 0) {
+        for (int i = 0; i < count; ++i) inst[i]->I.omp_mode = 1;
+        for (int n = 0; n < nsteps; ++n)
+            for (int i = 0; i < count; ++i) cs += one(i, n);
+    } else {
+        for (int i = 0; i < count; ++i) inst[i]->I.omp_mode = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cs)
+        for (int i = 0; i < count; ++i)
+            for (int n = 0; n < nsteps; ++n) cs += one(i, n);
+    }
+    const double el = now_s() - tstart;
+    if (checksum) *checksum = cs;
+    return el;
+}
+
 }  // extern "C"

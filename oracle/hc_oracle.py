@@ -66,6 +66,10 @@ def lib():
         L.orc_bench_steps.restype = C.c_double
         L.orc_bench_steps.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp,
                                       _dp, _dp, _dp]
+        L.orc_set_history.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.orc_bench_lockstep.restype = C.c_double
+        L.orc_bench_lockstep.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                         _dp, _dp, _dp]
         _LIB = L
     return _LIB
 
@@ -217,6 +221,13 @@ class Instance:
     def history_len(self):
         return lib().orc_history_len(self.h)
 
+    def set_history(self, times_newest_first, vel):
+        """Loads a velocity history (times newest first, vel[n][D]) as if the instance had been stepped through it."""
+        t, v = _c(times_newest_first), _c(vel)
+        assert v.shape == (t.size, self.D)
+        if lib().orc_set_history(self.h, t.size, _p(t), _p(v)):
+            raise OracleError(_err())
+
     def profile(self):
         s = np.empty(3)
         lib().orc_profile(self.h, _p(s))
@@ -294,3 +305,17 @@ def bench_steps(instances, nsteps, t0, dt, mode, amp, om, gvec=(0.0, 0.0, -9.81)
     cs = C.c_double()
     sec = lib().orc_bench_steps(arr, len(instances), nsteps, t0, dt, mode, _p(amp), _p(om), _p(g), C.byref(cs))
     return sec, cs.value
+
+
+def bench_lockstep(instances, times, pose, vel, buf0=0, mode=1, gvec=(0.0, 0.0, -9.81), want_forces=False):
+    """Steps `instances` through `times` with the GPU arm's inputs: step n takes pose/vel [nbuf][count][D] buffer
+    (buf0 + n) % nbuf.  Returns (seconds, checksum, forces[nsteps][count][D] or None)."""
+    arr = (C.c_void_p * len(instances))(*[i.h for i in instances])
+    times, pose, vel, g = _c(times), _c(pose), _c(vel), _c(gvec)
+    nbuf, count, D = pose.shape
+    assert count == len(instances) and vel.shape == pose.shape
+    F = np.empty((times.size, count, D)) if want_forces else None
+    cs = C.c_double()
+    sec = lib().orc_bench_lockstep(arr, count, times.size, _p(times), nbuf, buf0, _p(pose), _p(vel), mode, _p(g),
+                                   _p(F), C.byref(cs))
+    return sec, cs.value, F

@@ -662,3 +662,135 @@ def test_mixing_host_and_device_stepping_inside_a_block():
         got.append(F[sample].copy()); want.append(ref)
     _assert_parity(np.array(got), np.array(want), "mixed stepping")
     assert ens.rad_block_stats()["steps_served"] == 699
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("snap,pass_mode", [(1e-8, 1), (1e-8, 2), (0.0, 1)])
+def test_benchmark_state_parity(rm3, snap, pass_mode):
+    """Exactly what bench.py times: B = 16384, D = 12, L = 1001 lags over 60 s, dt = 0.01,
+    Le = 6000, nf = 1000 -- stepped from an empty history through the full window (6001 rows), past the point where
+    the history ring wraps, over > 120 radiation blocks of 48 steps; hc_step_device and hc_step alternate in runs of
+    7 / 5 steps.  Eight sampled instances are compared with the oracle at EVERY step.
+    Reference: src/hydro_forces.cpp:537-691 (radiation + history), src/wave_types.cpp:776-844 (excitation)."""
+    import torch
+    T, O = rm3
+    B, D, dt, NB = 16384, 12, 0.01, 8
+    nsteps = 6200
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, bracket_snap=snap, rad_pass_mode=pass_mode)
+    kw = dict(dt=dt, duration=(nsteps + 64) * dt, ramp=20.0, Hs=2.5, Tp=8.0, fmin=0.001, fmax=1.0, nfreq=1000, gamma=3.3)
+    seeds = np.arange(1, B + 1, dtype=np.int32)
+    ens.set_waves_irregular(seeds=seeds, **kw)
+    assert ens.irregular_sizes()[2] == [6000, 6000]
+    amp, om = synth.prescribed_motion(D)
+    ph = 0.01 * np.arange(B)[:, None]
+    pose = np.stack([amp * np.sin(om * (i * dt) + ph) for i in range(NB)])
+    vel = np.stack([amp * om * np.cos(om * (i * dt) + ph) for i in range(NB)])
+    dev = torch.device("cuda", 0)
+    h_pose = [torch.from_numpy(pose[i]).pin_memory() for i in range(NB)]
+    h_vel = [torch.from_numpy(vel[i]).pin_memory() for i in range(NB)]
+    d_pose = [x.to(dev) for x in h_pose]
+    d_vel = [x.to(dev) for x in h_vel]
+    d_force = torch.empty((B, D), dtype=torch.float64, device=dev)
+    h_force = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    sample = [0, 1, 63, 64, 4097, 8191, 12345, B - 1]
+    d_idx = torch.tensor(sample, device=dev)
+    times = _acc_times(nsteps, dt)
+    got = np.empty((nsteps, len(sample), D))
+    for n in range(nsteps):
+        if (n % 12) < 7:
+            ens.step_device(times[n], d_pose[n % NB], d_vel[n % NB], d_force)
+            ens.sync()
+            got[n] = d_force[d_idx].cpu().numpy()
+        else:
+            ens.step(times[n], h_pose[n % NB].numpy(), h_vel[n % NB].numpy(), G981, out=h_force.numpy())
+            got[n] = h_force.numpy()[sample]
+    assert ens.history_len() == 6001
+    st = ens.rad_block_stats()
+    if snap > 0:
+        assert st["steps_served"] >= nsteps - 2, st              # every step but the first ones came from a block
+        assert st["launches"] >= nsteps // 48, st
+    else:
+        assert ens.lookahead_state()["radiation"] in (0, -1)     # bit-faithful brackets: the per-step kernels serve
+    ens.close()
+    insts = []
+    for b in sample:
+        i = orc.Instance(O, omp_mode=0)
+        i.set_irregular(seed=int(seeds[b]), share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    _, _, ref = orc.bench_lockstep(insts, times, pose[:, sample, :].copy(), vel[:, sample, :].copy(), buf0=0, mode=1,
+                                   gvec=G981, want_forces=True)
+    assert insts[0].history_len() == 6001
+    worst = _assert_parity(got, ref, "benchmark state, snap %g, pass mode %d" % (snap, pass_mode))
+    print("benchmark-state parity: worst relative error %.2e over %d steps x %d instances" % (worst, nsteps, len(sample)))
+
+
+@pytest.mark.gpu
+def test_lookahead_restage_after_auto_disable_and_reset_rearm():
+    """the radiation look-ahead switches itself off after mispredicted blocks.  A TaperedDirect switch +
+    refresh_rirf while it is off must still re-stage the block path's kernel tables, and hc_ensemble_reset must arm
+    the path again: the next run is served by the blocks and convolves with the NEW kernel."""
+    raw = synth.rm3_like()
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)
+    B, D, dt = 64, 12, 0.01
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2)
+    check = [0, 31, 63]
+    assert ens.lookahead_state()["radiation"] == 1
+    # irregular step sizes: every prediction misses, three poor blocks switch the path off
+    t = 0.0
+    for n in range(40):
+        pose, vel = _motion(D, B, t)
+        ens.step(t, pose, vel)
+        t += dt * (1.0 + 0.37 * ((n * 7) % 5))
+    assert ens.lookahead_state()["radiation"] == 0
+    # switch the kernel while the path is off
+    T.set_convolution_mode("TaperedDirect", smoothing="sg", window_length=5, rirf_end_time=40.0, taper_start_percent=0.7,
+                           taper_end_percent=0.95, taper_final_amplitude=0.0)
+    O.set_tapered(smoothing="sg", window_length=5, rirf_end_time=40.0, start=0.7, end=0.95, final=0.0)
+    ens.refresh_rirf()
+    ens.reset()                                                   # a new run: empty history, look-ahead armed again
+    assert ens.lookahead_state()["radiation"] == 1
+    ens.rad_block_stats(reset=True)
+    insts = [orc.Instance(O) for _ in check]
+    got, want = [], []
+    for tt in _acc_times(200, dt):
+        pose, vel = _motion(D, B, tt)
+        F = ens.step(tt, pose, vel)
+        got.append(F[check].copy())
+        want.append(np.array([i.force(tt, pose[b], vel[b], G981) for b, i in zip(check, insts)]))
+    assert ens.rad_block_stats(reset=False)["steps_served"] >= 190
+    _assert_parity(np.array(got), np.array(want), "re-staged kernel after auto-disable")
+    ens.close()
+
+
+@pytest.mark.gpu
+def test_eta_window_error_leaves_reference_state(rm3):
+    """The reference throws from ComputeForceWaves (wave_types.cpp:833-840) after ComputeForceRadiationDampingConv has
+    pushed the sample and prev_time was set (hydro_forces.cpp:747-756): the history keeps the sample and a second call
+    at the same time returns the cached (zero) totals instead of throwing again."""
+    T, O = rm3
+    B, D, dt = 3, 12, 0.05
+    ens = hc.Ensemble(T, batch=B, dt_hint=dt)
+    kw = dict(dt=dt, duration=1.0, ramp=0.5, Hs=2.5, Tp=8.0, nfreq=16, gamma=3.3)
+    ens.set_waves_irregular(seeds=np.arange(1, B + 1, dtype=np.int32), **kw)
+    inst = orc.Instance(O)
+    inst.set_irregular(seed=1, **kw)
+    t, n_ok = 0.0, 0
+    while True:
+        pose, vel = _motion(D, B, t)
+        try:
+            ref = inst.force(t, pose[0], vel[0], G981)
+        except orc.OracleError:
+            break
+        F = ens.step(t, pose, vel)
+        _assert_parity(F[0], ref, "inside the window")
+        n_ok += 1
+        t += dt
+    assert n_ok > 5
+    hl = ens.history_len()
+    with pytest.raises(hc.HydroError) as ei:
+        ens.step(t, pose, vel)
+    assert "out of bounds" in str(ei.value)
+    assert ens.history_len() == hl + 1 == inst.history_len()      # sample pushed before the throw, as the reference
+    F = ens.step(t, pose, vel)                                    # cached totals of that time: the zeros of the reset
+    assert ens.last_recomputed is False and np.all(F == 0.0)
+    ens.close()
