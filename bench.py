@@ -113,6 +113,8 @@ def parse():
     ap.add_argument("--rad-lookahead", type=int, default=0, help="radiation look-ahead block: 0 auto (on, background), 1 off, 2 on (background), 3 on (in-stream)")
     ap.add_argument("--rad-pass-mode", type=int, default=0, help="pacing of the look-ahead pass: 0 auto, 1 gated slice per step, 2 ungated slice per step, 3 whole pass per block")
     ap.add_argument("--rad-kernel", type=int, default=0, help="0 auto (= 1), 1 FP64 FMA pipe, 2 FP64 tensor cores (DMMA, 12 DoF only), 3 tensor cores (rows 0-7) + FMA pipe (rows 8-11)")
+    ap.add_argument("--multi-devices", default="", help="single-process hc_multi_* mode on this comma-separated device list "
+                                                        "(a device may repeat: several shards on one GPU)")
     ap.add_argument("--workload", default="rm3_irregular_ensemble",
                     choices=["rm3_irregular_ensemble", "sphere_irregular_ensemble"])
     return ap.parse_args()
@@ -536,6 +538,94 @@ def ens_le(raw, dt):
     return int(np.ceil((te[-1] - te[0]) / dt))
 
 
+def run_multi(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: ONE process drives the N GPUs through the C ABI's multi-device
+    handle (hc_multi_*: one host thread + one hc_ensemble per GPU, contiguous shards, the caller's [B][6N] host arrays
+    partition without a copy).  Same metric; times are wall clock around the calls + a sync of every shard, since no
+    single CUDA stream spans the devices."""
+    import torch
+    import hydrochrono_b200 as hc
+    devs = [int(x) for x in args.multi_devices.split(",")] if args.multi_devices else list(range(args.gpus))
+    N = len(devs)
+    if torch.cuda.device_count() <= max(devs):
+        raise SystemExit("bench.py: devices %s but only %d CUDA devices" % (devs, torch.cuda.device_count()))
+    K, W = args.steps, max(args.warmup, 3)
+    prefill = args.prefill if args.prefill >= 0 else PREFILL
+    snap = 0.0 if args.faithful else SNAP
+    total_steps = prefill + 4 * (W + K) + 512
+    T = hc.Tables.from_raw(workload_tables())
+    amp, om = load_plain("synth").prescribed_motion(DOFS)
+    times = step_times(total_steps + 8)
+
+    def leg(B_total):
+        per = B_total // N
+        small = per // 64 < 148
+        m = hc.MultiEnsemble(T, batch=B_total, devices=devs, dt_hint=DT, bracket_snap=snap,
+                             rad_lookahead=args.rad_lookahead or (2 if small else 0),
+                             exc_lookahead=1 if args.no_lookahead else (args.lookahead_mode or (5 if small else 0)),
+                             rad_pass_mode=args.rad_pass_mode)
+        m.set_waves_irregular(dt=DT, duration=total_steps * DT, ramp=SEA["ramp"], Hs=SEA["Hs"], Tp=SEA["Tp"], fmin=SEA["fmin"],
+                              fmax=SEA["fmax"], nfreq=SEA["nfreq"], gamma=SEA["gamma"],
+                              seeds=(1 + np.arange(B_total)).astype(np.int32))
+        pose, vel = motion_buffers(amp, om, B_total, 0)
+        h_pose = [torch.from_numpy(pose[i]).pin_memory() for i in range(NBUF)]
+        h_vel = [torch.from_numpy(vel[i]).pin_memory() for i in range(NBUF)]
+        h_force = torch.empty((B_total, DOFS), dtype=torch.float64).pin_memory()
+        sh = m.shards()
+        d_pose = [[h_pose[i][s["first"]:s["first"] + s["count"]].to("cuda:%d" % s["device"]) for s in sh] for i in range(NBUF)]
+        d_vel = [[h_vel[i][s["first"]:s["first"] + s["count"]].to("cuda:%d" % s["device"]) for s in sh] for i in range(NBUF)]
+        d_force = [torch.empty((s["count"], DOFS), dtype=torch.float64, device="cuda:%d" % s["device"]) for s in sh]
+        n = 0
+        for _ in range(prefill + W):
+            m.step_device(times[n], d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC); n += 1
+        while n % 8:
+            m.step_device(times[n], d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC); n += 1
+        m.sync()
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            m.step_device(times[n], d_pose[n % NBUF], d_vel[n % NBUF], d_force, GVEC); n += 1
+        t_enq = time.perf_counter() - t0
+        m.sync()
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        t_dev = time.perf_counter() - t0
+        for _ in range(W):
+            m.step(times[n], h_pose[n % NBUF].numpy(), h_vel[n % NBUF].numpy(), GVEC, out=h_force.numpy()); n += 1
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            m.step(times[n], h_pose[n % NBUF].numpy(), h_vel[n % NBUF].numpy(), GVEC, out=h_force.numpy()); n += 1
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        t_e2e = time.perf_counter() - t0
+        # gather check: the instance of global index g on its shard equals a single-device run of the same seed
+        comps = m.components()
+        res = {"instances_total": B_total, "instances_per_gpu": per, "value": B_total * K / t_dev, "ms_per_step": 1e3 * t_dev / K,
+               "enqueue_ms_per_step": 1e3 * t_enq / K,
+               "e2e": {"value": B_total * K / t_e2e, "unit": "instance-steps/s", "ms_per_step": 1e3 * t_e2e / K,
+                       "h2d_bytes_per_step": 2 * B_total * DOFS * 8, "d2h_bytes_per_step": B_total * DOFS * 8},
+               "checksum": float(h_force.numpy()[:, 2].sum()), "components_gathered": [list(c.shape) for c in comps]}
+        m.close()
+        del d_pose, d_vel, d_force
+        torch.cuda.empty_cache()
+        return res
+
+    weak = leg(N * args.batch)
+    strong = None if args.no_strong else leg(TOTAL_INSTANCES)
+    line = {"metric": METRIC, "value": weak["value"], "unit": "instance-steps/s", "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": weak["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": base_config(args.batch, N), "e2e": weak["e2e"],
+            "launcher": "single process, hc_multi_* (one host thread + one hc_ensemble per GPU); value and e2e are wall "
+                        "clock around K calls + a synchronize of every device",
+            "weak": weak, "strong": dict(strong, scaling="strong") if strong else None,
+            "gpu_launches": None, "cpu_baseline": {"value": None, "unit": "instance-steps/s", "cores": None, "kind": "port",
+                                                   "sample": "not run at N > 1; see bench.py --impl reference"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     select_workload(args.workload)
@@ -544,6 +634,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if (args.gpus > 1 or args.multi_devices) and "WORLD_SIZE" not in os.environ:
+        run_multi(args)
         return
 
     import torch

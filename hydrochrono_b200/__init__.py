@@ -69,6 +69,38 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def wave_kinematics(omega, amplitude, phase, wavenumber, position, t, water_depth, mwl=0.0, wheeler_stretching=False):
+    """(eta, velocity[3], acceleration[3]) at a point for a sum of Airy components travelling along +x: the
+    arithmetic behind {RegularWave,IrregularWaves}::GetElevation / GetVelocity / GetAcceleration
+    (src/wave_types.cpp:14-160,301-313,515-550).  Host code, off the step path."""
+    om, am, ph, k = (_f64(np.atleast_1d(x)) for x in (omega, amplitude, phase, wavenumber))
+    pos = _f64(position)
+    eta = C.c_double()
+    v, a = np.empty(3), np.empty(3)
+    _check(lib.hc_wave_kinematics(om.size, _dp(om), _dp(am), _dp(ph), _dp(k), _dp(pos), float(t), float(water_depth),
+                                  float(mwl), int(bool(wheeler_stretching)), C.byref(eta), _dp(v), _dp(a)))
+    return eta.value, v, a
+
+
+def jonswap_spectrum_hz(f, Hs, Tp, gamma=3.3, is_normalized=False):
+    f = _f64(f)
+    S = np.empty_like(f)
+    _check(lib.hc_jonswap_spectrum_hz(f.size, _dp(f), Hs, Tp, gamma, int(is_normalized), _dp(S)))
+    return S
+
+
+def compute_wave_number(omega, water_depth, g):
+    k = C.c_double()
+    _check(lib.hc_compute_wave_number(omega, water_depth, g, C.byref(k)))
+    return k.value
+
+
+def random_phases(seed, n):
+    out = np.empty(n)
+    _check(lib.hc_random_phases(int(seed), int(n), _dp(out)))
+    return out
+
+
 def _dp(a):
     return a.ctypes.data_as(_capi.dp) if a is not None else None
 
@@ -411,6 +443,105 @@ class Ensemble:
     def close(self):
         if getattr(self, "_h", None):
             lib.hc_ensemble_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def multi_shard_range(total, shards, index):
+    """Contiguous block [first, first + count) of global instance indices owned by shard `index`."""
+    f, c = C.c_int(), C.c_int()
+    lib.hc_multi_shard_range(int(total), int(shards), int(index), C.byref(f), C.byref(c))
+    return f.value, c.value
+
+
+class MultiEnsemble:
+    """The instances of one ensemble partitioned over several GPUs of one node (hc_multi_*): one hc_ensemble and one
+    host thread per device, contiguous shards, no exchange between devices on the step path."""
+
+    def __init__(self, tables, batch, devices=None, dt_hint=0.0, bracket_snap=0.0, use_graph=True, exc_lookahead=0,
+                 rad_kernel=0, rad_lookahead=0, rad_pass_mode=0):
+        self.tables = tables
+        o = _capi.EnsembleOpts()
+        lib.hc_ensemble_default_opts(C.byref(o))
+        o.batch, o.dt_hint, o.bracket_snap, o.use_graph = int(batch), dt_hint, bracket_snap, int(use_graph)
+        o.exc_lookahead, o.rad_kernel, o.rad_lookahead, o.rad_pass_mode = int(exc_lookahead), int(rad_kernel), int(rad_lookahead), int(rad_pass_mode)
+        if devices is None:
+            devices = list(range(device_count()))
+        dv = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib.hc_multi_ensemble_create(tables._h, C.byref(o), dv, len(devices), C.byref(h)))
+        self._h = h
+        self.batch, self.dofs, self.devices = int(batch), tables.dofs, list(devices)
+
+    def shards(self):
+        out = []
+        for i in range(lib.hc_multi_ensemble_num_shards(self._h)):
+            d, f, c = C.c_int(), C.c_int(), C.c_int()
+            _check(lib.hc_multi_ensemble_shard(self._h, i, C.byref(d), C.byref(f), C.byref(c), None))
+            out.append({"device": d.value, "first": f.value, "count": c.value})
+        return out
+
+    def set_waves_none(self):
+        _check(lib.hc_multi_waves_none(self._h))
+
+    def set_waves_regular(self, amplitude, omega, phase=None):
+        a, w = _f64(np.atleast_1d(amplitude)), _f64(np.atleast_1d(omega))
+        p = _f64(np.atleast_1d(phase)) if phase is not None else None
+        _check(lib.hc_multi_waves_regular(self._h, a.size, _dp(a), _dp(w), _dp(p)))
+
+    def set_waves_irregular(self, dt, duration, ramp=0.0, Hs=0.0, Tp=0.0, fmin=0.001, fmax=1.0, nfreq=0, gamma=1.0,
+                            is_normalized=False, seed=1, seeds=None, Hs_per_instance=None, Tp_per_instance=None):
+        p = _capi.IrregularParams()
+        lib.hc_irregular_default_params(C.byref(p))
+        p.simulation_dt, p.simulation_duration, p.ramp_duration = dt, duration, ramp
+        p.wave_height, p.wave_period, p.frequency_min, p.frequency_max = Hs, Tp, fmin, fmax
+        p.nfrequencies, p.peak_enhancement_factor, p.is_normalized, p.seed = float(nfreq), gamma, int(is_normalized), int(seed)
+        sd = np.ascontiguousarray(seeds, dtype=np.int32) if seeds is not None else None
+        hs = _f64(Hs_per_instance) if Hs_per_instance is not None else None
+        tp = _f64(Tp_per_instance) if Tp_per_instance is not None else None
+        for a in (sd, hs, tp):
+            if a is not None and a.size != self.batch:
+                raise ValueError("per-instance arrays must have one entry per (global) instance")
+        _check(lib.hc_multi_waves_irregular(self._h, C.byref(p), sd.ctypes.data_as(_capi.ip) if sd is not None else None,
+                                            _dp(hs), _dp(tp)))
+
+    def step(self, t, pose, vel, gvec=(0.0, 0.0, -9.81), out=None):
+        """One lock-step of every instance on every device; host [B][6N] arrays in global instance order."""
+        pose, vel, g = _f64(pose), _f64(vel), _f64(gvec)
+        if pose.size != self.batch * self.dofs or vel.size != pose.size:
+            raise ValueError("pose/vel must be [B][6N]")
+        if out is None:
+            out = np.empty((self.batch, self.dofs))
+        re = C.c_int()
+        _check(lib.hc_multi_step(self._h, float(t), _ptr(pose), _ptr(vel), _dp(g), _ptr(out), C.byref(re)))
+        self.last_recomputed = bool(re.value)
+        return out
+
+    def step_device(self, t, d_pose, d_vel, d_force, gvec=(0.0, 0.0, -9.81)):
+        """Device-resident step: per shard one device buffer [count_i][6N] on that shard's device (torch CUDA tensors
+        or raw addresses); asynchronous on the shards' streams."""
+        g = _f64(gvec)
+        n = len(d_pose)
+        arr = [(C.c_void_p * n)(*[_ptr(x).value for x in lst]) for lst in (d_pose, d_vel, d_force)]
+        _check(lib.hc_multi_step_device(self._h, float(t), arr[0], arr[1], _dp(g), arr[2]))
+
+    def components(self):
+        shape = (self.batch, self.dofs)
+        hs, rad, wv = np.empty(shape), np.empty(shape), np.empty(shape)
+        _check(lib.hc_multi_get_components(self._h, _dp(hs), _dp(rad), _dp(wv)))
+        return hs, rad, wv
+
+    def sync(self):
+        _check(lib.hc_multi_sync(self._h))
+
+    def reset(self):
+        _check(lib.hc_multi_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hc_multi_ensemble_destroy(self._h)
             self._h = None
 
     def __del__(self):

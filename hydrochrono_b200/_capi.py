@@ -128,6 +128,20 @@ SIGNATURES = {
     "hc_rad_lookahead_check_step": (C.c_int, [vp, C.c_double, C.c_double, dp, C.c_int, C.POINTER(C.c_int)]),
     "hc_ensemble_rad_lookahead_steps": (C.c_int, [vp]),
     "hc_get_rad_block_stats": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp, C.c_int]),
+    "hc_multi_shard_range": (None, [C.c_int, C.c_int, C.c_int, ip, ip]),
+    "hc_multi_ensemble_create": (C.c_int, [vp, C.POINTER(EnsembleOpts), ip, C.c_int, C.POINTER(vp)]),
+    "hc_multi_ensemble_destroy": (None, [vp]),
+    "hc_multi_ensemble_num_shards": (C.c_int, [vp]),
+    "hc_multi_ensemble_batch": (C.c_int, [vp]),
+    "hc_multi_ensemble_shard": (C.c_int, [vp, C.c_int, ip, ip, ip, C.POINTER(vp)]),
+    "hc_multi_waves_none": (C.c_int, [vp]),
+    "hc_multi_waves_regular": (C.c_int, [vp, C.c_int, dp, dp, dp]),
+    "hc_multi_waves_irregular": (C.c_int, [vp, C.POINTER(IrregularParams), ip, dp, dp]),
+    "hc_multi_step": (C.c_int, [vp, C.c_double, vp, vp, dp, vp, ip]),
+    "hc_multi_step_device": (C.c_int, [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), dp, C.POINTER(vp)]),
+    "hc_multi_get_components": (C.c_int, [vp, dp, dp, dp]),
+    "hc_multi_sync": (C.c_int, [vp]),
+    "hc_multi_reset": (C.c_int, [vp]),
     "hc_host_alloc": (vp, [C.c_size_t]),
     "hc_host_free": (None, [vp]),
     "hc_pierson_moskowitz_spectrum_hz": (C.c_int, [C.c_int, dp, C.c_double, C.c_double, dp]),
@@ -135,11 +149,13 @@ SIGNATURES = {
     "hc_compute_wave_number": (C.c_int, [C.c_double, C.c_double, C.c_double, dp]),
     "hc_resample_excitation_irf": (C.c_int, [vp, C.c_double, C.c_int, ip, dp, dp, dp]),
     "hc_random_phases": (C.c_int, [C.c_int, C.c_int, dp]),
+    "hc_wave_kinematics": (C.c_int, [C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp]),
     "hc_h5_writer_create": (C.c_int, [C.POINTER(vp)]),
     "hc_h5_writer_destroy": (None, [vp]),
     "hc_h5_writer_put_group": (C.c_int, [vp, C.c_char_p]),
     "hc_h5_writer_put_f64": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), dp]),
     "hc_h5_writer_put_string": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
+    "hc_h5_writer_put_string_array": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
     "hc_h5_writer_attr_string": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p]),
     "hc_h5_writer_attr_f64": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_double]),
     "hc_h5_writer_save": (C.c_int, [vp, C.c_char_p]),

@@ -37,16 +37,25 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    // The ensemble's streams are non-blocking: they do NOT order against the legacy default stream that cudaMemset /
+    // cudaMemcpy run on, and both may return before the device has finished (memset is asynchronous; a pageable H2D
+    // returns once the data is staged).  Every fill therefore ends with a wait on that stream -- otherwise a kernel or
+    // copy enqueued right afterwards on the ensemble's stream can be overtaken by the fill (seen as a history ring
+    // zeroed AFTER grow_ring had copied the rows into it, once in ~15 runs).
     void alloc(size_t count, bool zero = true) {
         release();
         if (count == 0) return;
         CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
         n = count;
-        if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+        if (zero) {
+            CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+            CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
     }
     void upload(const T* src, size_t count) {
         alloc(count, false);
         CUDA_CHECK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
     }
     void upload(const std::vector<T>& v) { upload(v.data(), v.size()); }
 };
@@ -104,6 +113,7 @@ struct hc_ensemble {
     RadPlan rb_plan;                              // the same + bracket index / older-row weight per lag (hc_plan.cpp)
     DevBuf<double> d_Kyoung;                      // first 2 kRbT lags of that kernel, [lag][col][row] (k_step)
     DevBuf<double> d_Kpad, d_rb_partial[2];
+    DevBuf<int> d_rb_smax[2];
     std::vector<double> rb_scratch;
     struct RbBlock {
         double times[kRbT * kRbMaxM]; int smax[kRbT * kRbMaxM];
@@ -407,7 +417,10 @@ void hc_ensemble::setup_radiation_block() {
                       rad_block_smem_bytes, D, 8);
     rb_nchunk = (rb_Lk - 1 + rb_R - 1) / rb_R;
     rb_ahead = (want != 3);                                        // 3 = whole pass at the block's first step
-    for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+    for (int i = 0; i < (rb_ahead ? 2 : 1); ++i) {
+        d_rb_partial[i].alloc(size_t(kRbT) * rb_m * rb_nchunk * D * Bp, false);
+        d_rb_smax[i].alloc(kRbT * kRbMaxM);
+    }
     rb_pass_mode = opts.rad_pass_mode >= 1 && opts.rad_pass_mode <= 3 ? opts.rad_pass_mode : 1;
     if (!ev_rb[0]) { CUDA_CHECK(cudaEventCreate(&ev_rb[0])); CUDA_CHECK(cudaEventCreate(&ev_rb[1])); }
     if (rb_ahead && !rb_stream) {
@@ -415,7 +428,8 @@ void hc_ensemble::setup_radiation_block() {
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority (numerically largest)
         // gated slices: above the excitation block's stream (they are held back by the steps); ungated / whole pass:
         // below it, or the pass would starve the excitation block that the steps need sooner
-        CUDA_CHECK(cudaStreamCreateWithPriority(&rb_stream, cudaStreamNonBlocking, rb_pass_mode == 1 ? (lo + hi) / 2 : lo));
+        const int prio = rb_pass_mode == 1 ? (lo + hi) / 2 : lo;
+        CUDA_CHECK(cudaStreamCreateWithPriority(&rb_stream, cudaStreamNonBlocking, prio));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_rb_side, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_rb_snap, cudaEventDisableTiming));
     }
@@ -471,10 +485,11 @@ int hc_ensemble::rb_plan_block(RbBlock& Bk, double t, int base) {
 void hc_ensemble::rb_setup_pass(int buf) {
     RbBlock& Bk = rbk[buf];
     const int TT = kRbT * rb_m;
+    // (one small copy per pass of 8 m steps; pageable source, staged at call time)
+    CUDA_CHECK(cudaMemcpyAsync(d_rb_smax[buf].p, Bk.smax, TT * sizeof(int), cudaMemcpyHostToDevice, stream));
     RadBlockArgs& ba = rb_pass.args;
     ba = RadBlockArgs{};
-    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p;
-    std::copy(Bk.smax, Bk.smax + TT, ba.smax);
+    ba.hist = d_hist.p; ba.Kpad = d_Kpad.p; ba.partial = d_rb_partial[buf].p; ba.smax = d_rb_smax[buf].p;
     ba.head0 = head; ba.cap = cap; ba.n_res = std::min(int(times.size()) - 1, rb_m * (rb_Lk - 1));
     ba.D = D; ba.Bp = Bp; ba.R = rb_R; ba.nchunk = rb_nchunk; ba.m = rb_m; ba.g0 = Bk.base / rb_m;
     ba.nchunk_used = Bk.nchunk_used; ba.item0 = 0;

@@ -30,6 +30,7 @@ struct Node {
     std::map<std::string, std::unique_ptr<Node>> kids;   // sorted by name, as symbol nodes require
     // dataset payload
     bool is_string = false;
+    size_t str_size = 0;             // fixed element size of a string ARRAY (0: scalar string, size = all bytes)
     std::vector<uint64_t> dims;
     std::vector<uint8_t> bytes;
     std::vector<Attr> attrs;
@@ -109,7 +110,7 @@ void write_dataset(Out& o, Node& n) {
     o.raw(n.bytes.data(), n.bytes.size());
     std::vector<std::pair<uint16_t, std::vector<uint8_t>>> msgs;
     msgs.push_back({0x01, msg_dataspace(n.dims)});
-    msgs.push_back({0x03, n.is_string ? msg_type_str(n.bytes.size()) : msg_type_f64()});
+    msgs.push_back({0x03, n.is_string ? msg_type_str(n.str_size ? n.str_size : n.bytes.size()) : msg_type_f64()});
     msgs.push_back({0x05, msg_fill()});
     msgs.push_back({0x08, msg_layout(n.bytes.empty() ? UNDEF : data_at, n.bytes.size())});
     for (const Attr& a : n.attrs) msgs.push_back({0x0c, msg_attr(a)});
@@ -252,10 +253,26 @@ hc_status hc_h5_writer_put_f64(hc_h5_writer* w, const char* path, int rank, cons
 hc_status hc_h5_writer_put_string(hc_h5_writer* w, const char* path, const char* value) {
     HC_GUARD_BEGIN
     hc::Node* n = w->find(path, true, true);
-    n->is_group = false; n->is_string = true;
+    n->is_group = false; n->is_string = true; n->str_size = 0;
     n->dims.clear();
     const size_t len = std::strlen(value);
     n->bytes.assign(value, value + len + 1);
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// 1-D array of fixed-length, null-padded strings (what H5Writer::WriteStringArray produces in the reference)
+hc_status hc_h5_writer_put_string_array(hc_h5_writer* w, const char* path, int count, const char* const* values) {
+    HC_GUARD_BEGIN
+    if (count < 0 || (count > 0 && !values)) hc::fail(HC_ERR_INVALID, "h5 writer: bad string array");
+    hc::Node* n = w->find(path, true, true);
+    n->is_group = false; n->is_string = true;
+    size_t width = 1;
+    for (int i = 0; i < count; ++i) width = std::max(width, std::strlen(values[i]) + 1);
+    n->str_size = width;
+    n->dims.assign(1, uint64_t(count));
+    n->bytes.assign(size_t(count) * width, 0);
+    for (int i = 0; i < count; ++i) std::memcpy(n->bytes.data() + size_t(i) * width, values[i], std::strlen(values[i]));
     return HC_OK;
     HC_GUARD_END
 }

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
 size_t rad_block_smem_bytes(int D, int R) { return 16 + size_t(R + kRbT - 1) * rb_stride(D) * sizeof(double); }
 
 template <int D>
-__global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const __grid_constant__ RadBlockArgs a) {
+__global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadBlockArgs a) {
     constexpr int KS = (D + 3) / 4, DP = 4 * KS, STRIDE = rb_stride(D);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const __gr
     const int b0 = tile * kRbTileInst + warp * 16;
     const bool active = b0 < a.Bp;
     // row u feeds step rho + m g iff its lag u + g + 1 has a bracket at that step
-    const int rmax_g = a.smax[rho + a.m * g] - (g + a.g0) - 1;
+    const int rmax_g = __ldg(a.smax + rho + a.m * g) - (g + a.g0) - 1;
     int rmax_min = rmax_g;
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) rmax_min = min(rmax_min, __shfl_xor_sync(0xffffffffu, rmax_min, o));

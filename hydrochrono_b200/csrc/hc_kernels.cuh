@@ -193,7 +193,7 @@ struct RadBlockArgs {
     const double* Kpad;       // [lags + pad][rb_stride(D)]  (K w)[lag][row][col], zero beyond the last lag
     double* partial;          // [kRbT * m][nchunk][D][Bp]
     int D;
-    int smax[kRbT * kRbMaxM]; // per block step: largest lag with a bracket (by value: no copy per pass)
+    const int* smax;          // [kRbT * m] per block step: largest lag with a bracket
     int head0;                // ring slot of the block's first step (resident row r lives in slot head0 - 1 - r)
     int cap, n_res, Bp, R, nchunk;
     int m;                    // history rows per RIRF lag (lag s of a step = history row m s)

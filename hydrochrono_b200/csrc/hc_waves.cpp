@@ -251,6 +251,46 @@ hc_status hc_resample_excitation_irf(const hc_tables* t, double dt, int body, in
     } catch (const hc::StatusError& e) { hc::set_last_error(e.msg); return e.code; }
       catch (const std::exception& e) { hc::set_last_error(e.what()); return HC_ERR_INVALID; }
 }
+// Airy kinematics (src/wave_types.cpp:14-160,515-545); operation order of the reference, component by component.
+hc_status hc_wave_kinematics(int n, const double* omega, const double* amplitude, const double* phase,
+                             const double* wavenumber, const double position[3], double time, double water_depth,
+                             double mwl, int wheeler_stretching, double* eta_out, double velocity[3],
+                             double acceleration[3]) {
+    if (n < 0 || (n > 0 && (!omega || !amplitude || !phase || !wavenumber)) || !position) {
+        hc::set_last_error("null argument");
+        return HC_ERR_INVALID;
+    }
+    const double x_pos = position[0];
+    double eta = 0.0;
+    for (int i = 0; i < n; ++i) eta += amplitude[i] * std::cos(wavenumber[i] * x_pos - omega[i] * time + phase[i]);
+    if (eta_out) *eta_out = eta;
+    double pz = position[2];
+    if (wheeler_stretching) {
+        const double z_rel = position[2] - mwl;
+        pz = water_depth * (z_rel - eta) / (water_depth + eta);    // replaces position.z(); mwl is subtracted again below
+    }
+    const double z_pos = pz - mwl;
+    double v[3] = {0.0, 0.0, 0.0}, a[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) {
+        const double k = wavenumber[i], om = omega[i], A = amplitude[i];
+        const double th = k * x_pos - om * time + phase[i];
+        if (2 * M_PI / k > water_depth || k * water_depth > 500.0) {        // deep water
+            v[0] += om * A * std::exp(k * z_pos) * std::cos(th);
+            v[2] += om * A * std::exp(k * z_pos) * std::sin(th);
+            a[0] += om * om * A * std::exp(k * z_pos) * std::sin(th);
+            a[2] += -om * om * A * std::exp(k * z_pos) * std::cos(th);
+        } else {                                                            // finite depth
+            v[0] += om * A * std::cosh(k * (z_pos + water_depth)) / std::sinh(k * water_depth) * std::cos(th);
+            v[2] += om * A * std::sinh(k * (z_pos + water_depth)) / std::sinh(k * water_depth) * std::sin(th);
+            a[0] += om * om * A * std::cosh(k * (z_pos + water_depth)) / std::sinh(k * water_depth) * std::sin(th);
+            a[2] += -om * om * A * std::sinh(k * (z_pos + water_depth)) / std::sinh(k * water_depth) * std::cos(th);
+        }
+    }
+    if (velocity) std::copy(v, v + 3, velocity);
+    if (acceleration) std::copy(a, a + 3, acceleration);
+    return HC_OK;
+}
+
 hc_status hc_random_phases(int seed, int n, double* out) {
     hc::dvec v = hc::random_phases(seed, n);
     std::copy(v.begin(), v.end(), out);

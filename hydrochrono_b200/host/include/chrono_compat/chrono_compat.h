@@ -1,7 +1,9 @@
 // chrono_compat -- the slice of Project Chrono's API that HydroChrono's hydro plugin touches, plus a
 // small rigid-body stepper, so that the host layer (hydroc/*.h) and the reference-style demo mains can be built
-// and run where Project Chrono is not installed.  It is NOT a multibody engine: bodies are free 6-DoF rigid
-// bodies, optionally locked to heave by a ChLinkLockPrismatic to a fixed body and damped by a ChLinkTSDA;
+// and run where Project Chrono is not installed.  It is NOT a general multibody engine: bodies are 6-DoF rigid bodies,
+// a ChLinkLockPrismatic either locks a body to translation along the joint axis relative to a fixed body or makes it
+// the 1-DoF child of another moving body (reduced coordinates: the pair moves as one rigid body plus the relative
+// slide -- the RM3 float / spar arrangement), a ChLinkTSDA adds a spring-damper (the PTO);
 // ChSystem::DoStepDynamics advances with the linearised-Euler scheme the reference's sphere goldens were produced
 // with (force evaluated once at (t_n, x_n, v_n), v += dt (M + M_added)^-1 F, x += dt v), or, after
 // SetTimestepperType(HHT) as in the reference's YAML runs, with an HHT-alpha step (chrono_compat.cpp).
@@ -85,6 +87,8 @@ class ChQuaterniond {
         const ChVector3d t = 2.0 * (u % v);
         return v + e0 * t + (u % t);
     }
+    ChQuaterniond GetConjugate() const { return ChQuaterniond(e0, -e1, -e2, -e3); }
+    ChVector3d RotateBack(const ChVector3d& v) const { return GetConjugate().Rotate(v); }
 };
 inline ChQuaterniond QuatFromAngleAxis(double angle, const ChVector3d& axis) {
     const double h = 0.5 * angle, s = std::sin(h);
@@ -268,17 +272,41 @@ class ChLoadContainer {
 class ChLinkBase {
   public:
     virtual ~ChLinkBase() = default;
-};
-// Prismatic joint between a body and a FIXED body: the moving body keeps only its heave DoF.
-class ChLinkLockPrismatic : public ChLinkBase {
-  public:
-    void Initialize(std::shared_ptr<ChBody> b1, std::shared_ptr<ChBody> b2, bool, const ChFramed&, const ChFramed&) { Set(b1, b2); }
-    void Initialize(std::shared_ptr<ChBody> b1, std::shared_ptr<ChBody> b2, const ChFramed&) { Set(b1, b2); }
+    void SetName(const std::string& n) { name_ = n; }
+    const std::string& GetName() const { return name_; }
+    virtual ChBody* GetBody1() const { return nullptr; }
+    virtual ChBody* GetBody2() const { return nullptr; }
 
   private:
-    void Set(const std::shared_ptr<ChBody>& b1, const std::shared_ptr<ChBody>& b2) {
-        ChBody* m = b1->IsFixed() ? b2.get() : b1.get();
-        for (int i = 0; i < 6; ++i) m->free_dof[i] = (i == 2);
+    std::string name_;
+};
+// Prismatic joint: the only relative motion left between the two bodies is a translation along the z axis of the
+// joint frame (Chrono's convention).  One body fixed: the other keeps one DoF.  Both moving: body 1 becomes the
+// 1-DoF child of body 2 (ChSystem handles it in reduced coordinates, chrono_compat.cpp).
+class ChLinkLockPrismatic : public ChLinkBase {
+  public:
+    void Initialize(std::shared_ptr<ChBody> b1, std::shared_ptr<ChBody> b2, bool, const ChFramed& f1, const ChFramed&) { Set(b1, b2, f1); }
+    void Initialize(std::shared_ptr<ChBody> b1, std::shared_ptr<ChBody> b2, const ChFramed& f) { Set(b1, b2, f); }
+    ChBody* GetBody1() const override { return body1.get(); }
+    ChBody* GetBody2() const override { return body2.get(); }
+    // reaction of the joint on body 1 (world frame, at body 1's reference point) at the last force balance of a step;
+    // body 2 receives the opposite force (and the torque transported to its own reference point)
+    const ChVector3d& GetReactForce1() const { return react_force1; }
+    const ChVector3d& GetReactTorque1() const { return react_torque1; }
+    std::shared_ptr<ChBody> body1, body2;
+    mutable ChVector3d react_force1, react_torque1;
+    ChVector3d axis_in_parent{0, 0, 1};   // joint axis in body 2's frame (world frame when body 2 is fixed)
+    ChVector3d offset_in_parent;          // body 1's position relative to body 2 at assembly, in body 2's frame
+    ChQuaterniond rel_rot;                // body 1's orientation relative to body 2 at assembly
+
+  private:
+    void Set(const std::shared_ptr<ChBody>& b1, const std::shared_ptr<ChBody>& b2, const ChFramed& frame) {
+        body1 = b1; body2 = b2;
+        if (b1->IsFixed() && !b2->IsFixed()) std::swap(body1, body2);      // the moving body is the child
+        const ChQuaterniond qp = body2->GetRot();
+        axis_in_parent = qp.RotateBack(frame.rot.Rotate(ChVector3d(0, 0, 1)));
+        offset_in_parent = qp.RotateBack(body1->GetPos() - body2->GetPos());
+        rel_rot = qp.GetConjugate() * body1->GetRot();
     }
 };
 // Translational spring-damper between two points given in the absolute frame.
@@ -288,13 +316,32 @@ class ChLinkTSDA : public ChLinkBase {
                     const ChVector3d& p2) {
         body1 = std::move(b1); body2 = std::move(b2);
         off1 = p1 - body1->GetPos(); off2 = p2 - body2->GetPos();
+        loc1 = body1->GetRot().RotateBack(off1); loc2 = body2->GetRot().RotateBack(off2);
         rest = (p1 - p2).Length();
     }
     void SetSpringCoefficient(double k) { k_ = k; }
     void SetDampingCoefficient(double c) { c_ = c; }
     void SetRestLength(double r) { rest = r; }
+    double GetSpringCoefficient() const { return k_; }
+    double GetDampingCoefficient() const { return c_; }
+    double GetRestLength() const { return rest; }
+    ChBody* GetBody1() const override { return body1.get(); }
+    ChBody* GetBody2() const override { return body2.get(); }
+    ChVector3d GetPoint1Abs() const { return body1->GetPos() + body1->GetRot().Rotate(loc1); }
+    ChVector3d GetPoint2Abs() const { return body2->GetPos() + body2->GetRot().Rotate(loc2); }
+    double GetLength() const { return (GetPoint1Abs() - GetPoint2Abs()).Length(); }
+    double GetVelocity() const {     // rate of change of the length
+        const ChVector3d d = GetPoint1Abs() - GetPoint2Abs();
+        const double len = d.Length();
+        if (len == 0.0) return 0.0;
+        const ChVector3d v1 = body1->GetPosDt() + (body1->GetAngVelParent() % body1->GetRot().Rotate(loc1));
+        const ChVector3d v2 = body2->GetPosDt() + (body2->GetAngVelParent() % body2->GetRot().Rotate(loc2));
+        return (v1 - v2).Dot(d * (1.0 / len));
+    }
+    double GetForce() const { return -(k_ * (GetLength() - rest) + c_ * GetVelocity()); }   // Chrono's sign: > 0 pushes apart
     std::shared_ptr<ChBody> body1, body2;
-    ChVector3d off1, off2;
+    ChVector3d off1, off2;      // attachment points relative to the bodies at assembly, world frame
+    ChVector3d loc1, loc2;      // the same in the bodies' own frames
     double rest = 0, k_ = 0, c_ = 0;
 };
 
@@ -322,8 +369,12 @@ class ChSystem {
     void Add(std::shared_ptr<ChLoadContainer> c) { load_containers_.push_back(std::move(c)); }
     void AddLink(std::shared_ptr<ChLinkBase> l) {
         if (auto t = std::dynamic_pointer_cast<ChLinkTSDA>(l)) tsdas_.push_back(t);
+        if (auto p = std::dynamic_pointer_cast<ChLinkLockPrismatic>(l)) prismatics_.push_back(p);
         links_.push_back(std::move(l));
     }
+    const std::vector<std::shared_ptr<ChLinkBase>>& GetLinks() const { return links_; }
+    const std::vector<std::shared_ptr<ChLinkTSDA>>& GetTSDAs() const { return tsdas_; }
+    const std::vector<std::shared_ptr<ChLinkLockPrismatic>>& GetPrismatics() const { return prismatics_; }
     double GetChTime() const { return time_; }
     void SetChTime(double t) { time_ = t; }
     double GetStep() const { return step_; }
@@ -336,12 +387,29 @@ class ChSystem {
     }
     // Advances one step (see the header comment).  Returns 1 like ChSystem::DoStepDynamics.
     int DoStepDynamics(double dt);
+    // The same step in two halves, for several systems advanced in lock-step around ONE batched force evaluation
+    // (hydroc/hydro_ensemble.h): StepBegin brings the system to the state its forces are evaluated at (HHT: the
+    // predictor at t + dt; linearised Euler: nothing, its forces belong to t), StepEnd evaluates the forces and
+    // completes the step.  DoStepDynamics(dt) == StepBegin(dt); StepEnd().
+    void StepBegin(double dt);
+    void StepEnd();
+    // compat-only: every system's StepBegin, then every system's StepEnd
+    static void DoStepDynamicsLockstep(const std::vector<ChSystem*>& systems, double dt) {
+        for (ChSystem* s : systems) s->StepBegin(dt);
+        for (ChSystem* s : systems) s->StepEnd();
+    }
 
   private:
     void Assemble(const std::vector<ChBody*>& act, std::vector<double>& F, std::vector<double>& M);
     std::vector<double> SolveAccelerations(const std::vector<ChBody*>& act, const std::vector<double>& rhs,
                                            const std::vector<double>& M);
-    int StepHHT(const std::vector<ChBody*>& act, double h);
+    void ProjectOntoJoints(const std::vector<ChBody*>& act);
+    void StepHHTBegin(const std::vector<ChBody*>& act, double h);
+    void StepHHTEnd(const std::vector<ChBody*>& act, double h);
+    std::vector<ChBody*> ActiveBodies() const;
+    struct HHTSaved { ChVector3d x, v, w; ChQuaterniond q; };
+    std::vector<HHTSaved> hht_s0_;
+    double pending_dt_ = 0.0;
     ChTimestepper::Type stepper_ = ChTimestepper::Type::EULER_IMPLICIT_LINEARIZED;
     std::vector<double> hht_F_, hht_a_;      // generalised force and accelerations at t_n (HHT)
     ChVector3d g_{0, 0, -9.81};
@@ -351,6 +419,7 @@ class ChSystem {
     std::vector<std::shared_ptr<ChLoadContainer>> load_containers_;
     std::vector<std::shared_ptr<ChLinkBase>> links_;
     std::vector<std::shared_ptr<ChLinkTSDA>> tsdas_;
+    std::vector<std::shared_ptr<ChLinkLockPrismatic>> prismatics_;
 };
 class ChSystemNSC : public ChSystem {};
 class ChSystemSMC : public ChSystem {};

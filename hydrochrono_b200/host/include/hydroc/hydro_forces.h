@@ -5,6 +5,7 @@
 #define HYDROC_B200_HYDRO_FORCES_H
 #pragma once
 
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -124,6 +125,7 @@ class TestHydro {
     std::vector<double> force_hydrostatic_, force_radiation_damping_, force_waves_, total_force_;
     double prev_time;
     bool components_fetched_ = false;
+    std::unique_ptr<std::ofstream> trace_;   // HYDROC_STATE_TRACE=<file>: log of every evaluation (debugging / parity tests)
 
     std::shared_ptr<ChLoadContainer> my_loadcontainer;
     std::shared_ptr<ChLoadAddedMass> my_loadbodyinertia;

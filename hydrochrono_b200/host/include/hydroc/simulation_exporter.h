@@ -2,8 +2,10 @@
 // per-step body states and writes one results .h5 in schema v0.3 at Finalize() -- /inputs/model/bodies/<name>/*,
 // /inputs/simulation/{time,environment,waves[/irregular]}, /results/time/time,
 // /results/model/bodies/<name>/{position,velocity,acceleration,orientation,orientation_xyz,angular_velocity},
-// /meta -- through the library's libhdf5-free writer (hc_h5_writer_*).  Joint / TSDA / RSDA result channels are
-// Chrono link internals and are not produced by the stand-in system.
+// /inputs/model/{joints,tsdas,rsdas}/names + per-link metadata, /results/model/tsdas/<name>/{force_vec,force_mag,
+// extension,speed,spring_force,damping_force,reaction_force_body1,2}, /results/model/joints/<name>/reaction{1,2}_{force,
+// torque}, /meta -- through the library's libhdf5-free writer (hc_h5_writer_*).  Joint reactions are reported in the
+// world frame (the reference reports Chrono's link-frame wrenches); the stand-in system has no rotational dampers.
 #ifndef HYDROC_B200_SIMULATION_EXPORTER_H
 #define HYDROC_B200_SIMULATION_EXPORTER_H
 

@@ -141,9 +141,11 @@ class IrregularWaves : public WaveBase {
 
   private:
     void FetchSpectrum() const;
+    void FetchComponents() const;
     IrregularWaveParams params_;
     const WaveMode mode_ = WaveMode::irregular;
     mutable std::vector<double> freqs_, S_, widths_, phases_, wavenumbers_;
+    mutable std::vector<double> comp_omega_, comp_amp_;
     mutable bool spectrum_fetched_ = false;
     std::string mesh_file_name_;
 };

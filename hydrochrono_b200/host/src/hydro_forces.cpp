@@ -6,6 +6,9 @@
 // same time return the cache -- the reference's own once-per-time-value contract (:742-755).
 #include <hydroc/hydro_forces.h>
 
+#include <cstdlib>
+#include <iomanip>
+
 #include <hydroc/chloadaddedmass.h>
 
 #include <cstring>
@@ -132,6 +135,7 @@ void TestHydro::Construct(std::shared_ptr<WaveBase> waves) {
     hc_throw_on_error(hc_ensemble_create(file_info_.handle(), &o, &ens_));
 
     for (int b = 0; b < num_bodies_; ++b) force_per_body_.emplace_back(bodies_[b], this);
+    if (const char* tr = std::getenv("HYDROC_STATE_TRACE")) trace_ = std::make_unique<std::ofstream>(tr);
 
     // added mass (reference :223-234)
     my_loadcontainer = chrono_types::make_shared<ChLoadContainer>();
@@ -221,6 +225,14 @@ void TestHydro::EvaluateAtCurrentTime() {
     hc_throw_on_error(hc_step(ens_, t, pose.data(), vel.data(), gv, total_force_.data(), nullptr));
     prev_time = t;
     components_fetched_ = false;
+    if (trace_) {   // HYDROC_STATE_TRACE: one line per evaluation -- t, pose[6N], vel[6N], g[3], total force[6N]
+        *trace_ << std::setprecision(17) << t;
+        for (double x : pose) *trace_ << ' ' << x;
+        for (double x : vel) *trace_ << ' ' << x;
+        *trace_ << ' ' << gv[0] << ' ' << gv[1] << ' ' << gv[2];
+        for (double x : total_force_) *trace_ << ' ' << x;
+        *trace_ << '\n';
+    }
 }
 
 static void fetch_components(hc_ensemble* ens, std::vector<double>& hs, std::vector<double>& rad, std::vector<double>& wv) {

@@ -17,6 +17,35 @@ struct SimulationExporter::Impl {
     };
     std::vector<BodyBuf> bodies;
     std::vector<double> time;
+    // links (reference src/simulation_exporter.cpp:103-152): translational spring-dampers and joints
+    struct TsdaBuf {
+        std::string name;
+        chrono::ChLinkTSDA* link = nullptr;
+        double rest_length = 0, k = 0, c = 0;
+        std::vector<double> force_vec, force_mag, extension, speed, spring_force, damping_force, react_b1, react_b2;
+    };
+    struct JointBuf {
+        std::string name;
+        chrono::ChLinkLockPrismatic* link = nullptr;
+        std::vector<double> f1, t1, f2, t2;
+    };
+    std::vector<TsdaBuf> tsdas;
+    std::vector<JointBuf> joints;
+    std::vector<std::string> joint_names, tsda_names, rsda_names;
+    static std::string Sanitize(const std::string& in) {     // reference :162-175
+        std::string out;
+        for (char ch : in) {
+            if (ch == ' ') out.push_back('_');
+            else if (ch == '/' || ch == '\\' || ch == ':') continue;
+            else out.push_back(ch);
+        }
+        return out.empty() ? std::string("unnamed") : out;
+    }
+    void names(const std::string& p, const std::vector<std::string>& v) {
+        std::vector<const char*> c;
+        for (const auto& x : v) c.push_back(x.c_str());
+        hc_throw_on_error(hc_h5_writer_put_string_array(w, p.c_str(), int(c.size()), c.data()));
+    }
 
     void group(const std::string& p) { hc_throw_on_error(hc_h5_writer_put_group(w, p.c_str())); }
     void attr(const std::string& p, const std::string& n, const std::string& v) {
@@ -116,6 +145,57 @@ void SimulationExporter::WriteModel(chrono::ChSystem* system) {
         buf.name = name;
         I.bodies.push_back(std::move(buf));
     }
+    // joints and dampers (reference :437-641)
+    I.tsdas.clear(); I.joints.clear(); I.joint_names.clear(); I.tsda_names.clear(); I.rsda_names.clear();
+    int tsda_idx = 0, joint_idx = 0;
+    auto body_name = [](chrono::ChBody* b) { return b ? b->GetName() : std::string(); };
+    for (auto& link_ptr : system->GetLinks()) {
+        chrono::ChLinkBase* base = link_ptr.get();
+        if (auto* tsda = dynamic_cast<chrono::ChLinkTSDA*>(base)) {
+            std::string raw = base->GetName();
+            if (raw.empty()) raw = "TSDA_" + std::to_string(++tsda_idx);
+            const std::string nm = Impl::Sanitize(raw), g = "/inputs/model/tsdas/" + nm;
+            I.tsda_names.push_back(nm);
+            I.group(g);
+            I.attr(g, "type", std::string("TSDA"));
+            I.attr(g, "body1", body_name(tsda->GetBody1()));
+            I.attr(g, "body2", body_name(tsda->GetBody2()));
+            const auto p1 = tsda->GetBody1()->GetPos(), p2 = tsda->GetBody2()->GetPos();
+            I.vec(g + "/point1", {p1.x(), p1.y(), p1.z()});
+            I.vec(g + "/point2", {p2.x(), p2.y(), p2.z()});
+            I.attr(g, "frame", std::string("world"));
+            I.attr(g, "spring_coefficient", tsda->GetSpringCoefficient());
+            I.attr(g, "damping_coefficient", tsda->GetDampingCoefficient());
+            I.attr(g, "free_length", tsda->GetRestLength());
+            Impl::TsdaBuf buf;
+            buf.name = nm; buf.link = tsda; buf.rest_length = tsda->GetRestLength();
+            buf.k = tsda->GetSpringCoefficient(); buf.c = tsda->GetDampingCoefficient();
+            I.tsdas.push_back(std::move(buf));
+            continue;
+        }
+        if (auto* lock = dynamic_cast<chrono::ChLinkLockPrismatic*>(base)) {
+            std::string raw = base->GetName();
+            if (raw.empty()) raw = "joint_" + std::to_string(++joint_idx);
+            const std::string nm = Impl::Sanitize(raw), g = "/inputs/model/joints/" + nm;
+            I.joint_names.push_back(nm);
+            I.group(g);
+            I.attr(g, "type", std::string("LOCK"));
+            I.attr(g, "body1", body_name(lock->GetBody1()));
+            I.attr(g, "body2", body_name(lock->GetBody2()));
+            const auto loc = lock->GetBody1()->GetPos();
+            const auto ax = lock->GetBody2()->GetRot().Rotate(lock->axis_in_parent);
+            I.vec(g + "/location", {loc.x(), loc.y(), loc.z()});
+            I.vec(g + "/axis", {ax.x(), ax.y(), ax.z()});
+            I.attr(g, "frame", std::string("world"));
+            Impl::JointBuf buf;
+            buf.name = nm; buf.link = lock;
+            I.joints.push_back(std::move(buf));
+        }
+    }
+    // names arrays are always written, even when empty (reference :638-641)
+    I.names("/inputs/model/joints/names", I.joint_names);
+    I.names("/inputs/model/tsdas/names", I.tsda_names);
+    I.names("/inputs/model/rsdas/names", I.rsda_names);
 }
 
 void SimulationExporter::BeginResults(chrono::ChSystem* system, int expected_steps) {
@@ -141,6 +221,35 @@ void SimulationExporter::RecordStep(chrono::ChSystem* system) {
         buf.quat.insert(buf.quat.end(), {q.e0, q.e1, q.e2, q.e3});
         buf.euler.insert(buf.euler.end(), {e.x(), e.y(), e.z()});
         buf.wvel.insert(buf.wvel.end(), {w.x(), w.y(), w.z()});
+    }
+    // TSDA channels (reference :760-794): direction body1 -> body2, speed = relative velocity along it
+    for (auto& t : I.tsdas) {
+        chrono::ChLinkTSDA* L = t.link;
+        const double fmag = L->GetForce(), ext = L->GetLength() - t.rest_length;
+        const auto p1 = L->GetBody1()->GetPos(), p2 = L->GetBody2()->GetPos();
+        const auto d12 = p2 - p1;
+        const double nrm = d12.Length();
+        const chrono::ChVector3d dir = nrm > 1e-12 ? d12 * (1.0 / nrm) : chrono::ChVector3d(1, 0, 0);
+        const auto fvec = dir * fmag;
+        const double rel_speed = (L->GetBody2()->GetPosDt() - L->GetBody1()->GetPosDt()).Dot(dir);
+        t.force_vec.insert(t.force_vec.end(), {fvec.x(), fvec.y(), fvec.z()});
+        t.force_mag.push_back(fmag);
+        t.extension.push_back(ext);
+        t.speed.push_back(rel_speed);
+        t.spring_force.push_back(t.k * ext);
+        t.damping_force.push_back(t.c * rel_speed);
+        t.react_b1.insert(t.react_b1.end(), {fvec.x(), fvec.y(), fvec.z()});
+        t.react_b2.insert(t.react_b2.end(), {-fvec.x(), -fvec.y(), -fvec.z()});
+    }
+    // joint reactions (reference :823-851), world frame: body 2 gets the opposite force and the torque moved to it
+    for (auto& j : I.joints) {
+        const auto f = j.link->GetReactForce1(), tq = j.link->GetReactTorque1();
+        const auto arm = j.link->GetBody1()->GetPos() - j.link->GetBody2()->GetPos();
+        const auto t2 = -(tq + (arm % f));
+        j.f1.insert(j.f1.end(), {f.x(), f.y(), f.z()});
+        j.t1.insert(j.t1.end(), {tq.x(), tq.y(), tq.z()});
+        j.f2.insert(j.f2.end(), {-f.x(), -f.y(), -f.z()});
+        j.t2.insert(j.t2.end(), {t2.x(), t2.y(), t2.z()});
     }
 }
 
@@ -191,6 +300,39 @@ void SimulationExporter::Finalize() {
         I.attr(g, "orientation_xyz_convention", std::string("TaitBryan_extrinsic_XYZ"));
         I.attr(g, "orientation_xyz_units", std::string("rad"));
         I.attr(g, "angular_velocity_units", std::string("rad/s"));
+    }
+    for (auto& t : I.tsdas) {
+        const std::string g = "/results/model/tsdas/" + t.name;
+        I.group(g);
+        I.attr(g, "type", std::string("TSDA"));
+        I.attr(g, "time_ref", std::string("/results/time/time"));
+        I.attr(g, "frame", std::string("world"));
+        I.attr(g, "units_force", std::string("N"));
+        I.attr(g, "units_extension", std::string("m"));
+        I.attr(g, "units_speed", std::string("m/s"));
+        I.mat(g + "/force_vec", t.force_vec, 3);
+        I.vec(g + "/force_mag", t.force_mag);
+        I.vec(g + "/extension", t.extension);
+        I.vec(g + "/speed", t.speed);
+        I.vec(g + "/spring_force", t.spring_force);
+        I.vec(g + "/damping_force", t.damping_force);
+        I.mat(g + "/reaction_force_body1", t.react_b1, 3);
+        I.mat(g + "/reaction_force_body2", t.react_b2, 3);
+    }
+    for (auto& j : I.joints) {
+        const std::string g = "/results/model/joints/" + j.name;
+        I.group(g);
+        I.attr(g, "type", std::string("LOCK"));
+        I.attr(g, "class", std::string("ChLinkLockPrismatic"));
+        I.attr(g, "time_ref", std::string("/results/time/time"));
+        I.attr(g, "frame1", std::string("world"));
+        I.attr(g, "frame2", std::string("world"));
+        I.attr(g, "units_force", std::string("N"));
+        I.attr(g, "units_torque", std::string("N*m"));
+        I.mat(g + "/reaction1_force", j.f1, 3);
+        I.mat(g + "/reaction1_torque", j.t1, 3);
+        I.mat(g + "/reaction2_force", j.f2, 3);
+        I.mat(g + "/reaction2_torque", j.t2, 3);
     }
     const Options& o = I.options;
     if (!o.run_started_at_utc.empty()) I.attr("/meta/run", "started_at_utc", o.run_started_at_utc);

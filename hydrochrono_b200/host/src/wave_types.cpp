@@ -30,39 +30,21 @@ Eigen::VectorXd JONSWAPSpectrumHz(Eigen::VectorXd& f, double Hs, double Tp, doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// Airy kinematics of one component (src/wave_types.cpp:14-25,61-122); waves travel along global +x
+// Airy kinematics (src/wave_types.cpp:14-160,515-550): the arithmetic lives behind the C ABI (hc_wave_kinematics,
+// host code, off the step path as in the reference); waves travel along global +x
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct Component { double omega, amplitude, phase, k; };
-
-double eta_of(const Component& c, double x, double t) { return c.amplitude * std::cos(c.k * x - c.omega * t + c.phase); }
-
-bool deep(const Component& c, double depth) { return 2 * M_PI / c.k > depth || c.k * depth > 500.0; }
-
-Eigen::Vector3d velocity_of(const Component& c, const Eigen::Vector3d& p, double t, double depth, double mwl) {
-    const double z = p.z() - mwl, th = c.k * p.x() - c.omega * t + c.phase;
-    Eigen::Vector3d v(0.0, 0.0, 0.0);
-    if (deep(c, depth)) {
-        v[0] = c.omega * c.amplitude * std::exp(c.k * z) * std::cos(th);
-        v[2] = c.omega * c.amplitude * std::exp(c.k * z) * std::sin(th);
-    } else {
-        v[0] = c.omega * c.amplitude * std::cosh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::cos(th);
-        v[2] = c.omega * c.amplitude * std::sinh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::sin(th);
-    }
-    return v;
-}
-
-Eigen::Vector3d acceleration_of(const Component& c, const Eigen::Vector3d& p, double t, double depth, double mwl) {
-    const double z = p.z() - mwl, th = c.k * p.x() - c.omega * t + c.phase;
-    Eigen::Vector3d a(0.0, 0.0, 0.0);
-    if (deep(c, depth)) {
-        a[0] = c.omega * c.omega * c.amplitude * std::exp(c.k * z) * std::sin(th);
-        a[2] = -c.omega * c.omega * c.amplitude * std::exp(c.k * z) * std::cos(th);
-    } else {
-        a[0] = c.omega * c.omega * c.amplitude * std::cosh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::sin(th);
-        a[2] = -c.omega * c.omega * c.amplitude * std::sinh(c.k * (z + depth)) / std::sinh(c.k * depth) * std::cos(th);
-    }
-    return a;
+struct Kin { double eta; Eigen::Vector3d vel, acc; };
+Kin kinematics(const std::vector<double>& omega, const std::vector<double>& amp, const std::vector<double>& phase,
+               const std::vector<double>& k, const Eigen::Vector3d& p, double t, double depth, double mwl, bool wheeler) {
+    Kin r{0.0, Eigen::Vector3d(0.0, 0.0, 0.0), Eigen::Vector3d(0.0, 0.0, 0.0)};
+    const double pos[3] = {p.x(), p.y(), p.z()};
+    double v[3], a[3];
+    hc_throw_on_error(hc_wave_kinematics(int(omega.size()), omega.data(), amp.data(), phase.data(), k.data(), pos, t, depth,
+                                         mwl, wheeler ? 1 : 0, &r.eta, v, a));
+    r.vel = Eigen::Vector3d(v[0], v[1], v[2]);
+    r.acc = Eigen::Vector3d(a[0], a[1], a[2]);
+    return r;
 }
 }  // namespace
 
@@ -132,15 +114,16 @@ Eigen::VectorXd RegularWave::GetExcitationPhase() const {
 }
 
 double RegularWave::GetElevation(const Eigen::Vector3d& position, double time) {
-    return eta_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position.x(), time);
+    return kinematics({regular_wave_omega_}, {regular_wave_amplitude_}, {regular_wave_phase_}, {wavenumber_}, position, time,
+                      water_depth_, mwl_, false).eta;
 }
 Eigen::Vector3d RegularWave::GetVelocity(const Eigen::Vector3d& position, double time) {
-    return velocity_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position, time,
-                       water_depth_, mwl_);
+    return kinematics({regular_wave_omega_}, {regular_wave_amplitude_}, {regular_wave_phase_}, {wavenumber_}, position, time,
+                      water_depth_, mwl_, false).vel;
 }
 Eigen::Vector3d RegularWave::GetAcceleration(const Eigen::Vector3d& position, double time) {
-    return acceleration_of({regular_wave_omega_, regular_wave_amplitude_, regular_wave_phase_, wavenumber_}, position, time,
-                           water_depth_, mwl_);
+    return kinematics({regular_wave_omega_}, {regular_wave_amplitude_}, {regular_wave_phase_}, {wavenumber_}, position, time,
+                      water_depth_, mwl_, false).acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +156,7 @@ void IrregularWaves::Bind(hc_ensemble* ens, const HydroData::SimulationParameter
     q.seed = params_.seed_;
     hc_throw_on_error(hc_waves_irregular(ens, &q, nullptr, nullptr, nullptr));
     spectrum_fetched_ = false;
+    comp_omega_.clear(); comp_amp_.clear();
 }
 
 void IrregularWaves::FetchSpectrum() const {
@@ -209,46 +193,32 @@ std::vector<double> IrregularWaves::GetFreeSurfaceTime() const {
 
 Eigen::VectorXd IrregularWaves::GetForceAtTime(double t) { return DeviceForce(t); }
 
-double IrregularWaves::GetElevation(const Eigen::Vector3d& position, double time) {
+// per-component omega = 2 pi f and amplitude = sqrt(2 S df) exactly as GetEtaIrregular forms them (:38-40)
+void IrregularWaves::FetchComponents() const {
     FetchSpectrum();
-    double eta = 0.0;
+    if (comp_omega_.size() == freqs_.size()) return;
+    comp_omega_.resize(freqs_.size()); comp_amp_.resize(freqs_.size());
     for (size_t i = 0; i < freqs_.size(); ++i) {
-        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
-        eta += eta_of(c, position.x(), time);
+        comp_amp_[i] = std::sqrt(2 * S_[i] * widths_[i]);
+        comp_omega_[i] = 2 * M_PI * freqs_[i];
     }
-    return eta;
+}
+
+double IrregularWaves::GetElevation(const Eigen::Vector3d& position, double time) {
+    FetchComponents();
+    return kinematics(comp_omega_, comp_amp_, phases_, wavenumbers_, position, time, water_depth_, mwl_, false).eta;
 }
 
 Eigen::Vector3d IrregularWaves::GetVelocity(const Eigen::Vector3d& position, double time) {
-    FetchSpectrum();
-    Eigen::Vector3d p = position;
-    if (params_.wave_stretching_) {   // Wheeler stretching (:516-525)
-        const double eta = GetElevation(position, time);
-        const double z = position.z() - mwl_;
-        p[2] = water_depth_ * (z - eta) / (water_depth_ + eta);
-    }
-    Eigen::Vector3d v(0.0, 0.0, 0.0);
-    for (size_t i = 0; i < freqs_.size(); ++i) {
-        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
-        v += velocity_of(c, p, time, water_depth_, mwl_);
-    }
-    return v;
+    FetchComponents();       // Wheeler stretching (:516-525) inside hc_wave_kinematics
+    return kinematics(comp_omega_, comp_amp_, phases_, wavenumbers_, position, time, water_depth_, mwl_,
+                      params_.wave_stretching_).vel;
 }
 
 Eigen::Vector3d IrregularWaves::GetAcceleration(const Eigen::Vector3d& position, double time) {
-    FetchSpectrum();
-    Eigen::Vector3d p = position;
-    if (params_.wave_stretching_) {
-        const double eta = GetElevation(position, time);
-        const double z = position.z() - mwl_;
-        p[2] = water_depth_ * (z - eta) / (water_depth_ + eta);
-    }
-    Eigen::Vector3d a(0.0, 0.0, 0.0);
-    for (size_t i = 0; i < freqs_.size(); ++i) {
-        const Component c{2 * M_PI * freqs_[i], std::sqrt(2 * S_[i] * widths_[i]), phases_[i], wavenumbers_[i]};
-        a += acceleration_of(c, p, time, water_depth_, mwl_);
-    }
-    return a;
+    FetchComponents();
+    return kinematics(comp_omega_, comp_amp_, phases_, wavenumbers_, position, time, water_depth_, mwl_,
+                      params_.wave_stretching_).acc;
 }
 
 // Free-surface strip mesh for visualisation: two vertices per elevation sample, two triangles per quad.

@@ -318,6 +318,48 @@ HC_API hc_status hc_measure_fp64_mma_peak(int device, double* tflops);
 HC_API void* hc_host_alloc(size_t bytes);
 HC_API void hc_host_free(void* p);
 
+/* -------------------------------------------------------------------------------------
+ * Multi-device ensemble: the B instances of one ensemble partitioned over several GPUs of one node.
+ * Instances are independent and the tables are replicated, so there is no exchange between devices on the step
+ * path; the reference has no counterpart (it steps one system on one CPU thread) -- the per-step contract kept is
+ * "one evaluation per time value" (src/hydro_forces.cpp:742-767) for every shard.  Shard i owns the contiguous block
+ * hc_multi_shard_range(B, n, i) of global instance indices, has its own hc_ensemble on devices[i] and its own host
+ * thread.  opts->batch is the TOTAL number of instances, opts->device is ignored, opts->stream must be NULL; the
+ * look-ahead "auto" thresholds apply per shard (pass explicit modes for small shards).  A device may be listed more
+ * than once (several shards on one GPU).
+ * ------------------------------------------------------------------------------------- */
+typedef struct hc_multi_ensemble hc_multi_ensemble;
+HC_API void hc_multi_shard_range(int total, int shards, int index, int* first, int* count);
+HC_API hc_status hc_multi_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, const int* devices /* NULL: 0..n-1 */,
+                                          int n_devices, hc_multi_ensemble** out);
+HC_API void hc_multi_ensemble_destroy(hc_multi_ensemble* m);
+HC_API int hc_multi_ensemble_num_shards(const hc_multi_ensemble* m);
+HC_API int hc_multi_ensemble_batch(const hc_multi_ensemble* m);          /* total instances */
+/* Device, first global instance, instance count and the per-device handle of shard `index` (any out pointer may be
+ * NULL).  The handle may be used with the single-device queries (hc_waves_irregular_eta, hc_get_profile, ...) from the
+ * calling thread while no hc_multi_* call is in flight. */
+HC_API hc_status hc_multi_ensemble_shard(const hc_multi_ensemble* m, int index, int* device, int* first, int* count,
+                                         hc_ensemble** ens);
+/* Wave set-up for all shards at once; per-instance arrays are indexed by GLOBAL instance ([B]). */
+HC_API hc_status hc_multi_waves_none(hc_multi_ensemble* m);
+HC_API hc_status hc_multi_waves_regular(hc_multi_ensemble* m, int count /* 1 or B */, const double* amplitude,
+                                        const double* omega, const double* phase /* may be NULL */);
+HC_API hc_status hc_multi_waves_irregular(hc_multi_ensemble* m, const hc_irregular_params* p, const int* seeds /* [B] or NULL */,
+                                          const double* Hs /* [B] or NULL */, const double* Tp /* [B] or NULL */);
+/* One lock-step of every instance on every device: host [B][6N] arrays in global instance order (pinned recommended);
+ * each shard uploads, evaluates and downloads its own slice concurrently -- the result gather is the slices landing
+ * in `force`.  Synchronous at return.  Same status codes and time-keyed cache as hc_step. */
+HC_API hc_status hc_multi_step(hc_multi_ensemble* m, double t, const double* pose, const double* vel, const double g_vec[3],
+                               double* force, int* recomputed /* may be NULL */);
+/* Device-resident variant: per shard a device pointer on that shard's device ([count_i][6N]); asynchronous on the
+ * shards' streams (hc_multi_sync waits). */
+HC_API hc_status hc_multi_step_device(hc_multi_ensemble* m, double t, const double* const* d_pose, const double* const* d_vel,
+                                      const double g_vec[3], double* const* d_force);
+/* Final gather of the three force components of the last evaluation, host [B][6N] each (may be NULL). */
+HC_API hc_status hc_multi_get_components(hc_multi_ensemble* m, double* hydrostatic, double* radiation, double* waves);
+HC_API hc_status hc_multi_sync(hc_multi_ensemble* m);
+HC_API hc_status hc_multi_reset(hc_multi_ensemble* m);
+
 /* ---- stand-alone wave helpers on the reference's public surface (host, setup-time) ---- */
 HC_API hc_status hc_pierson_moskowitz_spectrum_hz(int n, const double* f, double Hs, double Tp, double* S);
 HC_API hc_status hc_jonswap_spectrum_hz(int n, const double* f, double Hs, double Tp, double gamma,
@@ -329,6 +371,17 @@ HC_API hc_status hc_resample_excitation_irf(const hc_tables* t, double dt, int b
                                             double* width_out, double* f_out /*[6][n]*/);
 /* Random phases of CreateSpectrum (src/wave_types.cpp:663-669): std::mt19937(seed), uniform_real(0, 2 pi). */
 HC_API hc_status hc_random_phases(int seed, int n, double* out);
+/* Airy water kinematics at a point for a sum of n wave components travelling along +x (host arithmetic, off the step
+ * path as in the reference): GetEta / GetEtaIrregular (src/wave_types.cpp:14-45), GetWaterVelocity /
+ * GetWaterAcceleration (+Irregular) (:61-160, deep-water branch when 2 pi / k > depth or k depth > 500), and the Wheeler
+ * stretching of IrregularWaves::GetVelocity / GetAcceleration (:515-545) when wheeler_stretching != 0:
+ * z' = depth (z - mwl - eta) / (depth + eta).  Components are summed in ascending order.  n = 1 with
+ * wheeler_stretching = 0 is RegularWave::GetElevation / GetVelocity / GetAcceleration (:301-313).
+ * Any of eta / velocity / acceleration may be NULL. */
+HC_API hc_status hc_wave_kinematics(int n, const double* omega, const double* amplitude, const double* phase,
+                                    const double* wavenumber, const double position[3], double time, double water_depth,
+                                    double mwl, int wheeler_stretching, double* eta, double velocity[3],
+                                    double acceleration[3]);
 
 /* ---------------------------------------------------------------------------------------
  * HDF5 output / generic input without libhdf5 (classic format: superblock v0, old-style groups, contiguous
@@ -343,6 +396,8 @@ HC_API hc_status hc_h5_writer_put_group(hc_h5_writer* w, const char* path);
 HC_API hc_status hc_h5_writer_put_f64(hc_h5_writer* w, const char* path, int rank, const uint64_t* dims,
                                       const double* data);
 HC_API hc_status hc_h5_writer_put_string(hc_h5_writer* w, const char* path, const char* value);
+/* 1-D dataset of fixed-length, null-padded strings (names arrays of the results schema). */
+HC_API hc_status hc_h5_writer_put_string_array(hc_h5_writer* w, const char* path, int count, const char* const* values);
 HC_API hc_status hc_h5_writer_attr_string(hc_h5_writer* w, const char* path, const char* name, const char* value);
 HC_API hc_status hc_h5_writer_attr_f64(hc_h5_writer* w, const char* path, const char* name, double value);
 HC_API hc_status hc_h5_writer_save(hc_h5_writer* w, const char* file);

@@ -470,6 +470,92 @@ static double EtaIrregular(double x_pos, double time, const Waves& W) {
     return eta;
 }
 
+// ---- water kinematics (off the per-step force path; WaveBase surface) -------------------------------------------
+struct V3 { double x = 0, y = 0, z = 0; };
+// wave_types.cpp:14-25 GetEta
+static double GetEta(const V3& position, double time, double omega, double amplitude, double phase, double wavenumber) {
+    double x_pos = position.x;
+    double eta = amplitude * std::cos(wavenumber * x_pos - omega * time + phase);
+    return eta;
+}
+// wave_types.cpp:61-91 GetWaterVelocity
+static V3 GetWaterVelocity(const V3& position, double time, double omega, double amplitude, double phase, double wavenumber,
+                           double water_depth, double mwl) {
+    double x_pos = position.x;
+    double z_pos = position.z - mwl;
+    V3 water_velocity;
+    if (2 * M_PI / wavenumber > water_depth || wavenumber * water_depth > 500.0) {
+        water_velocity.x = omega * amplitude * std::exp(wavenumber * z_pos) * std::cos(wavenumber * x_pos - omega * time + phase);
+        water_velocity.z = omega * amplitude * std::exp(wavenumber * z_pos) * std::sin(wavenumber * x_pos - omega * time + phase);
+    } else {
+        water_velocity.x = omega * amplitude * std::cosh(wavenumber * (z_pos + water_depth)) /
+                           std::sinh(wavenumber * water_depth) * std::cos(wavenumber * x_pos - omega * time + phase);
+        water_velocity.z = omega * amplitude * std::sinh(wavenumber * (z_pos + water_depth)) /
+                           std::sinh(wavenumber * water_depth) * std::sin(wavenumber * x_pos - omega * time + phase);
+    }
+    return water_velocity;
+}
+// wave_types.cpp:93-122 GetWaterAcceleration
+static V3 GetWaterAcceleration(const V3& position, double time, double omega, double amplitude, double phase,
+                               double wavenumber, double water_depth, double mwl) {
+    double x_pos = position.x;
+    double z_pos = position.z - mwl;
+    V3 water_acceleration;
+    if (2 * M_PI / wavenumber > water_depth || wavenumber * water_depth > 500.0) {
+        water_acceleration.x =
+            omega * omega * amplitude * std::exp(wavenumber * z_pos) * std::sin(wavenumber * x_pos - omega * time + phase);
+        water_acceleration.z =
+            -omega * omega * amplitude * std::exp(wavenumber * z_pos) * std::cos(wavenumber * x_pos - omega * time + phase);
+    } else {
+        water_acceleration.x = omega * omega * amplitude * std::cosh(wavenumber * (z_pos + water_depth)) /
+                               std::sinh(wavenumber * water_depth) * std::sin(wavenumber * x_pos - omega * time + phase);
+        water_acceleration.z = -omega * omega * amplitude * std::sinh(wavenumber * (z_pos + water_depth)) /
+                               std::sinh(wavenumber * water_depth) * std::cos(wavenumber * x_pos - omega * time + phase);
+    }
+    return water_acceleration;
+}
+// wave_types.cpp:124-141 / 143-160 GetWaterVelocityIrregular / GetWaterAccelerationIrregular
+static V3 GetWaterVelocityIrregular(const V3& position, double time, const Waves& W, double water_depth, double mwl) {
+    V3 water_velocity;
+    for (size_t i = 0; i < W.freqs.size(); ++i) {
+        double amplitude = std::sqrt(2 * W.S[i] * W.widths[i]);
+        double omega = 2 * M_PI * W.freqs[i];
+        V3 c = GetWaterVelocity(position, time, omega, amplitude, W.phases[i], W.wavenumbers[i], water_depth, mwl);
+        water_velocity.x += c.x; water_velocity.y += c.y; water_velocity.z += c.z;
+    }
+    return water_velocity;
+}
+static V3 GetWaterAccelerationIrregular(const V3& position, double time, const Waves& W, double water_depth, double mwl) {
+    V3 water_acceleration;
+    for (size_t i = 0; i < W.freqs.size(); ++i) {
+        double amplitude = std::sqrt(2 * W.S[i] * W.widths[i]);
+        double omega = 2 * M_PI * W.freqs[i];
+        V3 c = GetWaterAcceleration(position, time, omega, amplitude, W.phases[i], W.wavenumbers[i], water_depth, mwl);
+        water_acceleration.x += c.x; water_acceleration.y += c.y; water_acceleration.z += c.z;
+    }
+    return water_acceleration;
+}
+// {NoWave,RegularWave,IrregularWaves}::GetElevation / GetVelocity / GetAcceleration
+// (include/hydroc/wave_types.h:103-109, wave_types.cpp:301-313, :515-550 incl. Wheeler stretching)
+static void WaveKinematics(const Tables& T, const Waves& W, const V3& position, double time, bool wave_stretching,
+                           double mwl, double& eta, V3& vel, V3& acc) {
+    eta = 0.0; vel = V3(); acc = V3();
+    if (W.mode == kRegular) {
+        eta = GetEta(position, time, W.reg_omega, W.reg_amplitude, W.reg_phase, W.wavenumber);
+        vel = GetWaterVelocity(position, time, W.reg_omega, W.reg_amplitude, W.reg_phase, W.wavenumber, T.depth, mwl);
+        acc = GetWaterAcceleration(position, time, W.reg_omega, W.reg_amplitude, W.reg_phase, W.wavenumber, T.depth, mwl);
+    } else if (W.mode == kIrregular) {
+        eta = EtaIrregular(position.x, time, W);
+        V3 position_stretched = position;
+        if (wave_stretching) {
+            double z_pos = position.z - mwl;
+            position_stretched.z = T.depth * (z_pos - eta) / (T.depth + eta);      // Wheeler stretching
+        }
+        vel = GetWaterVelocityIrregular(position_stretched, time, W, T.depth, mwl);
+        acc = GetWaterAccelerationIrregular(position_stretched, time, W, T.depth, mwl);
+    }
+}
+
 // wave_types.cpp:717-774 CreateFreeSurfaceElevation
 static void CreateFreeSurfaceElevation(Waves& W) {
     const IrregularParams& p = W.ip;
@@ -1056,6 +1142,20 @@ double orc_bench_steps(OrcInstance** inst, int count, int nsteps, double t0, dou
     const double el = now_s() - tstart;
     if (checksum) *checksum = cs;
     return el;
+}
+
+// WaveBase::GetElevation / GetVelocity / GetAcceleration of the instance's wave object at a point.
+int orc_wave_kinematics(OrcInstance* o, const double* position, double time, int wave_stretching, double mwl, double* eta,
+                        double* vel, double* acc) {
+    ORC_TRY
+    V3 p; p.x = position[0]; p.y = position[1]; p.z = position[2];
+    double e; V3 v, a;
+    WaveKinematics(*o->I.T, o->I.W, p, time, wave_stretching != 0, mwl, e, v, a);
+    if (eta) *eta = e;
+    if (vel) { vel[0] = v.x; vel[1] = v.y; vel[2] = v.z; }
+    if (acc) { acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; }
+    return 0;
+    ORC_CATCH
 }
 
 // Test/bench infrastructure (not a restatement of reference code): loads a velocity history as if the instance had

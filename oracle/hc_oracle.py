@@ -66,6 +66,7 @@ def lib():
         L.orc_bench_steps.restype = C.c_double
         L.orc_bench_steps.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp,
                                       _dp, _dp, _dp]
+        L.orc_wave_kinematics.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int, C.c_double, _dp, _dp, _dp]
         L.orc_set_history.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.orc_bench_lockstep.restype = C.c_double
         L.orc_bench_lockstep.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, C.c_int,
@@ -220,6 +221,16 @@ class Instance:
 
     def history_len(self):
         return lib().orc_history_len(self.h)
+
+    def kinematics(self, position, t, wave_stretching=True, mwl=0.0):
+        """(eta, velocity[3], acceleration[3]) of the wave object at a point: WaveBase::GetElevation / GetVelocity /
+        GetAcceleration (src/wave_types.cpp:301-313,515-550)."""
+        p = _c(position)
+        eta = C.c_double()
+        v, a = np.empty(3), np.empty(3)
+        if lib().orc_wave_kinematics(self.h, _p(p), t, int(wave_stretching), mwl, C.byref(eta), _p(v), _p(a)):
+            raise OracleError(_err())
+        return eta.value, v, a
 
     def set_history(self, times_newest_first, vel):
         """Loads a velocity history (times newest first, vel[n][D]) as if the instance had been stepped through it."""

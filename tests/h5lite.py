@@ -160,6 +160,8 @@ class H5Lite:
             n = int(np.prod(dims)) if dims else 1
             return np.frombuffer(raw, dtype="<f8", count=n).reshape(dims).copy()
         if dt_class == 3:
+            if dims:        # 1-D array of fixed-length strings
+                return [raw[i * dt_size:(i + 1) * dt_size].split(b"\0")[0].decode() for i in range(int(dims[0]))]
             return raw.split(b"\0")[0].decode()
         raise ValueError("datatype class %d size %d unsupported" % (dt_class, dt_size))
 

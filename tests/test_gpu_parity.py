@@ -32,8 +32,9 @@ def _assert_parity(got, ref, what, rel=1e-9):
     err = np.abs(got - ref)
     ratio = np.where(tol > 0, err / np.where(tol > 0, tol, 1.0), np.where(err > 0, np.inf, 0.0))
     worst = np.unravel_index(np.argmax(ratio), err.shape)
-    assert np.all(err <= tol), "%s: worst at %s: got %r ref %r (err/tol %.3g)" % (
-        what, worst, got[worst], ref[worst], ratio[worst])
+    bad = np.unique(np.argwhere(err > tol)[:, 0]) if err.ndim > 1 else np.argwhere(err > tol).ravel()
+    assert np.all(err <= tol), "%s: worst at %s: got %r ref %r (err/tol %.3g); %d failing entries along axis 0: %s ... %s" % (
+        what, worst, got[worst], ref[worst], ratio[worst], bad.size, bad[:12].tolist(), bad[-4:].tolist())
     return float(ratio.max()) * rel       # worst error in units of max(|F_ref|, floor)
 
 
@@ -704,7 +705,7 @@ def test_benchmark_state_parity(rm3, snap, pass_mode):
         else:
             ens.step(times[n], h_pose[n % NB].numpy(), h_vel[n % NB].numpy(), G981, out=h_force.numpy())
             got[n] = h_force.numpy()[sample]
-    assert ens.history_len() == 6001
+    hist_len = ens.history_len()
     st = ens.rad_block_stats()
     if snap > 0:
         assert st["steps_served"] >= nsteps - 2, st              # every step but the first ones came from a block
@@ -719,7 +720,7 @@ def test_benchmark_state_parity(rm3, snap, pass_mode):
         insts.append(i)
     _, _, ref = orc.bench_lockstep(insts, times, pose[:, sample, :].copy(), vel[:, sample, :].copy(), buf0=0, mode=1,
                                    gvec=G981, want_forces=True)
-    assert insts[0].history_len() == 6001
+    assert insts[0].history_len() == hist_len >= 6001          # full window (+ the extra entry kept for bracketing)
     worst = _assert_parity(got, ref, "benchmark state, snap %g, pass mode %d" % (snap, pass_mode))
     print("benchmark-state parity: worst relative error %.2e over %d steps x %d instances" % (worst, nsteps, len(sample)))
 
@@ -763,11 +764,12 @@ def test_lookahead_restage_after_auto_disable_and_reset_rearm():
 
 
 @pytest.mark.gpu
-def test_eta_window_error_leaves_reference_state(rm3):
+def test_eta_window_error_leaves_reference_state():
     """The reference throws from ComputeForceWaves (wave_types.cpp:833-840) after ComputeForceRadiationDampingConv has
     pushed the sample and prev_time was set (hydro_forces.cpp:747-756): the history keeps the sample and a second call
     at the same time returns the cached (zero) totals instead of throwing again."""
-    T, O = rm3
+    raw = synth.rm3_like(exc_irf_steps=201, exc_half_window=5.0)     # eta window ends at t ~ 6 s, long before the
+    T, O = hc.Tables.from_raw(raw), orc.Tables(raw)                  # 60 s radiation window starts pruning
     B, D, dt = 3, 12, 0.05
     ens = hc.Ensemble(T, batch=B, dt_hint=dt)
     kw = dict(dt=dt, duration=1.0, ramp=0.5, Hs=2.5, Tp=8.0, nfreq=16, gamma=3.3)
@@ -794,3 +796,53 @@ def test_eta_window_error_leaves_reference_state(rm3):
     F = ens.step(t, pose, vel)                                    # cached totals of that time: the zeros of the reset
     assert ens.last_recomputed is False and np.all(F == 0.0)
     ens.close()
+
+
+@pytest.mark.gpu
+def test_multi_device_handle_matches_single_ensemble(rm3):
+    """hc_multi_* (SURVEY 8e): the instances partitioned into contiguous shards, one hc_ensemble + one host thread per
+    shard.  Run here as 3 uneven shards on whatever devices exist (several shards may share a GPU).  Forces and the
+    gathered components must equal, bit for bit, what three stand-alone ensembles of the shard sizes give (seeds follow
+    the GLOBAL instance index), and agree with one ensemble of all 200 instances to rounding (the lag-chunk and
+    eta-segment partitions, hence the summation grouping, depend on the batch size)."""
+    T, O = rm3
+    B, D, dt = 200, 12, 0.01
+    ndev = hc.device_count()
+    devices = [i % ndev for i in range(3)]
+    kw = dict(dt=dt, duration=3.0, ramp=1.0, Hs=2.5, Tp=8.0, nfreq=24, gamma=3.3)
+    opts = dict(dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2, exc_lookahead=4)
+    seeds = np.arange(11, 11 + B, dtype=np.int32)
+    one = hc.Ensemble(T, batch=B, **opts)
+    one.set_waves_irregular(seeds=seeds, **kw)
+    multi = hc.MultiEnsemble(T, batch=B, devices=devices, **opts)
+    multi.set_waves_irregular(seeds=seeds, **kw)
+    sh = multi.shards()
+    assert [s["count"] for s in sh] == [67, 67, 66] and [s["first"] for s in sh] == [0, 67, 134]
+    assert [s["device"] for s in sh] == devices
+    parts = []
+    for s in sh:
+        e = hc.Ensemble(T, batch=s["count"], device=s["device"], **opts)
+        e.set_waves_irregular(seeds=seeds[s["first"]:s["first"] + s["count"]], **kw)
+        parts.append(e)
+    for t in _acc_times(130, dt):
+        pose, vel = _motion(D, B, t)
+        F1 = one.step(t, pose, vel)
+        F2 = multi.step(t, pose, vel)
+        F3 = np.concatenate([e.step(t, pose[s["first"]:s["first"] + s["count"]], vel[s["first"]:s["first"] + s["count"]])
+                             for e, s in zip(parts, sh)])
+        np.testing.assert_array_equal(F2, F3)
+        _assert_parity(F2, F1, "sharded vs one ensemble", rel=1e-11)
+    for a, b in zip(multi.components(), [np.concatenate(c) for c in zip(*[e.components() for e in parts])]):
+        np.testing.assert_array_equal(a, b)
+    F4 = multi.step(t, pose, vel)                           # same time again: every shard serves its cache
+    assert multi.last_recomputed is False
+    np.testing.assert_array_equal(F4, F2)
+    inst = orc.Instance(O)
+    inst.set_irregular(seed=int(seeds[150]), **kw)
+    ref = [inst.force(tt, *[x[150] for x in _motion(D, B, tt)], G981) for tt in _acc_times(130, dt)]
+    _assert_parity(F2[150], ref[-1], "instance 150 (third shard)")
+    with pytest.raises(hc.HydroError):                      # time going backwards is reported with the shard it came from
+        multi.step(0.0, pose, vel)
+    one.close(); multi.close()
+    for e in parts:
+        e.close()

@@ -234,3 +234,20 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"hc_oracle|libhc_oracle|from oracle|import oracle|orc_", txt):
                     bad.append(os.path.join(dp_, fn))
     assert not bad, bad
+
+
+def test_multi_shard_ranges_and_no_device():
+    """hc_multi_*: contiguous shards that differ by at most one instance (the same rule as shard.shard_range, which
+    the torchrun ranks of bench.py use), and no CPU fallback for the multi-device handle either."""
+    import hydrochrono_b200 as hc
+    from hydrochrono_b200 import shard, synth
+    for total in (7, 16384, 16385):
+        for n in (1, 2, 3, 8):
+            blocks = [hc.multi_shard_range(total, n, i) for i in range(n)]
+            assert blocks == [(lo, hi - lo) for lo, hi in (shard.shard_range(total, n, r) for r in range(n))]
+    if hc.device_count() == 0:
+        T = hc.Tables.from_raw(synth.make_tables(num_bodies=1, rirf_steps=21, rirf_duration=1.0, exc_irf_steps=21,
+                                                 exc_half_window=1.0))
+        with pytest.raises(hc.HydroError) as ei:
+            hc.MultiEnsemble(T, batch=8, devices=[0, 1])
+        assert "no CPU fallback" in str(ei.value)

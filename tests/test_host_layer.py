@@ -147,3 +147,150 @@ def test_iea_sphere_yaml_run_and_results_file(host_build, sphere_h5, tmp_path):
     et = h5io.read_f64(out_h5, "inputs/simulation/waves/irregular/free_surface_time")
     assert f.size == S.size == 40 and eta.size == et.size > 4000      # nf = ceil((1.0 - 0.001) * 40 s)
     assert np.abs(eta).max() > 0.1
+
+
+@pytest.mark.gpu
+def test_wave_kinematics_through_the_class_surface(host_build, sphere_h5, tmp_path):
+    """SURVEY a13: RegularWave / IrregularWaves::GetElevation / GetVelocity / GetAcceleration of the C++ host layer
+    (spectrum fetched from the device ensemble, Airy arithmetic behind hc_wave_kinematics) against the oracle's
+    restatement of /root/reference/src/wave_types.cpp:14-160,301-313,515-550, Wheeler stretching off and on,
+    mean water level 0 and != 0.  Bar: 1e-12 relative."""
+    from oracle import hc_oracle as orc
+    o = tmp_path / "kin.txt"
+    out = subprocess.run([os.path.join(host_build, "test_kinematics"), sphere_h5, str(o)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    O = orc.Tables(common.sphere_raw())
+    reg = orc.Instance(O)
+    reg.set_regular(0.8, 0.9, 0.4)
+    irr = orc.Instance(O)
+    irr.set_irregular(dt=0.05, duration=20.0, ramp=0.0, Hs=2.0, Tp=9.0, fmin=0.02, fmax=0.6, nfreq=60, gamma=3.3, seed=7)
+    cases = {"regular": (reg, False, 0.0), "regular_mwl": (reg, False, 0.3), "irregular": (irr, False, 0.0),
+             "irregular_mwl": (irr, False, -0.2), "irregular_wheeler": (irr, True, 0.0),
+             "irregular_wheeler_mwl": (irr, True, -0.2)}
+    seen = {k: 0 for k in cases}
+    for line in open(o):
+        tag, *vals = line.split()
+        v = np.array([float(x) for x in vals])
+        inst, stretch, mwl = cases[tag]
+        eta, vel, acc = inst.kinematics(v[0:3], v[3], wave_stretching=stretch, mwl=mwl)
+        ref = np.concatenate([[eta], vel, acc])
+        scale = np.abs(ref).max()
+        assert np.all(np.abs(v[4:] - ref) <= 1e-12 * scale), (tag, v, ref)
+        seen[tag] += 1
+    assert all(n == 20 for n in seen.values()), seen
+
+
+@pytest.mark.gpu
+def test_demo_rm3_reg_waves_constrained_two_body(host_build, tmp_path):
+    """BASELINE config 2 / SURVEY f3: RM3 float + spar plate on a prismatic joint between two MOVING bodies with a
+    linear PTO damper (demos/yaml/rm3/rm3_linearPTO.model.yaml: 1.2e6 N s/m), HHT at dt = 0.01, regular waves
+    A = 1.0 m / omega = 2.10 rad/s, through the C++ TestHydro on the GPU
+    (/root/reference/demos/rm3/demo_rm3_reg_waves.cpp:63,97-150).  Every evaluation TestHydro made (time, pose,
+    velocity, gravity -> total 12-DoF force) is replayed through the oracle: per-step force parity at 1e-9 on the
+    same states.  rm3.h5 is stripped from the reference snapshot, so the tables are the synthetic RM3-shaped ones and
+    the trajectory itself is only checked for physical sanity and for the joint holding."""
+    from oracle import hc_oracle as orc
+    raw = synth.rm3_like()
+    h5 = tmp_path / "rm3_like.h5"
+    h5io.write_bemio(h5, raw)
+    o, trace = tmp_path / "rm3_reg_waves.txt", tmp_path / "trace.txt"
+    env = dict(os.environ, HYDROC_STATE_TRACE=str(trace))
+    res = tmp_path / "results.regular.h5"
+    out = subprocess.run([os.path.join(host_build, "demo_rm3_reg_waves"), str(h5), str(o), "12.0", "1200000", str(res)],
+                         capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    a = np.loadtxt(o, skiprows=1)
+    t, zf, zp, xf = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    assert t.size == 1201 and abs(t[-1] - 12.01) < 1e-9
+    words = out.stdout.split()
+    assert int(words[words.index("radiation_calls") + 1]) == t.size + 1     # one evaluation per time value (+ t = 0)
+    assert float(words[words.index("joint_transverse") + 1]) < 1e-10 and float(words[words.index("joint_rel_rot") + 1]) < 1e-12
+    # sanity: both bodies heave at the wave frequency around their equilibrium with a bounded amplitude; the PTO
+    # couples them (the relative heave is smaller than it would be for free bodies is not asserted -- synthetic tables)
+    late = t > 6.0
+    assert 0.01 < np.ptp(zf[late]) < 6.0 and 0.001 < np.ptp(zp[late]) < 6.0
+    assert abs(zf[late].mean() + 0.72) < 1.0 and abs(zp[late].mean() + 21.29) < 1.0 and np.all(np.isfinite(a))
+    # per-step force parity on the same states
+    tr = np.loadtxt(trace)
+    assert tr.shape == (t.size + 1, 1 + 12 + 12 + 3 + 12)
+    O = orc.Tables(raw)
+    inst = orc.Instance(O)
+    inst.set_regular(1.0, 2.10)
+    ref = np.array([inst.force(r[0], r[1:13], r[13:25], r[25:28]) for r in tr])
+    got = tr[:, 28:40]
+    tol = common.force_tol(ref)
+    assert np.all(np.abs(got - ref) <= tol), float((np.abs(got - ref) / tol).max())
+    # results file: joint / TSDA channels of the reference's schema (src/simulation_exporter.cpp:67-69,120-152,303-353)
+    from h5lite import H5Lite
+    H = H5Lite(str(res))
+    assert H.read("inputs/model/joints/names") == ["joint_1"] and H.read("inputs/model/tsdas/names") == ["TSDA_1"]
+    assert H.read("inputs/model/rsdas/names") == []
+    assert h5io.list_group(res, "results/model/tsdas") == ["TSDA_1"] and h5io.list_group(res, "results/model/joints") == ["joint_1"]
+    speed = h5io.read_f64(res, "results/model/tsdas/TSDA_1/speed")
+    damp = h5io.read_f64(res, "results/model/tsdas/TSDA_1/damping_force")
+    fmag = h5io.read_f64(res, "results/model/tsdas/TSDA_1/force_mag")
+    ext = h5io.read_f64(res, "results/model/tsdas/TSDA_1/extension")
+    assert speed.shape == (t.size,) and np.abs(speed).max() > 1e-3
+    np.testing.assert_array_equal(damp, 1200000.0 * speed)
+    np.testing.assert_allclose(fmag, damp, rtol=1e-9, atol=1e-3)      # no spring: the PTO force is the damper's (Chrono's sign)
+    zf_h5 = h5io.read_f64(res, "results/model/bodies/body1/position")[:, 2]
+    zp_h5 = h5io.read_f64(res, "results/model/bodies/body2/position")[:, 2]
+    np.testing.assert_allclose(ext, (zf_h5 - zp_h5) - (21.29 - 0.72), atol=1e-6)   # pitch stays small
+    f1 = h5io.read_f64(res, "results/model/joints/joint_1/reaction1_force")
+    f2 = h5io.read_f64(res, "results/model/joints/joint_1/reaction2_force")
+    assert f1.shape == (t.size, 3) and np.abs(f1[:, 0]).max() > 1e3           # the joint carries the float's surge load
+    np.testing.assert_array_equal(f2, -f1)
+    q = h5io.read_f64(res, "results/model/bodies/body2/orientation")         # wxyz; joint axis = the spar's z axis
+    axis = np.stack([2 * (q[:, 1] * q[:, 3] + q[:, 0] * q[:, 2]), 2 * (q[:, 2] * q[:, 3] - q[:, 0] * q[:, 1]),
+                     1 - 2 * (q[:, 1] ** 2 + q[:, 2] ** 2)], axis=1)
+    along = np.abs((f1 * axis).sum(axis=1))
+    assert along.max() <= 1e-6 * np.abs(f1).max()                             # a prismatic joint transmits nothing along its axis
+    # the joint makes the 12 DoF truly coupled: both bodies carry the same angular velocity in every evaluation
+    np.testing.assert_allclose(tr[:, 13 + 3:13 + 6], tr[:, 13 + 9:13 + 12], rtol=0, atol=1e-14)
+    assert np.abs(tr[:, 13 + 4]).max() > 1e-6                               # ... and it is not trivially zero (pitch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stepper_name,wave", [("euler", "regular"), ("hht", "irregular")])
+def test_yaml_period_sweep_maps_onto_ensemble_instances(host_build, sphere_h5, tmp_path, stepper_name, wave):
+    """waves.period.values / linspace (parsed by the reference, /root/reference/src/hydro_yaml_parser.cpp:441-524,
+    but never consumed) become the instances of ONE batched device ensemble (SetupHydroSweepFromYAML + TestHydroEnsemble):
+    every instance must reproduce the single-system TestHydro run of its sweep point, the batch takes one device
+    evaluation per time value, and (regular waves, Euler) the heave of every instance matches the oracle stepped with
+    the reference's integrator."""
+    from oracle import hc_oracle as orc
+    import stepper
+    y = tmp_path / "sweep.hydro.yaml"
+    if wave == "regular":
+        y.write_text("hydrodynamics:\n  bodies:\n    - name: body1\n      h5_file: %s\n  waves:\n    type: regular\n"
+                     "    height: 0.5\n    period:\n      values: [3.0, 4.4, 6.0]\n" % sphere_h5)
+        seeds = 1
+    else:
+        y.write_text("hydrodynamics:\n  bodies:\n    - name: body1\n      h5_file: %s\n  waves:\n    type: irregular\n"
+                     "    height: 1.5\n    seed: 4\n    period:\n      linspace: { start: 8.0, stop: 12.0, num: 3 }\n" % sphere_h5)
+        seeds = 2
+    o = tmp_path / "sweep.txt"
+    duration = 12.0
+    out = subprocess.run([os.path.join(host_build, "demo_sweep_yaml"), str(y), str(o), stepper_name, str(duration), str(seeds)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    words = out.stdout.split()
+    B, nsteps = 3 * seeds, int(round(duration / 0.015))
+    assert int(words[words.index("instances") + 1]) == B and int(words[words.index("steps") + 1]) == nsteps
+    # one batched evaluation per time value: Euler evaluates at t_0 .. t_{n-1}; HHT at t_0 (initial accelerations) + t_1 .. t_n
+    assert int(words[words.index("device_evaluations") + 1]) == nsteps + (1 if stepper_name == "hht" else 0)
+    assert float(words[words.index("max_abs_diff_vs_single_runs") + 1]) <= 1e-12
+    a = np.loadtxt(o)
+    assert a.shape == (nsteps, 1 + B)
+    assert np.abs(a[:, 1:] + 2.0).max() < 1.5 and np.ptp(a[:, 1]) > 1e-3
+    # the instances differ (different periods / seeds)
+    assert np.abs(a[:, 1] - a[:, 2]).max() > 1e-4 and np.abs(a[:, 1] - a[:, -1]).max() > 1e-4
+    if wave == "regular":
+        O = orc.Tables(common.sphere_raw())
+        for k, T in enumerate([3.0, 4.4, 6.0]):
+            inst = orc.Instance(O)
+            inst.set_regular(0.25, 2.0 * np.pi / T)
+            free = np.zeros(6, bool); free[2] = True
+            _, x = stepper.run(lambda t_, x_, v_: inst.force(t_, x_, v_), O.added_mass(), [common.SPHERE_MASS], [[1.0, 1.0, 1.0]],
+                               [0, 0, -2.0, 0, 0, 0], 0.015, nsteps, free=free)
+            assert np.abs(x[:, 2] - a[:, 1 + k]).max() < 1e-8, (k, np.abs(x[:, 2] - a[:, 1 + k]).max())
