@@ -32,6 +32,7 @@ struct H5File {
         for (int i = n - 1; i >= 0; --i) v = (v << 8) | buf[off + i];
         return v;
     }
+    uint8_t byte(uint64_t off) const { need(off, 1); return buf[off]; }   // every file-controlled offset is checked
 
     explicit H5File(const char* p) : path(p) {
         FILE* f = std::fopen(p, "rb");
@@ -59,11 +60,17 @@ struct H5File {
         std::vector<std::pair<uint64_t, uint64_t>> blocks{{hdr + 16, u(hdr + 8, 4)}};
         std::vector<Msg> out;
         for (size_t bi = 0; bi < blocks.size() && out.size() < count; ++bi) {
+            if (bi > 64) bad("too many object-header continuation blocks");
             uint64_t p = blocks[bi].first;
+            need(p, blocks[bi].second);                            // the whole block lies inside the file
             const uint64_t end = p + blocks[bi].second;
             while (p + 8 <= end && out.size() < count) {
                 Msg m{uint16_t(u(p, 2)), p + 8, uint16_t(u(p + 2, 2))};
-                if (m.type == 0x10) blocks.push_back({u(m.off, 8), u(m.off + 8, 8)});
+                if (m.off + m.size > end) bad("object-header message runs past its block");
+                if (m.type == 0x10) {
+                    if (m.size < 16) bad("short continuation message");
+                    blocks.push_back({u(m.off, 8), u(m.off + 8, 8)});
+                }
                 out.push_back(m);
                 p = m.off + m.size;
             }
@@ -71,14 +78,18 @@ struct H5File {
         return out;
     }
 
-    void collect(uint64_t node, uint64_t heap_data, std::map<std::string, uint64_t>& out) const {
+    void collect(uint64_t node, uint64_t heap_data, std::map<std::string, uint64_t>& out, int depth = 0) const {
+        if (depth > 32) bad("group B-tree too deep (cyclic node?)");
         need(node, 24);
         if (std::memcmp(&buf[node], "TREE", 4) == 0) {
+            const unsigned level = byte(node + 5);
+            if (int(level) + depth > 32) bad("group B-tree too deep (cyclic node?)");
             const unsigned used = unsigned(u(node + 6, 2));
             uint64_t p = node + 24;
             for (unsigned i = 0; i < used; ++i, p += 16) {
                 const uint64_t child = u(p + 8, 8);
-                collect(child, heap_data, out);   // level > 0: another TREE node; level 0: a SNOD
+                if (child == node) bad("self-referencing group B-tree node");
+                collect(child, heap_data, out, depth + 1);   // level > 0: another TREE node; level 0: a SNOD
             }
         } else if (std::memcmp(&buf[node], "SNOD", 4) == 0) {
             const unsigned n = unsigned(u(node + 6, 2));
@@ -135,17 +146,18 @@ struct H5File {
         bool have_space = false, have_layout = false;
         for (const Msg& m : messages(resolve(p))) {
             if (m.type == 0x01) {
-                const int ver = buf[m.off], rank = buf[m.off + 1];
+                const int ver = byte(m.off), rank = byte(m.off + 1);
+                if (rank > 32) bad("dataspace rank out of range");
                 uint64_t q = m.off + (ver == 1 ? 8 : 4);
                 for (int r = 0; r < rank; ++r) d.dims.push_back(u(q + 8 * r, 8));
                 have_space = true;
             } else if (m.type == 0x03) {
-                d.type_class = buf[m.off] & 0x0f;
+                d.type_class = byte(m.off) & 0x0f;
                 d.type_size = unsigned(u(m.off + 4, 4));
-                if (d.type_class == 1 && (buf[m.off + 1] & 1)) bad("big-endian floats unsupported");
+                if (d.type_class == 1 && (byte(m.off + 1) & 1)) bad("big-endian floats unsupported");
             } else if (m.type == 0x08) {
-                if (buf[m.off] != 3) bad("unsupported data layout version");
-                const int cls = buf[m.off + 1];
+                if (byte(m.off) != 3) bad("unsupported data layout version");
+                const int cls = byte(m.off + 1);
                 if (cls == 1) { d.data_off = u(m.off + 2, 8); d.data_size = u(m.off + 10, 8); }
                 else if (cls == 0) { d.data_size = u(m.off + 2, 2); d.data_off = m.off + 4; }
                 else bad("chunked datasets unsupported");
@@ -164,7 +176,10 @@ struct H5File {
         Dataset d = dataset(p);
         if (d.type_class != 1 || (d.type_size != 8 && d.type_size != 4)) bad("'" + p + "' is not a float dataset");
         uint64_t n = 1;
-        for (uint64_t x : d.dims) n *= x;
+        for (uint64_t x : d.dims) {                                 // checked multiply: dims come from the file
+            if (x != 0 && n > (uint64_t(1) << 40) / x) bad("dataset '" + p + "' dimensions overflow");
+            n *= x;
+        }
         if (n * d.type_size > d.data_size) bad("dataset '" + p + "' storage too small");
         dvec out(n);
         for (uint64_t i = 0; i < n; ++i) {

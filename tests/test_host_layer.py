@@ -232,7 +232,7 @@ def test_demo_rm3_reg_waves_constrained_two_body(host_build, tmp_path):
     ext = h5io.read_f64(res, "results/model/tsdas/TSDA_1/extension")
     assert speed.shape == (t.size,) and np.abs(speed).max() > 1e-3
     np.testing.assert_array_equal(damp, 1200000.0 * speed)
-    np.testing.assert_allclose(fmag, damp, rtol=1e-9, atol=1e-3)      # no spring: the PTO force is the damper's (Chrono's sign)
+    np.testing.assert_allclose(fmag, -damp, rtol=1e-9, atol=1e-3)     # no spring: ChLinkTSDA::GetForce = -(k ext + c d(len)/dt)
     zf_h5 = h5io.read_f64(res, "results/model/bodies/body1/position")[:, 2]
     zp_h5 = h5io.read_f64(res, "results/model/bodies/body2/position")[:, 2]
     np.testing.assert_allclose(ext, (zf_h5 - zp_h5) - (21.29 - 0.72), atol=1e-6)   # pitch stays small
