@@ -383,9 +383,14 @@ class Leg:
         synth = load_plain("synth")
         amp, om = synth.prescribed_motion(DOFS)
         self.pose_np, self.vel_np = motion_buffers(amp, om, batch, offset)
-        self.h_pose = [torch.from_numpy(self.pose_np[i]).pin_memory() for i in range(NBUF)]
-        self.h_vel = [torch.from_numpy(self.vel_np[i]).pin_memory() for i in range(NBUF)]
+        # pinned host state, [vel, pose] of a step adjacent in memory (hc_step then uploads them in one copy)
+        self.h_state = [torch.from_numpy(np.stack([self.vel_np[i], self.pose_np[i]])).pin_memory() for i in range(NBUF)]
+        self.h_vel = [x[0] for x in self.h_state]
+        self.h_pose = [x[1] for x in self.h_state]
         self.h_force = torch.empty((batch, DOFS), dtype=torch.float64).pin_memory()
+        self.h_pose_np = [x.numpy() for x in self.h_pose]      # views of the pinned buffers, made once
+        self.h_vel_np = [x.numpy() for x in self.h_vel]
+        self.h_force_np = self.h_force.numpy()
         self.d_pose = [x.to(dev) for x in self.h_pose]
         self.d_vel = [x.to(dev) for x in self.h_vel]
         self.d_force = torch.empty((batch, DOFS), dtype=torch.float64, device=dev)
@@ -400,8 +405,7 @@ class Leg:
 
     def host_step(self):
         n = self.n
-        self.ens.step(self.times[n], self.h_pose[n % NBUF].numpy(), self.h_vel[n % NBUF].numpy(), GVEC,
-                      out=self.h_force.numpy())
+        self.ens.step(self.times[n], self.h_pose_np[n % NBUF], self.h_vel_np[n % NBUF], GVEC, out=self.h_force_np)
         self.n = n + 1
 
     def align(self, multiple=8):

@@ -297,6 +297,9 @@ class Ensemble:
         self.batch = batch
         self.dofs = tables.dofs
         self.device = device
+        self._gcache = {}
+        self._re_val = C.c_int()
+        self._re = C.byref(self._re_val)
 
     # -- waves ---------------------------------------------------------------
     def set_waves_none(self):
@@ -355,15 +358,28 @@ class Ensemble:
 
     def step(self, t, pose, vel, gvec=(0.0, 0.0, -9.81), out=None):
         """Host-buffer step: returns force [B][6N] (numpy)."""
-        pose, vel, g = _f64(pose), _f64(vel), _f64(gvec)
+        pose, vel = _f64(pose), _f64(vel)
+        g = self._gvec(gvec)
         if pose.size != self.batch * self.dofs or vel.size != pose.size:
             raise ValueError("pose/vel must be [B][6N]")
         if out is None:
             out = np.empty((self.batch, self.dofs))
-        re = C.c_int()
-        _check(lib.hc_step(self._h, float(t), _ptr(pose), _ptr(vel), _dp(g), _ptr(out), C.byref(re)))
-        self.last_recomputed = bool(re.value)
+        re = self._re
+        _check(lib.hc_step(self._h, t, pose.ctypes.data, vel.ctypes.data, g, out.ctypes.data, re))
+        self.last_recomputed = bool(self._re_val.value)
         return out
+
+    def _gvec(self, gvec):
+        """ctypes pointer to the gravity vector; tuples are converted once (a step is tens of microseconds)."""
+        if isinstance(gvec, tuple):
+            hit = self._gcache.get(gvec)
+            if hit is None:
+                arr = _f64(gvec)
+                hit = self._gcache[gvec] = (arr, _dp(arr))
+            return hit[1]
+        arr = _f64(gvec)
+        self._gtmp = arr
+        return _dp(arr)
 
     def step_device(self, t, d_pose, d_vel, d_force, gvec=(0.0, 0.0, -9.81)):
         """Device-pointer step (torch CUDA tensors or raw addresses); asynchronous on the ensemble stream."""

@@ -152,8 +152,23 @@ struct hc_ensemble {
     long long tr_n = 0;              // what the captured graph of each phase contains
 
     // step I/O
-    DevBuf<StepHeader> d_hdr;
-    DevBuf<double> d_pose, d_vel, d_force, d_comp, d_wave_tmp;
+    // the step's inputs live in ONE device block [header (256 B) | vel [B][D] | pose [B][D]] so that a small ensemble can
+    // receive all of them in a single copy (compact host path, below)
+    DevBuf<unsigned char> d_stage;
+    struct Ptr { StepHeader* p = nullptr; } d_hdr;
+    struct DPtr { double* p = nullptr; } d_pose, d_vel;
+    DevBuf<double> d_force, d_comp, d_wave_tmp;
+    // compact host path (hc_step on a small ensemble served by the per-step kernels -- the drop-in B = 1 case): inputs
+    // staged in one pinned block, ONE captured graph per step = H2D of the block + every kernel of the step + D2H of
+    // the forces; one driver call + one synchronise instead of nine calls
+    PinBuf h_stage;
+    size_t stage_bytes = 0;
+    bool compact_ok = false, defer_launch = false;
+    cudaGraph_t graph_c = nullptr;
+    cudaGraphExec_t graph_c_exec = nullptr;
+    int graph_c_key = -1;
+    void run_compact();
+
     PinBuf h_pose, h_vel, h_force;
 
     // waves
@@ -246,6 +261,9 @@ struct hc_ensemble {
         if (graph1) cudaGraphDestroy(graph1);
         graph_exec = nullptr; graph = nullptr; graph_valid = false;
         graph1_exec = nullptr; graph1 = nullptr; graph1_valid = false;
+        if (graph_c_exec) cudaGraphExecDestroy(graph_c_exec);
+        if (graph_c) cudaGraphDestroy(graph_c);
+        graph_c_exec = nullptr; graph_c = nullptr; graph_c_key = -1;
     }
     void use_device() const { CUDA_CHECK(cudaSetDevice(dev)); }
 
@@ -809,6 +827,9 @@ void hc_ensemble::begin_step(double t, const double* g, const double* d_pose_in,
         la_blk[0].valid = la_blk[1].valid = false;
         last_step_fast = false;
         if (inputs_on_copy_stream) CUDA_CHECK(cudaStreamWaitEvent(stream, ev_inputs, 0));
+        if (defer_launch)       // compact host path: the state is still in the pinned staging block
+            CUDA_CHECK(cudaMemcpyAsync(d_stage.p + 256, static_cast<unsigned char*>(h_stage.p) + 256, stage_bytes - 256,
+                                       cudaMemcpyHostToDevice, stream));
         CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
         PrestepArgs pa{};
         pa.hdr = d_hdr.p; pa.hist = d_hist.p; pa.times = d_times.p; pa.B = B; pa.Bp = Bp; pa.D = D; pa.L = L;
@@ -830,10 +851,12 @@ void hc_ensemble::begin_step(double t, const double* g, const double* d_pose_in,
     // k_step takes the header by value; every other kernel of a step reads it from d_hdr.  Pageable source: the runtime
     // stages small copies at call time, so hdr_h can be rewritten by the next step at once.
     hdr_on_device = !(rb_use && !per_step_exc) || profiling;
-    if (hdr_on_device) CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
     last_step_fast = rb_use && !per_step_exc && !profiling;
+    phase1_launches = last_step_fast ? 0 : (rb_use ? 0 : 1) + ((rb_use && !per_step_exc) ? 0 : 1) + (per_step_exc ? int(groups.size()) : 0);
+    if (defer_launch && !rb_use) return;                        // compact host path: header + both phases go in one graph
+    defer_launch = false;
+    if (hdr_on_device) CUDA_CHECK(cudaMemcpyAsync(d_hdr.p, &hh, sizeof(StepHeader), cudaMemcpyHostToDevice, stream));
     if (last_step_fast) return;                                 // phase 1 is empty
-    phase1_launches = (rb_use ? 0 : 1) + ((rb_use && !per_step_exc) ? 0 : 1) + (per_step_exc ? int(groups.size()) : 0);
     launch_phase(1);
 }
 
@@ -869,7 +892,10 @@ void hc_ensemble::setup_lookahead() {
     if (!la_stream) {
         int lo = 0, hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority
-        CUDA_CHECK(cudaStreamCreateWithPriority(&la_stream, cudaStreamNonBlocking, lo));
+        // below the per-step kernels; above the radiation pass when that pass is not held back by the steps (ungated
+        // slices / whole pass), because the steps need the excitation block sooner (8 steps) than the radiation block
+        const int rpm = opts.rad_pass_mode >= 1 && opts.rad_pass_mode <= 3 ? opts.rad_pass_mode : 1;
+        CUDA_CHECK(cudaStreamCreateWithPriority(&la_stream, cudaStreamNonBlocking, rpm == 1 ? lo : (lo + hi) / 2));
         for (auto& x : ev_la_done) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         for (auto& x : ev_la_free) CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_la_build, cudaEventDisableTiming));
@@ -989,6 +1015,33 @@ int hc_ensemble::lookahead_slot(double t) {
     return la_cur * kLaT + la_pos++;
 }
 
+// Compact host path: the staged inputs (header, velocities, pose: one pinned block) go up in ONE copy, every kernel of
+// the step runs, the forces come back into the pinned force buffer -- all nodes of one captured graph.
+void hc_ensemble::run_compact() {
+    const int key = (phase_uses_lookahead ? 1 : 0) | (skip_radiation ? 4 : 0);
+    if (!graph_c_exec || graph_c_key != key) {
+        if (graph_c_exec) cudaGraphExecDestroy(graph_c_exec);
+        if (graph_c) cudaGraphDestroy(graph_c);
+        graph_c_exec = nullptr; graph_c = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            CUDA_CHECK(cudaMemcpyAsync(d_stage.p, h_stage.p, stage_bytes, cudaMemcpyHostToDevice, stream));
+            enqueue_phase(1, false);
+            enqueue_phase(2, false);
+            CUDA_CHECK(cudaMemcpyAsync(h_force.p, d_force.p, size_t(B) * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        } catch (...) {
+            cudaGraph_t tmp = nullptr;
+            cudaStreamEndCapture(stream, &tmp);
+            if (tmp) cudaGraphDestroy(tmp);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(stream, &graph_c));
+        CUDA_CHECK(cudaGraphInstantiate(&graph_c_exec, graph_c, 0));
+        graph_c_key = key;
+    }
+    CUDA_CHECK(cudaGraphLaunch(graph_c_exec, stream));
+}
+
 void hc_ensemble::finish_step(double t) {
     launch_phase(2);
     if (rb_use && rb_pass_mode != 3) rb_launch_slices(1, true);    // this step's share of the next block's pass
@@ -1087,9 +1140,16 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     e->d_pr_new.alloc(L); e->d_pr_old.alloc(L); e->d_pr_wn.alloc(L); e->d_pr_wo.alloc(L); e->d_pr_wd.alloc(L);
     e->d_pr_head.alloc(L); e->d_pr_lead.alloc(L);
     e->setup_radiation_chunks();
-    e->d_hdr.alloc(1);
     const size_t bd = size_t(e->B) * D;
-    e->d_pose.alloc(bd); e->d_vel.alloc(bd); e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
+    e->stage_bytes = 256 + 2 * bd * sizeof(double);
+    e->d_stage.alloc(e->stage_bytes);
+    e->d_hdr.p = reinterpret_cast<StepHeader*>(e->d_stage.p);
+    e->d_vel.p = reinterpret_cast<double*>(e->d_stage.p + 256);
+    e->d_pose.p = e->d_vel.p + bd;
+    static_assert(sizeof(StepHeader) <= 256, "step header must fit its slot of the staging block");
+    e->compact_ok = e->stage_bytes <= 64 * 1024 && opts->use_graph;
+    if (e->compact_ok) e->h_stage.alloc(e->stage_bytes);
+    e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
     CUDA_CHECK(cudaDeviceSynchronize());
     *out = e.release();
@@ -1441,7 +1501,44 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
     int re = 0;
     const bool tr = e->trace && t != e->prev_time;
     const auto h0 = std::chrono::steady_clock::now();
+    bool compact_done = false;
     if (t != e->prev_time) {
+        e->host_stepping = true;
+        const bool try_compact = e->compact_ok && !e->profiling && !tr && e->opts.use_graph;
+        if (try_compact) {
+            // small ensemble (the drop-in B = 1 case): stage the inputs in the pinned block; if the per-step kernels serve
+            // this step the whole step is ONE graph launch
+            unsigned char* hs = static_cast<unsigned char*>(e->h_stage.p);
+            std::memcpy(hs + 256, vel, bytes);
+            std::memcpy(hs + 256 + bytes, pose, bytes);
+            e->defer_launch = true;
+            e->inputs_on_copy_stream = false;
+            bool began = false;
+            try {
+                e->begin_step(t, g, e->d_pose.p, e->d_vel.p, e->d_force.p);
+                began = true;
+            } catch (...) {
+                e->defer_launch = false;
+                cudaStreamSynchronize(e->stream);
+                throw;
+            }
+            if (began && e->defer_launch) {              // per-step kernels: one graph
+                e->defer_launch = false;
+                std::memcpy(hs, &e->hdr_h, sizeof(StepHeader));
+                e->run_compact();
+                e->prof.kernel_launches += e->phase1_launches + 2;
+                e->prof.hydrostatics_calls++; e->prof.radiation_calls++; e->prof.waves_calls++;
+                e->prev_time = t;
+                e->force_valid = true;
+                CUDA_CHECK(cudaStreamSynchronize(e->stream));
+                std::memcpy(force, e->h_force.p, bytes);
+                compact_done = true;
+            } else {                                     // a look-ahead block serves the step: upload, then as usual
+                CUDA_CHECK(cudaMemcpyAsync(e->d_stage.p + 256, hs + 256, 2 * bytes, cudaMemcpyHostToDevice, e->stream));
+                e->finish_step(t);
+            }
+            re = 1;
+        } else {
         // State upload.  A step served by both look-aheads has nothing to run before its state arrives (phase 1 is
         // empty): everything goes down the main stream, no cross-stream events.  Otherwise the upload runs on the copy
         // stream underneath the state-independent phase 1 (plans, per-step convolutions).  Which of the two this step
@@ -1454,7 +1551,10 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
         if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[1], cs));
         if (on_copy) CUDA_CHECK(cudaEventRecord(e->ev_inputs, e->copy_stream));
         e->inputs_on_copy_stream = on_copy;
-        e->host_stepping = true;
+        // (Measured and not kept, 2048 instances per GPU: k_step reading the state straight from pinned host memory
+        //  -- SM-issued PCIe reads of 0.4 MB take ~50 us against 11 us for the copy engine; k_step writing the totals
+        //  straight into a pinned result buffer, and one merged upload of adjacent arrays -- no gain, 65.7 vs 65.2 us per
+        //  step: the chain is k_step's own ~26 us latency plus host wake-up, not the copies.)
         try {
             e->begin_step(t, g, e->d_pose.p, e->d_vel.p, e->d_force.p);
         } catch (...) {
@@ -1467,11 +1567,14 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
         if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[2], e->stream));
         e->finish_step(t);
         re = 1;
+        }
     }
-    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[3], e->stream));
-    CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));
-    if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[4], e->stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (!compact_done) {
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[3], e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(force, e->d_force.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (tr) CUDA_CHECK(cudaEventRecord(e->ev_tr[4], e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
     if (tr) {
         float a = 0, b = 0, c = 0, d = 0, f = 0;
         cudaEventElapsedTime(&a, e->ev_tr[0], e->ev_tr[1]);

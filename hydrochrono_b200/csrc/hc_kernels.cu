@@ -628,9 +628,9 @@ __global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadB
 // then hydrostatics, waves and the total as k_finalize).  One CTA = 32 instances x D DoF; thread (b, d).
 constexpr int kRsInst = 32;
 struct FinalizeArgs;
-__device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                                             const StepHeader& h, const int d, const int b, const bool have_fr,
-                                             const double fr_block);
+__device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                                               const StepHeader& h, const int d, const int b, const bool have_fr,
+                                               const double fr_block, const double* pose6);
 
 template <int D>
 __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
@@ -640,6 +640,7 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
     constexpr int LAGS = (D <= 12) ? 8 : 4;          // young lags staged per pass
     __shared__ double s_K[LAGS * D * D];             // (K w)[lag][col][row]
     __shared__ double s_v[LAGS][D][kRsInst];         // young rows, [lag][col][instance]
+    __shared__ double s_io[kRsInst][D];              // the CTA's tile of pose (in), then of the totals (out)
     const int j = h.rb_j;
     const int nl = min(min(h.rb_jj / a.m, h.rb_smax), a.L - 1) + 1;   // young lags 0 .. nl - 1
     const int tid = threadIdx.x;
@@ -647,7 +648,13 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
     const int b0 = blockIdx.x * kRsInst;
     const int b = b0 + bl;
     const size_t row_stride = (size_t)D * a.Bp;
-    // Everything this thread will read later (row-chunk partials, look-ahead wave-force segments, the instance's pose)
+    // the CTA's [32][D] tile of pose is contiguous: one coalesced read (the buffer may be pinned HOST memory that the
+    // kernel reads across PCIe -- hc_step's zero-copy path for small ensembles -- so every value is fetched once)
+    {
+        const int lb = tid / D, c = tid - lb * D;
+        s_io[lb][c] = (b0 + lb < a.B) ? h.pose[(size_t)(b0 + lb) * D + c] : 0.0;
+    }
+    // Everything this thread will read later (row-chunk partials, look-ahead wave-force segments)
     // is requested from DRAM now, so that the dependent sums below find it in L2: one DRAM round trip instead of ~10.
     {
         const double* p = a.partial[h.rb_buf] + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
@@ -657,7 +664,6 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
             const double* e = fa.exc_cache + (((size_t)buf * fa.exc_S * kLaT + pos) * D + d) * a.Bp + b;
             for (int sg = 0; sg < fa.exc_S; ++sg) prefetch_l2(e + (size_t)sg * kLaT * D * a.Bp);
         }
-        if (b < a.B && d % 6 == 0) prefetch_l2(h.pose + (size_t)b * D + d);
     }
     // fixed-order sum of the row-chunk partials of block step j
     double fr = 0.0;
@@ -705,7 +711,15 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
             fr = __dadd_rn(fr, acc);
         }
     }
-    if (b < a.B) finalize_one(fa, hs, eg, h, d, b, true, fr);
+    // (the loop above ran at least once, so s_io is visible to every thread)
+    const double total = (b < a.B) ? finalize_one(fa, hs, eg, h, d, b, true, fr, &s_io[bl][6 * (d / 6)]) : 0.0;
+    if (h.force2) {      // second copy of the totals (the caller's buffer, possibly pinned host memory): coalesced tile
+        __syncthreads();
+        s_io[bl][d] = total;
+        __syncthreads();
+        const int lb = tid / D, c = tid - lb * D;
+        if (b0 + lb < a.B) h.force2[(size_t)(b0 + lb) * D + c] = s_io[lb][c];
+    }
 }
 
 template <int D>
@@ -1128,9 +1142,10 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
 // ------------------------------------------------------------------------------------------
 
 // Force of (dof d, instance b).  fr_block: the radiation force when the caller already holds it (k_step).
-__device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
-                                             const StepHeader& h, const int d, const int b, const bool have_fr,
-                                             const double fr_block) {
+// Returns the total; writes it to h.force (and the components to a.comp).  pose6: the 6 pose values of (b, body).
+__device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
+                                               const StepHeader& h, const int d, const int b, const bool have_fr,
+                                               const double fr_block, const double* pose6) {
     const int D = a.D;
     const int body = d / 6, i = d - 6 * body;
     const double gx = h.g[0], gy = h.g[1], gz = h.g[2];
@@ -1140,7 +1155,7 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
     const double rho_g = __dmul_rn(hs.rho, glen);
     double fh = 0.0;
     if (!a.waves_only) {
-    const double* pose = h.pose + (size_t)b * D + 6 * body;
+    const double* pose = pose6;
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 6; ++j)
@@ -1221,16 +1236,16 @@ __device__ __forceinline__ void finalize_one(const FinalizeArgs& a, const Hydros
         }
     }
     const size_t o = (size_t)b * D + d;
-    if (a.waves_only) { h.force[o] = fw; return; }
+    if (a.waves_only) { h.force[o] = fw; return fw; }
     const double total = __dadd_rn(__dsub_rn(fh, fr), fw);           // hs - rad + waves (:758-760)
     h.force[o] = total;
-    if (h.force2) h.force2[o] = total;
     if (a.comp) {
         const size_t BD = (size_t)a.B * D;
         a.comp[o] = fh;
         a.comp[BD + o] = fr;
         a.comp[2 * BD + o] = fw;
     }
+    return total;
 }
 
 __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
@@ -1241,7 +1256,9 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const __
     const int b = tid - d * a.Bp;
     if (d >= a.D || b >= a.B) return;
     const StepHeader h = *a.hdr;
-    finalize_one(a, hs, eg, h, d, b, false, 0.0);
+    const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
+                                      a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6));
+    if (h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -235,7 +235,7 @@ HC_API hc_status hc_waves_regular_coeffs(const hc_ensemble* e, int instance, dou
  * force [B][6N]: total = hydrostatic - radiation + waves
  * Calling twice with the same t returns the cached forces (status HC_OK, *recomputed = 0), like the reference's
  * time-keyed cache; a new t appends (t, vel) to the history and recomputes.
- * Host-pointer version: H2D, kernels, D2H, synchronous at return. */
+ * Host-pointer version: H2D, kernels, D2H, synchronous at return.  Pinned buffers are recommended. */
 HC_API hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* vel, const double g_vec[3],
                          double* force, int* recomputed /* may be NULL */);
 /* Device-pointer version: pointers are device memory on the ensemble's device; asynchronous on the

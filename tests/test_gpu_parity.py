@@ -846,3 +846,42 @@ def test_multi_device_handle_matches_single_ensemble(rm3):
     one.close(); multi.close()
     for e in parts:
         e.close()
+
+
+@pytest.mark.gpu
+def test_pinned_and_pageable_host_buffers_agree(rm3):
+    """hc_step on a modest ensemble served by the look-aheads (the 2048-per-GPU split of the north star) with pinned
+    host buffers and with pageable arrays: bit-identical results, both matching the oracle."""
+    import torch
+    T, O = rm3
+    B, D, dt = 1024, 12, 0.01
+    opts = dict(dt_hint=dt, bracket_snap=1e-8, rad_lookahead=2, exc_lookahead=4)
+    kw = dict(dt=dt, duration=4.0, ramp=1.0, Hs=2.5, Tp=8.0, nfreq=24, gamma=3.3)
+    seeds = np.arange(1, B + 1, dtype=np.int32)
+    a = hc.Ensemble(T, batch=B, **opts)
+    b = hc.Ensemble(T, batch=B, **opts)
+    a.set_waves_irregular(seeds=seeds, **kw)
+    b.set_waves_irregular(seeds=seeds, **kw)
+    st = torch.empty((2, B, D), dtype=torch.float64).pin_memory()         # [vel, pose] adjacent: one upload
+    hv, hp = st[0], st[1]
+    hf = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    check = [0, 31, 32, 500, B - 1]
+    insts = []
+    for k in check:
+        i = orc.Instance(O)
+        i.set_irregular(seed=int(seeds[k]), share_irf_from=insts[0] if insts else None, **kw)
+        insts.append(i)
+    got, want = [], []
+    for t in _acc_times(150, dt):
+        pose, vel = _motion(D, B, t)
+        hp.copy_(torch.from_numpy(pose)); hv.copy_(torch.from_numpy(vel))
+        Fa = a.step(t, hp.numpy(), hv.numpy(), G981, out=hf.numpy())       # pinned in, pinned out
+        Fb = b.step(t, pose.copy(), vel.copy(), G981)                      # pageable
+        np.testing.assert_array_equal(Fa, Fb)
+        got.append(Fa[check].copy())
+        want.append(np.array([i.force(t, pose[k], vel[k], G981) for k, i in zip(check, insts)]))
+    assert a.rad_block_stats(reset=False)["steps_served"] >= 148
+    for x, y in zip(a.components(), b.components()):
+        np.testing.assert_array_equal(x, y)
+    _assert_parity(np.array(got), np.array(want), "pinned host buffers")
+    a.close(); b.close()
