@@ -188,6 +188,7 @@ struct hc_ensemble {
         DevBuf<int> la_idx;
         DevBuf<double> la_w1, la_w2, la_taps;
         int la_rows_cap = 0;
+        int la_row0 = 0, la_nrows = 0;    // eta rows of the block being built (second half of a split build)
     };
     std::vector<std::unique_ptr<Group>> groups;
     int exc_chunk = 0, exc_total_chunks = 0, exc_ndmax = 0;
@@ -285,7 +286,9 @@ struct hc_ensemble {
     void begin_step(double t, const double* g, const double* d_pose_in, const double* d_vel_in, double* d_force_out);
     void setup_lookahead();
     int lookahead_slot(double t);
-    int enqueue_lookahead_block(int buf, double t0, cudaStream_t st);
+    int enqueue_lookahead_block(int buf, double t0, cudaStream_t st, int part = -1);
+    void finish_split_build();
+    int la_half_pending = -1;         // buffer whose block still lacks the second half of its segments
     void prefetch_lookahead(int buf);
     void finish_step(double t);
     void collect_events();
@@ -824,7 +827,7 @@ void hc_ensemble::begin_step(double t, const double* g, const double* d_pose_in,
         // has pushed the step's sample and after prev_time was set (hydro_forces.cpp:747-756): the history keeps the
         // sample, the force cache of this time holds the zeros it was reset to, and the caller sees the exception.
         rb_invalidate();
-        la_blk[0].valid = la_blk[1].valid = false;
+        la_blk[0].valid = la_blk[1].valid = false; la_half_pending = -1;
         last_step_fast = false;
         if (inputs_on_copy_stream) CUDA_CHECK(cudaStreamWaitEvent(stream, ev_inputs, 0));
         if (defer_launch)       // compact host path: the state is still in the pinned staging block
@@ -863,7 +866,7 @@ void hc_ensemble::begin_step(double t, const double* g, const double* d_pose_in,
 // ---- excitation look-ahead ---------------------------------------------------------------------
 void hc_ensemble::setup_lookahead() {
     la_enabled = false; la_pos = 0; la_cur = 0; la_builds = 0; la_hits_this_block = 0; la_poor_blocks = 0;
-    la_blk[0].valid = la_blk[1].valid = false;
+    la_blk[0].valid = la_blk[1].valid = false; la_half_pending = -1;
     if (la_stream) CUDA_CHECK(cudaStreamSynchronize(la_stream));
     if (wave_mode != 2 || n_eta == 0) return;
     const int want = opts.exc_lookahead;
@@ -915,8 +918,25 @@ void hc_ensemble::setup_lookahead() {
 // Builds the block of wave forces for the predicted times t0, t0+dt, ... into cache buffer `buf` on stream `st`.
 // Returns the number of valid block times (0: t0 is outside the eta window).  The per-group scratch (brackets,
 // taps) is shared by all builds, which are therefore chained through ev_la_build.
-int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
+// part = -1: the whole block; 0: plan + the first half of the eta-row segments; 1: the second half (same plan, same
+// taps).  A background build is split like that, the halves launched 4 steps apart, so that the excitation work the
+// steps give rise to is spread evenly over them (and a timing window of any multiple of 4 steps holds its exact share).
+int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st, int part) {
     LaBlock& Bk = la_blk[buf];
+    if (part == 1) {
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            Group& G = *groups[gi];
+            LookaheadArgs la{};
+            la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * la_S * kLaT * D * Bp;
+            la.S = la_S; la.seg0 = la_S / 2; la.nseg = la_S - la_S / 2;
+            la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = G.la_row0;
+            la.nchunk = (G.la_nrows + kLaRows - 1) / kLaRows; la.use_mma = 1;
+            CUDA_CHECK(launch_lookahead(la, st));
+            prof.kernel_launches += 1;
+        }
+        CUDA_CHECK(cudaEventRecord(ev_la_build, st));
+        return Bk.len;
+    }
     Bk.valid = false; Bk.len = 0;
     const double tmin = eta_t_h.front(), tmax = eta_t_h.back();
     int T = 0;
@@ -961,8 +981,10 @@ int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st) {
         LookaheadArgs la{};
         la.eta = d_eta.p; la.taps = G.la_taps.p; la.cache = d_la_cache.p + size_t(buf) * la_S * kLaT * D * Bp;
         la.S = la_mma ? la_S : 1;
+        la.seg0 = 0; la.nseg = (part == 0) ? la_S / 2 : la.S;
         la.n_eta = n_eta; la.Bp = Bp; la.D = D; la.dof0 = G.dof0; la.nd = G.nd; la.row0 = row0;
         la.nchunk = (nrows + kLaRows - 1) / kLaRows; la.use_mma = la_mma ? 1 : 0;
+        G.la_row0 = row0; G.la_nrows = nrows;
         CUDA_CHECK(launch_lookahead(la, st));
         prof.kernel_launches += 3;
     }
@@ -981,15 +1003,33 @@ void hc_ensemble::prefetch_lookahead(int buf) {
     // (profiling runs every kernel back-to-back in the main stream so that per-kernel event times are meaningful)
     if (!la_background || profiling || !Cur.valid || Cur.len < kLaT) return;   // short block: end of the eta window
     CUDA_CHECK(cudaStreamWaitEvent(la_stream, ev_la_free[buf], 0));
-    if (enqueue_lookahead_block(buf, Cur.times[kLaT - 1] + la_dt, la_stream) > 0)
-        CUDA_CHECK(cudaEventRecord(ev_la_done[buf], la_stream));
+    const bool split = la_mma && la_S >= 2;
+    if (enqueue_lookahead_block(buf, Cur.times[kLaT - 1] + la_dt, la_stream, split ? 0 : -1) > 0) {
+        if (split) la_half_pending = buf;                 // second half: 4 steps from now (lookahead_slot)
+        else CUDA_CHECK(cudaEventRecord(ev_la_done[buf], la_stream));
+    }
+}
+
+// Second half of a split background build (no-op when none is pending).
+void hc_ensemble::finish_split_build() {
+    if (la_half_pending < 0) return;
+    const int buf = la_half_pending;
+    la_half_pending = -1;
+    enqueue_lookahead_block(buf, 0.0, la_stream, 1);
+    CUDA_CHECK(cudaEventRecord(ev_la_done[buf], la_stream));
 }
 
 // Cache slot holding the wave force for time t (bitwise match with a predicted time), building / switching blocks as
 // needed; -1 when look-ahead cannot serve this step (the per-step kernels run instead).
 int hc_ensemble::lookahead_slot(double t) {
     LaBlock& Cur = la_blk[la_cur];
-    if (Cur.valid && la_pos < Cur.len && Cur.times[la_pos] == t) { ++la_hits_this_block; return la_cur * kLaT + la_pos++; }
+    if (Cur.valid && la_pos < Cur.len && Cur.times[la_pos] == t) {
+        if (la_pos >= kLaT / 2) finish_split_build();
+        ++la_hits_this_block;
+        return la_cur * kLaT + la_pos++;
+    }
+    finish_split_build();             // a switch or a rebuild follows: the build in flight must be complete (its scratch
+                                      // is reused by the next one, and the switch waits for its event)
     LaBlock& Nxt = la_blk[la_cur ^ 1];
     if (la_background && !profiling && Nxt.valid && Nxt.len > 0 && Nxt.times[0] == t) {
         const int old = la_cur;
@@ -1001,7 +1041,7 @@ int hc_ensemble::lookahead_slot(double t) {
     }
     // miss: first step, end of a block without prefetch, or a time the prediction did not foresee
     if (la_builds > 0 && la_hits_this_block < 2) {                // a block that served < 2 steps was wasted work
-        if (++la_poor_blocks >= 3) { la_enabled = false; la_blk[0].valid = la_blk[1].valid = false; drop_graph(); return -1; }
+        if (++la_poor_blocks >= 3) { la_enabled = false; la_blk[0].valid = la_blk[1].valid = false; la_half_pending = -1; drop_graph(); return -1; }
     } else {
         la_poor_blocks = 0;
     }
@@ -1169,7 +1209,7 @@ hc_status hc_ensemble_reset(hc_ensemble* e) {
     e->times.clear();
     e->head = -1;
     if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
-    e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0;
+    e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_pos = 0; e->la_half_pending = -1;
     if (e->rb_stream) CUDA_CHECK(cudaStreamSynchronize(e->rb_stream));
     e->rb_invalidate(); e->rb_hits_this_block = 0; e->rb_builds = 0; e->rb_poor_blocks = 0;
     // a new run: look-aheads that the misprediction heuristics switched off are armed again
@@ -1323,7 +1363,7 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
 
     e->n_eta = 0; e->nf = 0;
     e->wave_mode = 2;
-    e->la_enabled = false; e->la_blk[0].valid = e->la_blk[1].valid = false;
+    e->la_enabled = false; e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_half_pending = -1;
     if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->drop_graph();
     const bool have_sea = (Hs_arr || p->wave_height != 0.0) && (Tp_arr || p->wave_period != 0.0);

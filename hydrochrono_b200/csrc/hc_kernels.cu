@@ -664,6 +664,12 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
             const double* e = fa.exc_cache + (((size_t)buf * fa.exc_S * kLaT + pos) * D + d) * a.Bp + b;
             for (int sg = 0; sg < fa.exc_S; ++sg) prefetch_l2(e + (size_t)sg * kLaT * D * a.Bp);
         }
+        // ... and the rows appended since the block's snapshot (lags 1 .. nl - 1; lag 0 is this step's own sample)
+        for (int l = 1; l < nl; ++l) {
+            int slot = (h.head - a.m * l) % h.cap;
+            if (slot < 0) slot += h.cap;
+            prefetch_l2(a.hist + (size_t)slot * row_stride + (size_t)d * a.Bp + b);
+        }
     }
     // fixed-order sum of the row-chunk partials of block step j
     double fr = 0.0;
@@ -1061,8 +1067,9 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
     const int b0 = (blockIdx.x * 4 + warp) * 16;             // 16 instances per warp
     const bool active = b0 < a.Bp;
     // this CTA's segment of the stages (eta rows): [c0, c1)
+    const int seg = a.seg0 + blockIdx.y;
     const int cps = (a.nchunk + a.S - 1) / a.S;
-    const int c0 = blockIdx.y * cps, c1 = min(a.nchunk, c0 + cps);
+    const int c0 = seg * cps, c1 = min(a.nchunk, c0 + cps);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -1126,7 +1133,7 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
     }
     if (active) {
         // C[mt][par][e]: A row m = mt*8 + g -> (block time m / ND, dof m % ND); instance b0 + 2*(2q + e) + par
-        double* cache = a.cache + (size_t)blockIdx.y * kLaT * a.D * a.Bp;
+        double* cache = a.cache + (size_t)seg * kLaT * a.D * a.Bp;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int m = mt * 8 + g, i = m / ND, d = m - i * ND;
@@ -1588,7 +1595,7 @@ static cudaError_t launch_la_mma_t(const LookaheadArgs& a, cudaStream_t st) {
         attr_set[dev & 63] = true;
     }
     const int tiles = (a.Bp + 63) / 64;                      // 4 warps x 16 instances per CTA
-    k_exc_block_mma<ND><<<dim3(tiles, a.S, 1), 128, smem, st>>>(a);
+    k_exc_block_mma<ND><<<dim3(tiles, a.nseg, 1), 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 

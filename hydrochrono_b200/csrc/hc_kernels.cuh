@@ -177,7 +177,8 @@ struct LookaheadArgs {
     double* cache;            // [S][T][D][Bp]: one partial block per segment of eta rows
     int n_eta, Bp, D, dof0, nd, row0, nchunk;
     int use_mma;              // 1: FP64 tensor-core kernel (taps in fragment order)
-    int S;                    // segments the stages are split into (grid.y of k_exc_block_mma; 1 for k_exc_block)
+    int S;                    // segments the stages are split into (1 for k_exc_block)
+    int seg0, nseg;           // k_exc_block_mma: this launch evaluates segments [seg0, seg0 + nseg) (grid.y = nseg)
 };
 // ---- radiation look-ahead: the share of the resident history rows in the next kRbT steps' convolutions, one pass ----
 constexpr int kRbT = 8;            // steps per M-tile (rows of one DMMA tile); a block covers kRbT * m steps
