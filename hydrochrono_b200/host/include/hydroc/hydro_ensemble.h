@@ -45,6 +45,9 @@ class TestHydroEnsemble {
     double CoordinateFuncForInstance(int inst, int b, int i);
     // the three components of the last evaluation, [B][6N] each
     void GetComponents(std::vector<double>& hydrostatic, std::vector<double>& radiation, std::vector<double>& waves);
+    // R[i] += c * M_added * w[i] for every instance at once on the device (ChLoadAddedMass::LoadIntLoadResidual_Mv,
+    // src/chloadaddedmass.cpp:55-71, batched: hc_added_mass_mv); w and R are [B][n_sys], n_sys >= 6 * bodies
+    void AddedMassMvAll(int n_sys, double c, const std::vector<double>& w, std::vector<double>& R);
     long long DeviceEvaluations() const { return evaluations_; }
     hc_ensemble* ensemble() const { return ens_; }
     HydroData& GetHydroData() { return file_info_; }

@@ -149,6 +149,12 @@ double TestHydroEnsemble::CoordinateFuncForInstance(int inst, int b, int i) {
     return force_[size_t(inst) * kDof * num_bodies_ + kDof * (b - 1) + i];
 }
 
+void TestHydroEnsemble::AddedMassMvAll(int n_sys, double c, const std::vector<double>& w, std::vector<double>& R) {
+    const size_t n = size_t(Batch()) * n_sys;
+    if (w.size() != n || R.size() != n) throw std::runtime_error("AddedMassMvAll: w and R must be [B][n_sys]");
+    hc_throw_on_error(hc_added_mass_mv(ens_, n_sys, c, w.data(), R.data()));
+}
+
 void TestHydroEnsemble::GetComponents(std::vector<double>& hs, std::vector<double>& rad, std::vector<double>& wv) {
     const size_t n = size_t(Batch()) * kDof * num_bodies_;
     hs.resize(n); rad.resize(n); wv.resize(n);

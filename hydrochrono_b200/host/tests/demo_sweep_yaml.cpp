@@ -4,6 +4,7 @@
 // evaluation per time value; the same cases are then run one by one through the single-system TestHydro and the
 // trajectories compared.
 // usage: demo_sweep_yaml <hydro.yaml> <out.txt> <euler|hht> [duration = 30] [seeds per period = 1]
+#include <hydroc/chloadaddedmass.h>
 #include <hydroc/hydro_ensemble.h>
 #include <hydroc/hydro_forces.h>
 #include <hydroc/hydro_yaml_parser.h>
@@ -66,6 +67,23 @@ int main(int argc, char* argv[]) {
             for (int i = 0; i < B; ++i) z[i][n] = inst[i]->body->GetPos().z();
         }
         std::cout << "instances " << B << " steps " << nsteps << " device_evaluations " << ens->DeviceEvaluations() << std::endl;
+        {   // batched added-mass residual on the device against each system's own ChLoadAddedMass (host) load
+            const int nsys = 6;
+            std::vector<double> w(size_t(B) * nsys), R(size_t(B) * nsys, 0.5);
+            for (size_t k = 0; k < w.size(); ++k) w[k] = 0.01 * double(k % 17) - 0.05;
+            ens->AddedMassMvAll(nsys, 1.75, w, R);
+            double worst_mv = 0.0;
+            std::vector<std::shared_ptr<ChLoadable>> loadables{inst[0]->body};
+            ChLoadAddedMass ref(ens->GetHydroData().GetBodyInfos(), loadables, &inst[0]->sys);
+            ref.ComputeJacobian(nullptr, nullptr);
+            for (int i = 0; i < B; ++i) {
+                ChVectorDynamic<> Rv(nsys), wv(nsys);
+                for (int k = 0; k < nsys; ++k) { Rv(k) = 0.5; wv(k) = w[size_t(i) * nsys + k]; }
+                ref.LoadIntLoadResidual_Mv(Rv, wv, 1.75);
+                for (int k = 0; k < nsys; ++k) worst_mv = std::max(worst_mv, std::fabs(Rv(k) - R[size_t(i) * nsys + k]) / (1.0 + std::fabs(Rv(k))));
+            }
+            std::cout << std::scientific << "added_mass_mv_batched_rel_diff " << worst_mv << std::endl;
+        }
 
         // ---- the same cases one at a time through the single-system TestHydro ----
         double worst = 0.0;

@@ -280,6 +280,7 @@ def test_yaml_period_sweep_maps_onto_ensemble_instances(host_build, sphere_h5, t
     # one batched evaluation per time value: Euler evaluates at t_0 .. t_{n-1}; HHT at t_0 (initial accelerations) + t_1 .. t_n
     assert int(words[words.index("device_evaluations") + 1]) == nsteps + (1 if stepper_name == "hht" else 0)
     assert float(words[words.index("max_abs_diff_vs_single_runs") + 1]) <= 1e-12
+    assert float(words[words.index("added_mass_mv_batched_rel_diff") + 1]) <= 1e-13      # k_added_mass_mv vs the host load
     a = np.loadtxt(o)
     assert a.shape == (nsteps, 1 + B)
     assert np.abs(a[:, 1:] + 2.0).max() < 1.5 and np.ptp(a[:, 1]) > 1e-3
