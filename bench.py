@@ -160,7 +160,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th, self.nvml, self.proc = index, [], False, None, None, None
-        self.period = float(os.environ.get("HC_BENCH_CLOCK_PERIOD", "0.02"))
+        self.period = float(os.environ.get("HC_BENCH_CLOCK_PERIOD", "0.005"))
 
     def start(self):
         if os.environ.get("HC_BENCH_NO_CLOCKS"):       # experiment switch: no sampling at all
@@ -691,33 +691,13 @@ def main():
         leg.dev_step()
     leg.align()
     sampler = ClockSampler(local_rank)              # every rank samples the GPU it drives
+    if world > 1 and "HC_BENCH_CLOCK_PERIOD" not in os.environ:
+        sampler.period = 0.02                       # eight processes polling NVML every 5 ms is more than the run needs
     launches0 = ens.profile()["kernel_launches"]
     ens.sync()
     barrier()
     sampler.start()
     t_dev, t_enq, t_wall = leg.timed_device(K, barrier)
-    mine = sampler.stop()
-    # over the ranks: the slowest GPU's median and minimum SM clock, any throttle reason seen anywhere
-    vec = torch.tensor(mine if mine else [0.0] * 8, dtype=torch.float64, device=dev)
-    lo, hi = vec.clone(), vec.clone()
-    if world > 1:
-        if not mine:
-            lo[:2] = float("inf")
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        tot = vec[7:8].clone()
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        nsamp = float(tot.item())
-    else:
-        nsamp = float(vec[7].item())
-    lo, hi = lo.tolist(), hi.tolist()
-    if nsamp > 0 and np.isfinite(lo[0]):
-        clocks = {"sm_mhz": lo[0], "sm_min_mhz": lo[1], "sm_max_mhz": hi[2],
-                  "reasons": [nm for nm, f in zip(ClockSampler.NAMES, hi[3:7]) if f > 0], "samples": int(nsamp), "gpus": world,
-                  "source": "NVML, one sampling thread per rank (20 ms period) during the timed region; sm_mhz = the "
-                            "slowest GPU's median"}
-    else:
-        clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0, "gpus": world}
     launches = ens.profile()["kernel_launches"] - launches0
     t_dev = max_over_ranks(t_dev)
     t_enq_max = max_over_ranks(t_enq)
@@ -744,6 +724,28 @@ def main():
         leg.host_step()
     t_e2e = max_over_ranks(leg.timed_host(K, barrier))
     checksum = float(leg.h_force.numpy()[:, 2].sum())
+    mine = sampler.stop()          # sampled from the start of the device-resident leg to the end of the end-to-end leg
+    # over the ranks: the slowest GPU's median and minimum SM clock, any throttle reason seen anywhere
+    vec = torch.tensor(mine if mine else [0.0] * 8, dtype=torch.float64, device=dev)
+    lo, hi = vec.clone(), vec.clone()
+    if world > 1:
+        if not mine:
+            lo[:2] = float("inf")
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        tot = vec[7:8].clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        nsamp = float(tot.item())
+    else:
+        nsamp = float(vec[7].item())
+    lo, hi = lo.tolist(), hi.tolist()
+    if nsamp > 0 and np.isfinite(lo[0]):
+        clocks = {"sm_mhz": lo[0], "sm_min_mhz": lo[1], "sm_max_mhz": hi[2],
+                  "reasons": [nm for nm, f in zip(ClockSampler.NAMES, hi[3:7]) if f > 0], "samples": int(nsamp), "gpus": world,
+                  "source": "NVML, one sampling thread per rank (5 ms period at N = 1, 20 ms at N > 1) from the start of the device-resident timed "
+                            "region to the end of the end-to-end timed region; sm_mhz = the slowest GPU's median"}
+    else:
+        clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0, "gpus": world}
 
     # ---- parity at the benchmarked state ----------------------------------------------------------------
     parity = None
