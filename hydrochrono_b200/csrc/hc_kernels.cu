@@ -648,8 +648,8 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
     const int b0 = blockIdx.x * kRsInst;
     const int b = b0 + bl;
     const size_t row_stride = (size_t)D * a.Bp;
-    // the CTA's [32][D] tile of pose is contiguous: one coalesced read (the buffer may be pinned HOST memory that the
-    // kernel reads across PCIe -- hc_step's zero-copy path for small ensembles -- so every value is fetched once)
+    // the CTA's [32][D] tile of pose is contiguous: one coalesced read, every value fetched once (finalize_one reads the
+    // 6 pose values of its body from shared memory instead of 6 x from global for each of the body's 6 DoF threads)
     {
         const int lb = tid / D, c = tid - lb * D;
         s_io[lb][c] = (b0 + lb < a.B) ? h.pose[(size_t)(b0 + lb) * D + c] : 0.0;

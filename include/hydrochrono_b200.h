@@ -151,7 +151,9 @@ typedef struct hc_ensemble_opts {
     int use_graph;            /* 1: capture the per-step kernel sequence in a CUDA graph (default 1) */
     int exc_lookahead;        /* irregular waves: 0 = auto (on when dt_hint > 0 and the batch fills the GPU), 1 = off,
                                  2 = on, blocks built in the step's stream (FMA-pipe kernel), 3 = next block built on a
-                                 low-priority side stream, 4 / 5 = like 2 / 3 with the FP64 tensor-core (DMMA) kernel.  The wave force is state-independent, so it is evaluated for the predicted
+                                 low-priority side stream, 4 / 5 = like 2 / 3 with the FP64 tensor-core (DMMA) kernel
+                                 (5: the background build is launched in two halves, 4 steps apart, so that the
+                                 look-ahead work is spread evenly over the steps).  The wave force is state-independent, so it is evaluated for the predicted
                                  times t, t+dt, ... of the next 8 steps in one pass over eta (t advanced by repeated
                                  addition of dt_hint, as Chrono advances ChTime); a step whose time is not bitwise
                                  equal to the prediction falls back to / rebuilds from the actual time, so results

@@ -27,5 +27,4 @@ for n in range(prefill + nsteps):
     if n >= prefill:
         lat.append(time.perf_counter() - t0)
     t += dt
-print("%s: median %.1f us  p10 %.1f  p90 %.1f  (HC_SMALL_CHUNKS=%s)" % (which, 1e6 * np.median(lat), 1e6 * np.percentile(lat, 10),
-                                                                      1e6 * np.percentile(lat, 90), os.environ.get("HC_SMALL_CHUNKS", "default")))
+print("%s: median %.1f us  p10 %.1f  p90 %.1f" % (which, 1e6 * np.median(lat), 1e6 * np.percentile(lat, 10), 1e6 * np.percentile(lat, 90)))
