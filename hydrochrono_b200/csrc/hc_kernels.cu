@@ -719,12 +719,141 @@ __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const R
     }
     // (the loop above ran at least once, so s_io is visible to every thread)
     const double total = (b < a.B) ? finalize_one(fa, hs, eg, h, d, b, true, fr, &s_io[bl][6 * (d / 6)]) : 0.0;
-    if (h.force2) {      // second copy of the totals (the caller's buffer, possibly pinned host memory): coalesced tile
+    if (h.force2) {      // second copy of the totals (the caller's buffer): coalesced tile
         __syncthreads();
         s_io[bl][d] = total;
         __syncthreads();
         const int lb = tid / D, c = tid - lb * D;
         if (b0 + lb < a.B) h.force2[(size_t)(b0 + lb) * D + c] = s_io[lb][c];
+    }
+}
+
+// k_step2<D>: the same step kernel with a fatter thread -- a CTA of 256 threads serves 64 instances x D DoF, every
+// thread 3 (instance, DoF) items (D = 12).  k_step is bound by a chain of dependent memory round trips, not by work, so
+// its cost to the step is the CTA slots it holds while waiting (slots the look-ahead passes' tensor CTAs would use):
+// three items per thread put three times the loads in flight per slot, and the CTA (256 x <= 80 registers, 64 KB of
+// shared memory) fits the slot one retiring k_rad_block CTA frees.  Arithmetic and summation order per item are k_step's.
+constexpr int kRs2Inst = 64, kRs2Threads = 256;
+template <int D>
+__global__ void __launch_bounds__(kRs2Threads, 3) k_step2(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
+                                                          const __grid_constant__ HydrostaticTables hs,
+                                                          const __grid_constant__ FinalizeGroups eg,
+                                                          const __grid_constant__ StepHeader h) {
+    constexpr int LAGS = 8;
+    constexpr int IPT = kRs2Inst * D / kRs2Threads;  // items per thread
+    static_assert(kRs2Inst * D % kRs2Threads == 0, "items must divide evenly");
+    extern __shared__ __align__(16) unsigned char smem2_raw[];      // 63 KB: dynamic (above the 48 KB static limit)
+    double* const s_K = reinterpret_cast<double*>(smem2_raw);                                     // (K w)[lag][col][row]
+    double (*s_v)[D][kRs2Inst] = reinterpret_cast<double (*)[D][kRs2Inst]>(s_K + LAGS * D * D);    // young rows [lag][col][inst]
+    double (*s_io)[D] = reinterpret_cast<double (*)[D]>(s_K + LAGS * D * D + LAGS * D * kRs2Inst); // pose tile in, totals out
+    const int j = h.rb_j;
+    const int nl = min(min(h.rb_jj / a.m, h.rb_smax), a.L - 1) + 1;   // young lags 0 .. nl - 1
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * kRs2Inst;
+    const size_t row_stride = (size_t)D * a.Bp;
+    int bl[IPT], dd[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) { const int it = tid + k * kRs2Threads; bl[k] = it % kRs2Inst; dd[k] = it / kRs2Inst; }
+    // pose tile [64][D], contiguous
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int it = tid + k * kRs2Threads, lb = it / D, c = it - lb * D;
+        s_io[lb][c] = (b0 + lb < a.B) ? h.pose[(size_t)(b0 + lb) * D + c] : 0.0;
+    }
+    // request everything the sums below will read
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int b = b0 + bl[k], d = dd[k];
+        const double* p = a.partial[h.rb_buf] + ((size_t)j * a.nchunk * D + d) * a.Bp + b;
+        for (int ch = 0; ch < h.rb_nchunk; ++ch) prefetch_l2(p + (size_t)ch * row_stride);
+        if (fa.wave_mode == 2 && h.exc_src == 1) {
+            const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
+            const double* e = fa.exc_cache + (((size_t)buf * fa.exc_S * kLaT + pos) * D + d) * a.Bp + b;
+            for (int sg = 0; sg < fa.exc_S; ++sg) prefetch_l2(e + (size_t)sg * kLaT * D * a.Bp);
+        }
+        for (int l = 1; l < nl; ++l) {
+            int slot = (h.head - a.m * l) % h.cap;
+            if (slot < 0) slot += h.cap;
+            prefetch_l2(a.hist + (size_t)slot * row_stride + (size_t)d * a.Bp + b);
+        }
+    }
+    // fixed-order sum of the row-chunk partials of block step j, the IPT items interleaved
+    double fr[IPT];
+    const double* pp[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        fr[k] = 0.0;
+        pp[k] = a.partial[h.rb_buf] + ((size_t)j * a.nchunk * D + dd[k]) * a.Bp + b0 + bl[k];
+    }
+    {
+        int ch = 0;
+        for (; ch + 4 <= h.rb_nchunk; ch += 4) {
+            double v[IPT][4];
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[k][i] = __ldg(pp[k] + (size_t)(ch + i) * row_stride);
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) fr[k] = __dadd_rn(fr[k], v[k][i]);
+        }
+        for (; ch < h.rb_nchunk; ++ch)
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) fr[k] = __dadd_rn(fr[k], __ldg(pp[k] + (size_t)ch * row_stride));
+    }
+    for (int l0 = ((nl - 1) / LAGS) * LAGS; l0 >= 0; l0 -= LAGS) {     // oldest lag group first
+        const int n = min(LAGS, nl - l0);
+        __syncthreads();
+        for (int i = tid; i < n * D * D; i += kRs2Threads) s_K[i] = a.K[(size_t)l0 * D * D + i];
+        for (int l = 0; l < n; ++l) {
+            if (l0 + l == 0) {
+#pragma unroll
+                for (int k = 0; k < IPT; ++k) {     // this step's sample: the CTA's [64][D] tile of vel is contiguous
+                    const int it = tid + k * kRs2Threads, lb = it / D, c = it - lb * D;
+                    s_v[0][c][lb] = (b0 + lb < a.B) ? h.vel[(size_t)(b0 + lb) * D + c] : 0.0;
+                }
+            } else {                                               // lag l: the row appended m l steps ago
+                int slot = (h.head - a.m * (l0 + l)) % h.cap;
+                if (slot < 0) slot += h.cap;
+#pragma unroll
+                for (int k = 0; k < IPT; ++k)
+                    s_v[l][dd[k]][bl[k]] = a.hist[(size_t)slot * row_stride + (size_t)dd[k] * a.Bp + b0 + bl[k]];
+            }
+        }
+        __syncthreads();
+        if (l0 == 0) {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+                a.hist[(size_t)h.head * row_stride + (size_t)dd[k] * a.Bp + b0 + bl[k]] = s_v[0][dd[k]][bl[k]];
+            if (blockIdx.x == 0 && tid == 0) a.times[h.head] = h.t;
+        }
+        for (int l = n - 1; l >= 0; --l) {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc = fma(s_K[(l * D + c) * D + dd[k]], s_v[l][c][bl[k]], acc);
+                fr[k] = __dadd_rn(fr[k], acc);
+            }
+        }
+    }
+    double total[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int b = b0 + bl[k];
+        total[k] = (b < a.B) ? finalize_one(fa, hs, eg, h, dd[k], b, true, fr[k], &s_io[bl[k]][6 * (dd[k] / 6)]) : 0.0;
+    }
+    if (h.force2) {      // second copy of the totals (the caller's buffer): coalesced tile
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) s_io[bl[k]][dd[k]] = total[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int it = tid + k * kRs2Threads, lb = it / D, c = it - lb * D;
+            if (b0 + lb < a.B) h.force2[(size_t)(b0 + lb) * D + c] = s_io[lb][c];
+        }
     }
 }
 
@@ -764,6 +893,19 @@ cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const Hydr
         cudaFuncSetAttribute(k_step<12>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_step<18>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set[dev & 63] = true;
+    }
+    static int use2 = -1;
+    if (use2 < 0) { const char* v = std::getenv("HC_KSTEP2"); use2 = (v && std::atoi(v) == 0) ? 0 : 1; }   // default on
+    if (use2 && a.D == 12 && a.Bp % kRs2Inst == 0) {
+        constexpr size_t smem2 = sizeof(double) * (8 * 12 * 12 + 8 * 12 * kRs2Inst + kRs2Inst * 12);
+        static bool attr2[64] = {};
+        if (!attr2[dev & 63]) {
+            cudaFuncSetAttribute(k_step2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            cudaFuncSetAttribute(k_step2<12>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr2[dev & 63] = true;
+        }
+        k_step2<12><<<a.Bp / kRs2Inst, kRs2Threads, smem2, st>>>(a, fa, hs, eg, hdr);
+        return cudaGetLastError();
     }
     switch (a.D) {
         case 6: k_step<6><<<a.Bp / kRsInst, kRsInst * 6, 0, st>>>(a, fa, hs, eg, hdr); break;
