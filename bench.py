@@ -724,6 +724,15 @@ def main():
         leg.host_step()
     t_e2e = max_over_ranks(leg.timed_host(K, barrier))
     checksum = float(leg.h_force.numpy()[:, 2].sum())
+    # the final result gather of the north star (the only inter-GPU traffic of the whole run besides the timing
+    # reductions): every rank's heave forces of the last step, in global instance order, on rank 0
+    gathered = None
+    if world > 1:
+        from hydrochrono_b200 import shard
+        full = shard.gather_results(leg.h_force.numpy()[:, 2:3].copy(), world * B, world, rank, dist=dist, device=dev)
+        if rank == 0:
+            gathered = {"instances": int(full.shape[0]), "checksum": float(full.sum()),
+                        "rank0_block_matches": bool(np.array_equal(full[:B, 0], leg.h_force.numpy()[:, 2]))}
     mine = sampler.stop()          # sampled from the start of the device-resident leg to the end of the end-to-end leg
     # over the ranks: the slowest GPU's median and minimum SM clock, any throttle reason seen anywhere
     vec = torch.tensor(mine if mine else [0.0] * 8, dtype=torch.float64, device=dev)
@@ -935,6 +944,7 @@ def main():
                               "device copies, so ms_per_step < sum(kernel_ms)",
             "setup": {"eta_synthesis_s": eta_s, "setup_and_prefill_s": setup_s},
             "checksum": checksum,
+            "gathered": gathered,
         }
         if world == 1 and not args.no_b1 and WORKLOAD == "rm3_irregular_ensemble":
             try:

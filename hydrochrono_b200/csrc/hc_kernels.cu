@@ -896,7 +896,10 @@ cudaError_t launch_step(const RadStepArgs& a, const FinalizeArgs& fa, const Hydr
     }
     static int use2 = -1;
     if (use2 < 0) { const char* v = std::getenv("HC_KSTEP2"); use2 = (v && std::atoi(v) == 0) ? 0 : 1; }   // default on
-    if (use2 && a.D == 12 && a.Bp % kRs2Inst == 0) {
+    // k_step2 pays where the step is throughput-bound (its CTAs compete with tensor CTAs for slots); a small ensemble's
+    // step is k_step's own latency chain, which three sequential items per thread only lengthen (8 x 2048 instances:
+    // 0.046 vs 0.041 ms per step)
+    if (use2 && a.D == 12 && a.Bp % kRs2Inst == 0 && a.Bp / kRs2Inst >= 148) {
         constexpr size_t smem2 = sizeof(double) * (8 * 12 * 12 + 8 * 12 * kRs2Inst + kRs2Inst * 12);
         static bool attr2[64] = {};
         if (!attr2[dev & 63]) {
