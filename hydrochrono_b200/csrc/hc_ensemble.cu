@@ -164,6 +164,9 @@ struct hc_ensemble {
     PinBuf h_stage;
     size_t stage_bytes = 0;
     bool compact_ok = false, defer_launch = false;
+    double* h_force_dev = nullptr;                // device-side address of the pinned force buffer (compact graph writes it directly)
+    bool compact_capture = false;                 // enqueue_phase is recording the compact graph (state already on the device)
+    cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
     cudaGraph_t graph_c = nullptr;
     cudaGraphExec_t graph_c_exec = nullptr;
     int graph_c_key = -1;
@@ -241,6 +244,8 @@ struct hc_ensemble {
         drop_graph();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (ev_cfork) cudaEventDestroy(ev_cfork);
+        if (ev_cjoin) cudaEventDestroy(ev_cjoin);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_inputs) cudaEventDestroy(ev_inputs);
         if (ev_force) cudaEventDestroy(ev_force);
@@ -653,8 +658,16 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
     }
     if (phase == 1) {
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
-        if (!rb_use || per_step_exc) CUDA_CHECK(launch_prestep(pa, 2, stream));
+        // compact graph: the state is on the device before anything runs, so the append rides in the plan kernel, and
+        // the excitation convolution (independent of the radiation convolution) is a parallel branch of the graph
+        if (!rb_use || per_step_exc) CUDA_CHECK(launch_prestep(pa, compact_capture ? 3 : 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
+        const bool fork = compact_capture && per_step_exc && !skip_radiation && !rb_use;
+        cudaStream_t es = fork ? copy_stream : stream;
+        if (fork) {
+            CUDA_CHECK(cudaEventRecord(ev_cfork, stream));
+            CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_cfork, 0));
+        }
         if (per_step_exc) {
             ExcitationArgs ea{};
             ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
@@ -662,9 +675,10 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
             for (size_t g = 0; g < groups.size(); ++g) {
                 Group& G = *groups[g];
                 ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
-                CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, stream));
+                CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, es));
             }
         }
+        if (fork) CUDA_CHECK(cudaEventRecord(ev_cjoin, copy_stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
         if (!skip_radiation && !rb_use) {
             // convolution over the history that is already resident: every row except this step's own sample
@@ -676,10 +690,11 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
             ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
             CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
         }
+        if (fork) CUDA_CHECK(cudaStreamWaitEvent(stream, ev_cjoin, 0));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
         return;
     }
-    if (!rb_use) {
+    if (!rb_use && !compact_capture) {
         CUDA_CHECK(launch_prestep(pa, 1, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_APPEND], stream));
     }
@@ -1063,18 +1078,27 @@ void hc_ensemble::run_compact() {
         if (graph_c_exec) cudaGraphExecDestroy(graph_c_exec);
         if (graph_c) cudaGraphDestroy(graph_c);
         graph_c_exec = nullptr; graph_c = nullptr;
+        if (!ev_cfork) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_cfork, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_cjoin, cudaEventDisableTiming));
+        }
         CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        compact_capture = true;
         try {
             CUDA_CHECK(cudaMemcpyAsync(d_stage.p, h_stage.p, stage_bytes, cudaMemcpyHostToDevice, stream));
             enqueue_phase(1, false);
             enqueue_phase(2, false);
-            CUDA_CHECK(cudaMemcpyAsync(h_force.p, d_force.p, size_t(B) * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            // (no D2H node when the finalize kernel stores its second copy of the totals straight into the pinned buffer)
+            if (!h_force_dev)
+                CUDA_CHECK(cudaMemcpyAsync(h_force.p, d_force.p, size_t(B) * D * sizeof(double), cudaMemcpyDeviceToHost, stream));
         } catch (...) {
+            compact_capture = false;
             cudaGraph_t tmp = nullptr;
             cudaStreamEndCapture(stream, &tmp);
             if (tmp) cudaGraphDestroy(tmp);
             throw;
         }
+        compact_capture = false;
         CUDA_CHECK(cudaStreamEndCapture(stream, &graph_c));
         CUDA_CHECK(cudaGraphInstantiate(&graph_c_exec, graph_c, 0));
         graph_c_key = key;
@@ -1191,6 +1215,14 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     if (e->compact_ok) e->h_stage.alloc(e->stage_bytes);
     e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
+    if (e->compact_ok) {
+        const char* v = std::getenv("HC_COMPACT_DIRECT");            // diagnostic: 0 = forces come back through a copy node
+        if (!(v && std::atoi(v) == 0)) {
+            void* dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, e->h_force.p, 0) == cudaSuccess) e->h_force_dev = static_cast<double*>(dp);
+            else cudaGetLastError();
+        }
+    }
     CUDA_CHECK(cudaDeviceSynchronize());
     *out = e.release();
     return HC_OK;
@@ -1564,9 +1596,10 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
             }
             if (began && e->defer_launch) {              // per-step kernels: one graph
                 e->defer_launch = false;
+                if (e->h_force_dev) e->hdr_h.force2 = e->h_force_dev;
                 std::memcpy(hs, &e->hdr_h, sizeof(StepHeader));
                 e->run_compact();
-                e->prof.kernel_launches += e->phase1_launches + 2;
+                e->prof.kernel_launches += e->phase1_launches + 1;       // (the append rides in the plan kernel)
                 e->prof.hydrostatics_calls++; e->prof.radiation_calls++; e->prof.waves_calls++;
                 e->prev_time = t;
                 e->force_valid = true;

@@ -630,7 +630,9 @@ constexpr int kRsInst = 32;
 struct FinalizeArgs;
 __device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                                                const StepHeader& h, const int d, const int b, const bool have_fr,
-                                               const double fr_block, const double* pose6);
+                                               const double fr_block, const double* pose6,
+                                               const double* fr_part_pre = nullptr, const double* fw_pre = nullptr,
+                                               const bool write = true);
 
 template <int D>
 __global__ void __launch_bounds__(kRsInst * D, (D == 12) ? 4 : 1) k_step(const RadStepArgs a, const __grid_constant__ FinalizeArgs fa,
@@ -1295,9 +1297,12 @@ __global__ void __launch_bounds__(128, 3) k_exc_block_mma(const LookaheadArgs a)
 
 // Force of (dof d, instance b).  fr_block: the radiation force when the caller already holds it (k_step).
 // Returns the total; writes it to h.force (and the components to a.comp).  pose6: the 6 pose values of (b, body).
+// fr_part_pre / fw_pre: the sum of the radiation lag-chunk partials / the wave force when the caller has already
+// reduced them (k_finalize_warp); write: whether this thread stores the results.
 __device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                                                const StepHeader& h, const int d, const int b, const bool have_fr,
-                                               const double fr_block, const double* pose6) {
+                                               const double fr_block, const double* pose6, const double* fr_part_pre,
+                                               const double* fw_pre, const bool write) {
     const int D = a.D;
     const int body = d / 6, i = d - 6 * body;
     const double gx = h.g[0], gy = h.g[1], gz = h.g[2];
@@ -1334,15 +1339,19 @@ __device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const Hydr
     if (!a.waves_only && have_fr) {
         fr = fr_block;                                                   // k_rad_block + this kernel (k_step)
     } else if (!a.waves_only) {
-        const double* p = a.rad_partial + (size_t)d * a.Bp + b;
-        const size_t stride = (size_t)D * a.Bp;
-        int ch = 0;
-        for (; ch + 4 <= a.rad_nchunk; ch += 4) {
-            const double p0 = p[(size_t)ch * stride], p1 = p[(size_t)(ch + 1) * stride];
-            const double p2 = p[(size_t)(ch + 2) * stride], p3 = p[(size_t)(ch + 3) * stride];
-            fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
+        if (fr_part_pre) {
+            fr = *fr_part_pre;
+        } else {
+            const double* p = a.rad_partial + (size_t)d * a.Bp + b;
+            const size_t stride = (size_t)D * a.Bp;
+            int ch = 0;
+            for (; ch + 4 <= a.rad_nchunk; ch += 4) {
+                const double p0 = p[(size_t)ch * stride], p1 = p[(size_t)(ch + 1) * stride];
+                const double p2 = p[(size_t)(ch + 2) * stride], p3 = p[(size_t)(ch + 3) * stride];
+                fr = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(fr, p0), p1), p2), p3);
+            }
+            for (; ch < a.rad_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
         }
-        for (; ch < a.rad_nchunk; ++ch) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
         // share of this step's own velocity sample (leading lags whose newer bracket sample is "now")
         const double* vel = h.vel + (size_t)b * D;
         for (int s = 0; s < a.L && a.pr_lead[s]; ++s) {   // leading lags: contiguous from lag 0
@@ -1360,6 +1369,8 @@ __device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const Hydr
         // mag * A * cos(omega t + phase[rowEx])  (wave_types.cpp:322-323; phase of body 0, reference quirk)
         const double arg = __dadd_rn(__dmul_rn(a.reg_omega[b], h.t), a.reg_phase[(size_t)i * a.Bp + b]);
         fw = __dmul_rn(__dmul_rn(a.reg_mag[(size_t)d * a.Bp + b], a.reg_amp[b]), cos(arg));
+    } else if (a.wave_mode == 2 && fw_pre) {
+        fw = *fw_pre;
     } else if (a.wave_mode == 2 && h.exc_src == 1) {
         // precomputed by k_exc_block(_mma): slot = buffer * T + block step; S row-segment partials in fixed order
         const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
@@ -1388,8 +1399,9 @@ __device__ __forceinline__ double finalize_one(const FinalizeArgs& a, const Hydr
         }
     }
     const size_t o = (size_t)b * D + d;
-    if (a.waves_only) { h.force[o] = fw; return fw; }
+    if (a.waves_only) { if (write) h.force[o] = fw; return fw; }
     const double total = __dadd_rn(__dsub_rn(fh, fr), fw);           // hs - rad + waves (:758-760)
+    if (!write) return total;
     h.force[o] = total;
     if (a.comp) {
         const size_t BD = (size_t)a.B * D;
@@ -1411,6 +1423,54 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const __
     const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
                                       a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6));
     if (h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
+}
+
+// k_finalize_warp: the same for SMALL ensembles (the drop-in B = 1 TestHydro): there the lag / tap chunks are short so
+// that the convolution kernels have CTAs to spread over, which leaves hundreds of partials per (dof, instance) -- 251 +
+// 286 for the RM3 shape -- and k_finalize's one thread per item sums them as one dependent chain (63 us cold, most of a
+// B = 1 step).  Here one WARP owns an item: lane l sums partials l, l + 32, ... in ascending order, a butterfly of
+// shuffles (symmetric, so every lane holds the same bits) adds the 32 lane sums, then the item is finished as above.
+// Deterministic; the association differs from k_finalize's, so the two agree to rounding (1e-16 relative), not bitwise --
+// which kernel serves an ensemble depends only on its size.
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
+                                                       const __grid_constant__ FinalizeGroups eg) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int d = w / a.B, b = w - d * a.B;            // real instances only
+    if (d >= a.D) return;                              // (uniform per warp)
+    const StepHeader h = *a.hdr;
+    const int D = a.D;
+    double fr = 0.0, fw = 0.0;
+    if (!a.waves_only) {
+        const double* p = a.rad_partial + (size_t)d * a.Bp + b;
+        const size_t stride = (size_t)D * a.Bp;
+        for (int ch = lane; ch < a.rad_nchunk; ch += 32) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
+        fr = warp_sum_fixed(fr);
+    }
+    if (a.wave_mode == 2 && h.exc_src == 1) {
+        const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
+        const double* p = a.exc_cache + (((size_t)buf * a.exc_S * kLaT + pos) * D + d) * a.Bp + b;
+        const size_t sstride = (size_t)kLaT * D * a.Bp;
+        for (int sg = lane; sg < a.exc_S; sg += 32) fw = __dadd_rn(fw, p[(size_t)sg * sstride]);
+        fw = warp_sum_fixed(fw);
+    } else if (a.wave_mode == 2) {
+        for (int g = 0; g < a.exc_ngroups; ++g) {
+            if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
+            const double* p = a.exc_partial + ((size_t)eg.chunk0[g] * a.exc_ndmax + (d - eg.dof0[g])) * a.Bp + b;
+            const size_t stride = (size_t)a.exc_ndmax * a.Bp;
+            double s = 0.0;
+            for (int ch = lane; ch < eg.nchunk[g]; ch += 32) s = __dadd_rn(s, p[(size_t)ch * stride]);
+            fw = __dadd_rn(fw, warp_sum_fixed(s));
+        }
+    }
+    const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
+                                      a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6), &fr, &fw, lane == 0);
+    if (lane == 0 && h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1609,7 +1669,10 @@ cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    k_finalize<<<(a.D * a.Bp + 255) / 256, 256, 0, st>>>(a, hs, eg);
+    if (a.B <= kFinalizeWarpMaxB)      // small ensemble: a warp per (dof, instance)
+        k_finalize_warp<<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);
+    else
+        k_finalize<<<(a.D * a.Bp + 255) / 256, 256, 0, st>>>(a, hs, eg);
     return cudaGetLastError();
 }
 
