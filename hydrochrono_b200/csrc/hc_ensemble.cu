@@ -165,11 +165,13 @@ struct hc_ensemble {
     size_t stage_bytes = 0;
     bool compact_ok = false, defer_launch = false;
     double* h_force_dev = nullptr;                // device-side address of the pinned force buffer (compact graph writes it directly)
+    bool compact_inline = true;                   // HC_COMPACT_INLINE=0: keep the plan kernel in the compact graph (diagnostic)
     bool compact_capture = false;                 // enqueue_phase is recording the compact graph (state already on the device)
     cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
     cudaGraph_t graph_c = nullptr;
     cudaGraphExec_t graph_c_exec = nullptr;
     int graph_c_key = -1;
+    bool graph_c_inline = false;                  // the captured compact graph has no plan kernel
     void run_compact();
 
     PinBuf h_pose, h_vel, h_force;
@@ -658,11 +660,23 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
     }
     if (phase == 1) {
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
-        // compact graph: the state is on the device before anything runs, so the append rides in the plan kernel, and
-        // the excitation convolution (independent of the radiation convolution) is a parallel branch of the graph
-        if (!rb_use || per_step_exc) CUDA_CHECK(launch_prestep(pa, compact_capture ? 3 : 2, stream));
+        // convolution over the history that is already resident: every row except this step's own sample
+        RadiationArgs ra{};
+        ra.hdr = d_hdr.p; ra.K = d_K.p; ra.Kfrag = rad_mma ? d_Kfrag.p : nullptr;
+        ra.Khyb = rad_hybrid ? d_Khyb.p : nullptr;
+        ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
+        ra.times = d_times.p; ra.partial = d_rad_partial.p;
+        ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
+        const bool run_rad = !skip_radiation && !rb_use;
+        // Compact graph: the state is on the device before anything runs.  The convolution kernels plan their own
+        // lags / taps and the radiation kernel appends the sample (no k_prestep level); the excitation convolution,
+        // independent of the radiation convolution, is a parallel branch of the graph.  Without a radiation kernel
+        // that can do so, the append at least rides in the plan kernel.
+        const bool plan_inline = compact_capture && compact_inline && run_rad && radiation_plans_inline(ra);
+        if (compact_capture) graph_c_inline = plan_inline;
+        if (!plan_inline && (!rb_use || per_step_exc)) CUDA_CHECK(launch_prestep(pa, compact_capture ? 3 : 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
-        const bool fork = compact_capture && per_step_exc && !skip_radiation && !rb_use;
+        const bool fork = compact_capture && per_step_exc && run_rad;
         cudaStream_t es = fork ? copy_stream : stream;
         if (fork) {
             CUDA_CHECK(cudaEventRecord(ev_cfork, stream));
@@ -675,20 +689,15 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
             for (size_t g = 0; g < groups.size(); ++g) {
                 Group& G = *groups[g];
                 ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
-                CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, es));
+                CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, es, plan_inline));
             }
         }
         if (fork) CUDA_CHECK(cudaEventRecord(ev_cjoin, copy_stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
-        if (!skip_radiation && !rb_use) {
-            // convolution over the history that is already resident: every row except this step's own sample
-            RadiationArgs ra{};
-            ra.hdr = d_hdr.p; ra.K = d_K.p; ra.Kfrag = rad_mma ? d_Kfrag.p : nullptr;
-            ra.Khyb = rad_hybrid ? d_Khyb.p : nullptr;
-            ra.rirf_t = d_rirf_t.p; ra.rirf_w = d_rirf_w.p; ra.hist = d_hist.p;
-            ra.times = d_times.p; ra.partial = d_rad_partial.p;
-            ra.L = L; ra.D = D; ra.Bp = Bp; ra.chunk = rad_chunk; ra.nchunk = rad_nchunk;
-            CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream));
+        if (run_rad) {
+            const InlinePlan ipl{d_pr_wd.p, d_pr_head.p, d_pr_lead.p, B};
+            CUDA_CHECK(launch_radiation(ra, d_pr_new.p, d_pr_old.p, d_pr_wn.p, d_pr_wo.p, d_pr_wd.p, stream,
+                                        plan_inline ? &ipl : nullptr));
         }
         if (fork) CUDA_CHECK(cudaStreamWaitEvent(stream, ev_cjoin, 0));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_RAD], stream));
@@ -1216,6 +1225,8 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
     if (e->compact_ok) {
+        const char* vi = std::getenv("HC_COMPACT_INLINE");
+        if (vi && std::atoi(vi) == 0) e->compact_inline = false;
         const char* v = std::getenv("HC_COMPACT_DIRECT");            // diagnostic: 0 = forces come back through a copy node
         if (!(v && std::atoi(v) == 0)) {
             void* dp = nullptr;
@@ -1599,7 +1610,7 @@ hc_status hc_step(hc_ensemble* e, double t, const double* pose, const double* ve
                 if (e->h_force_dev) e->hdr_h.force2 = e->h_force_dev;
                 std::memcpy(hs, &e->hdr_h, sizeof(StepHeader));
                 e->run_compact();
-                e->prof.kernel_launches += e->phase1_launches + 1;       // (the append rides in the plan kernel)
+                e->prof.kernel_launches += e->phase1_launches + (e->graph_c_inline ? 0 : 1);   // (no append kernel; no plan kernel either when the convolutions plan inline)
                 e->prof.hydrostatics_calls++; e->prof.radiation_calls++; e->prof.waves_calls++;
                 e->prev_time = t;
                 e->force_valid = true;

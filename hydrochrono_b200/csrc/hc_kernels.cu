@@ -61,6 +61,93 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // k_prestep
 // ------------------------------------------------------------------------------------------
 
+// Bracket + weights of radiation lag s at the step described by h (hydro_forces.cpp:601-610,343-381).  History index
+// i (0 = newest) lives in ring slot (head - i) mod cap; entry 0 is this step (time h.t: its slot may still be on its way
+// into the ring, so it is taken from the header).
+struct RadLagPlan { int slot_new, slot_old, lead; double wn, wo, wd, head_w; };
+__device__ __forceinline__ RadLagPlan plan_radiation_lag(const StepHeader& h, const double* __restrict__ times,
+                                                         const double* __restrict__ rirf_t,
+                                                         const double* __restrict__ rirf_w, const int s) {
+    auto hist_time = [&](int i) -> double {
+        if (i == 0) return h.t;
+        int sl = h.head - i;
+        if (sl < 0) sl += h.cap;
+        return times[sl];
+    };
+    RadLagPlan r{0, 0, 0, 0.0, 0.0, 0.0, 0.0};
+    if (h.len <= 1) return r;
+    const double q = h.t - rirf_t[s];                            // rirf_query_time, :601
+    // AdvanceToBracket (:374-381): smallest i with time(i+1) <= q, i+1 < len
+    const double t_oldest = hist_time(h.len - 1);
+    if (!(t_oldest <= q)) return r;
+    // The answer is unique for monotone times, so any search finds the same index.  Near-uniform steps: guess it
+    // from the mean step and walk a few entries (2 dependent loads instead of 13); otherwise bisect.
+    int lo = 0, hi = h.len - 2;                                  // answer in [lo, hi]
+    bool found = false;
+    const double dt_mean = (h.t - t_oldest) / (double)(h.len - 1);
+    if (dt_mean > 0.0) {
+        int i = (int)ceil((h.t - q) / dt_mean) - 1;
+        i = max(0, min(i, h.len - 2));
+        int probes = 0;
+        while (i > 0 && probes < 4 && hist_time(i) <= q) { --i; ++probes; }
+        while (i < h.len - 2 && probes < 8 && hist_time(i + 1) > q) { ++i; ++probes; }
+        if (hist_time(i + 1) <= q && (i == 0 || hist_time(i) > q)) { lo = i; found = true; }
+    }
+    if (!found) {
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (hist_time(mid + 1) <= q) hi = mid; else lo = mid + 1;
+        }
+    }
+    const double newer = hist_time(lo), older = hist_time(lo + 1);
+    // InterpolateVelocity6D (:343-371)
+    double wn = 0.0, wo = 0.0;
+    if (q == older) { wo = 1.0; wn = 0.0; }
+    else if (q == newer) { wn = 1.0; wo = 0.0; }
+    else if (q > older && q < newer) {
+        const double delta = newer - older;
+        wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
+        wn = 1.0 - wo;
+        if (h.snap > 0.0) {                                      // optional near-exact-hit snapping
+            if (wo <= h.snap) { wo = 0.0; wn = 1.0; }
+            else if (wn <= h.snap) { wn = 0.0; wo = 1.0; }
+        }
+    } else return r;                                             // cannot happen for monotone times
+    r.wd = rirf_w[s];                                            // step_width == 0 -> skipped (:622-625)
+    r.slot_new = h.head - lo; if (r.slot_new < 0) r.slot_new += h.cap;
+    r.slot_old = h.head - lo - 1; if (r.slot_old < 0) r.slot_old += h.cap;
+    r.wn = wn; r.wo = wo;
+    if (lo == 0) {
+        // The newer bracket sample is THIS step's velocity, which may still be on its way to the device: its share
+        // (K w)[s] * (wn * v_now)  is added by k_finalize, the convolution kernel only sees the older sample.
+        // (lags with lo == 0 are the leading lags)
+        r.lead = 1;
+        r.head_w = wn;
+        r.wn = 0.0;
+    }
+    return r;
+}
+
+// Bracket of excitation tap j (wave_types.cpp:796-829): largest i with eta_t[i] <= t - tau_j; exact hit or lerp.
+struct ExcTapPlan { int idx; double w1, w2; };
+__device__ __forceinline__ ExcTapPlan plan_excitation_tap(const double t, const double* __restrict__ tau,
+                                                          const double* __restrict__ eta_t, const int n_eta,
+                                                          const double eta_dt, const int j) {
+    const double tt = t - tau[j];
+    int i = (int)floor((tt - eta_t[0]) / eta_dt);
+    i = max(0, min(i, n_eta - 1));
+    while (i > 0 && eta_t[i] > tt) --i;
+    while (i + 1 < n_eta && eta_t[i + 1] <= tt) ++i;
+    ExcTapPlan r{i, 1.0, 0.0};
+    const double t1 = eta_t[i];
+    if (tt != t1 && i + 1 < n_eta) {
+        const double t2 = eta_t[i + 1];
+        r.w1 = (t2 - tt) / (t2 - t1);
+        r.w2 = 1.0 - r.w1;
+    }
+    return r;
+}
+
 // mode bit 0: history append (needs the step's velocities); bit 1: interpolation plans (need the header only).
 __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int mode) {
     const StepHeader h = *a.hdr;
@@ -77,80 +164,22 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int 
         }
         if (tid == 0) a.times[h.head] = h.t;
     }
-
-    // (2) radiation plan.  History index i (0 = newest) lives in ring slot (head - i) mod cap; entry 0 is this
-    //     step (time h.t, written above by another thread, so it is taken from the header).
-    auto hist_time = [&](int i) -> double {
-        if (i == 0) return h.t;
-        int s = h.head - i;
-        if (s < 0) s += h.cap;
-        return a.times[s];
-    };
     if (!(mode & 2)) return;
+
+    // (2) radiation plan
     for (int s = tid; s < a.L; s += nth) {
-        int slot_new = 0, slot_old = 0;
-        double wn = 0.0, wo = 0.0, wd = 0.0, head_w = 0.0;
-        int lead = 0;
-        if (h.len > 1) {
-            const double q = h.t - a.rirf_t[s];                      // rirf_query_time, :601
-            // AdvanceToBracket (:374-381): smallest i with time(i+1) <= q, i+1 < len
-            if (hist_time(h.len - 1) <= q) {
-                int lo = 0, hi = h.len - 2;                          // answer in [lo, hi]
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (hist_time(mid + 1) <= q) hi = mid; else lo = mid + 1;
-                }
-                const double newer = hist_time(lo), older = hist_time(lo + 1);
-                // InterpolateVelocity6D (:343-371)
-                bool ok = true;
-                if (q == older) { wo = 1.0; wn = 0.0; }
-                else if (q == newer) { wn = 1.0; wo = 0.0; }
-                else if (q > older && q < newer) {
-                    const double delta = newer - older;
-                    wo = (delta != 0.0) ? ((newer - q) / delta) : 0.0;
-                    wn = 1.0 - wo;
-                    if (h.snap > 0.0) {                              // optional near-exact-hit snapping
-                        if (wo <= h.snap) { wo = 0.0; wn = 1.0; }
-                        else if (wn <= h.snap) { wn = 0.0; wo = 1.0; }
-                    }
-                } else ok = false;                                   // cannot happen for monotone times
-                if (ok) {
-                    wd = a.rirf_w[s];                                // step_width == 0 -> skipped (:622-625)
-                    slot_new = h.head - lo; if (slot_new < 0) slot_new += h.cap;
-                    slot_old = h.head - lo - 1; if (slot_old < 0) slot_old += h.cap;
-                    if (lo == 0) {
-                        lead = 1;
-                        // The newer bracket sample is THIS step's velocity, which may still be on its way to the
-                        // device: its share  (K w)[s] * (wn * v_now)  is added by k_finalize, the convolution
-                        // kernel only sees the older sample.  (lags with lo == 0 are the leading lags)
-                        head_w = wn;
-                        wn = 0.0;
-                    }
-                }
-            }
-        }
-        a.pr_new[s] = slot_new; a.pr_old[s] = slot_old;
-        a.pr_wn[s] = wn; a.pr_wo[s] = wo; a.pr_wd[s] = wd;
-        a.pr_head[s] = head_w;
-        a.pr_lead[s] = lead;
+        const RadLagPlan r = plan_radiation_lag(h, a.times, a.rirf_t, a.rirf_w, s);
+        a.pr_new[s] = r.slot_new; a.pr_old[s] = r.slot_old;
+        a.pr_wn[s] = r.wn; a.pr_wo[s] = r.wo; a.pr_wd[s] = r.wd;
+        a.pr_head[s] = r.head_w;
+        a.pr_lead[s] = r.lead;
     }
 
-    // (3) excitation plan (wave_types.cpp:796-829): largest i with eta_t[i] <= t - tau_j; exact hit or lerp.
+    // (3) excitation plan
     for (int g = 0; g < a.ngroups; ++g) {
         for (int j = tid; j < a.Le[g]; j += nth) {
-            const double tt = h.t - a.tau[g][j];
-            int i = (int)floor((tt - a.eta_t[0]) / a.eta_dt);
-            i = max(0, min(i, a.n_eta - 1));
-            while (i > 0 && a.eta_t[i] > tt) --i;
-            while (i + 1 < a.n_eta && a.eta_t[i + 1] <= tt) ++i;
-            double w1 = 1.0, w2 = 0.0;
-            const double t1 = a.eta_t[i];
-            if (tt != t1 && i + 1 < a.n_eta) {
-                const double t2 = a.eta_t[i + 1];
-                w1 = (t2 - tt) / (t2 - t1);
-                w2 = 1.0 - w1;
-            }
-            a.pe_idx[g][j] = i; a.pe_w1[g][j] = w1; a.pe_w2[g][j] = w2;
+            const ExcTapPlan r = plan_excitation_tap(h.t, a.tau[g], a.eta_t, a.n_eta, a.eta_dt, j);
+            a.pe_idx[g][j] = r.idx; a.pe_w1[g][j] = r.w1; a.pe_w2[g][j] = r.w2;
         }
     }
 }
@@ -158,9 +187,16 @@ __global__ void __launch_bounds__(256) k_prestep(const PrestepArgs a, const int 
 // ------------------------------------------------------------------------------------------
 // k_radiation<D>: one CTA = kTileInst instances x one lag chunk.  acc[ipt][row] over all D columns.
 // ------------------------------------------------------------------------------------------
-struct RadPlanPtrs { const int* nw; const int* od; const double* wn; const double* wo; const double* wd; };
+struct RadPlanPtrs {
+    const int* nw; const int* od; const double* wn; const double* wo; const double* wd;
+    // INLINE only: what k_finalize needs of the plan (leading lags), and the real instance count for the append
+    double* out_wd; double* out_head; int* out_lead; int B;
+};
 
-template <int D>
+// INLINE (the compact graph of a small ensemble, where every kernel level costs as much as the kernel): each CTA plans
+// the lags of its own chunk instead of reading k_prestep's arrays, and the CTAs of chunk 0 append the step's sample to
+// the history (no kernel of the step reads that row) -- the step then has no k_prestep level at all.
+template <int D, bool INLINE = false>
 __global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const RadiationArgs a, const RadPlanPtrs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int s0 = blockIdx.y * a.chunk;
@@ -179,9 +215,27 @@ __global__ void __launch_bounds__(kThreads, (D <= 12) ? 2 : 1) k_radiation(const
         mbar_expect_tx(bar, bytes);
         bulk_g2s(Ks, a.K + (size_t)s0 * D * D, bytes, bar);
     }
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        s_wn[i] = p.wn[s0 + i]; s_wo[i] = p.wo[s0 + i]; s_wd[i] = p.wd[s0 + i];
-        s_new[i] = p.nw[s0 + i]; s_old[i] = p.od[s0 + i];
+    if constexpr (INLINE) {
+        const StepHeader h = *a.hdr;
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+            const RadLagPlan r = plan_radiation_lag(h, a.times, a.rirf_t, a.rirf_w, s0 + i);
+            s_wn[i] = r.wn; s_wo[i] = r.wo; s_wd[i] = r.wd; s_new[i] = r.slot_new; s_old[i] = r.slot_old;
+            if (blockIdx.x == 0) { p.out_wd[s0 + i] = r.wd; p.out_head[s0 + i] = r.head_w; p.out_lead[s0 + i] = r.lead; }
+        }
+        if (blockIdx.y == 0) {                                   // append (hydro_forces.cpp:560-574)
+            double* row = const_cast<double*>(a.hist) + (size_t)h.head * D * a.Bp;
+            const int bt = blockIdx.x * kTileInst;
+            for (int i = threadIdx.x; i < D * kTileInst; i += blockDim.x) {
+                const int c = i / kTileInst, b = bt + (i - c * kTileInst);
+                if (b < a.Bp) row[(size_t)c * a.Bp + b] = (b < p.B) ? h.vel[(size_t)b * D + c] : 0.0;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<double*>(a.times)[h.head] = h.t;
+        }
+    } else {
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+            s_wn[i] = p.wn[s0 + i]; s_wo[i] = p.wo[s0 + i]; s_wd[i] = p.wd[s0 + i];
+            s_new[i] = p.nw[s0 + i]; s_old[i] = p.od[s0 + i];
+        }
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -972,7 +1026,7 @@ __global__ void __launch_bounds__(kThreads) k_radiation_generic(const RadiationA
 // ------------------------------------------------------------------------------------------
 struct ExcPlanPtrs { const int* idx; const double* w1; const double* w2; };
 
-template <int ND>
+template <int ND, bool INLINE = false>     // INLINE: the CTA plans its own taps (compact graph, see k_radiation)
 __global__ void __launch_bounds__(kThreads, 2) k_excitation(const ExcitationArgs a, const ExcGroup g, const ExcPlanPtrs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int j0 = blockIdx.y * a.chunk;
@@ -989,8 +1043,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_excitation(const ExcitationArgs
         mbar_expect_tx(bar, bytes);
         bulk_g2s(Fs, g.fw + (size_t)j0 * ND, bytes, bar);
     }
-    for (int i = threadIdx.x; i < nj; i += blockDim.x) {
-        s_w1[i] = p.w1[j0 + i]; s_w2[i] = p.w2[j0 + i]; s_idx[i] = p.idx[j0 + i];
+    if constexpr (INLINE) {
+        const double t = a.hdr->t;
+        for (int i = threadIdx.x; i < nj; i += blockDim.x) {
+            const ExcTapPlan r = plan_excitation_tap(t, g.tau, a.eta_t, a.n_eta, a.eta_dt, j0 + i);
+            s_w1[i] = r.w1; s_w2[i] = r.w2; s_idx[i] = r.idx;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nj; i += blockDim.x) {
+            s_w1[i] = p.w1[j0 + i]; s_w2[i] = p.w2[j0 + i]; s_idx[i] = p.idx[j0 + i];
+        }
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -1438,6 +1500,20 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
     return v;
 }
 
+// lane's share of n strided partials: entries lane, lane + 32, ... in ascending order, four loads in flight at a time
+__device__ __forceinline__ double lane_sum_strided(const double* p, const size_t stride, const int n, const int lane) {
+    double s = 0.0;
+    for (int ch = lane; ch < n; ch += 128) {
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (ch + 32 * i < n) ? p[(size_t)(ch + 32 * i) * stride] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (ch + 32 * i < n) s = __dadd_rn(s, v[i]);
+    }
+    return s;
+}
+
 __global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
                                                        const __grid_constant__ FinalizeGroups eg) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1449,8 +1525,7 @@ __global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, con
     if (!a.waves_only) {
         const double* p = a.rad_partial + (size_t)d * a.Bp + b;
         const size_t stride = (size_t)D * a.Bp;
-        for (int ch = lane; ch < a.rad_nchunk; ch += 32) fr = __dadd_rn(fr, p[(size_t)ch * stride]);
-        fr = warp_sum_fixed(fr);
+        fr = warp_sum_fixed(lane_sum_strided(p, stride, a.rad_nchunk, lane));
     }
     if (a.wave_mode == 2 && h.exc_src == 1) {
         const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
@@ -1463,9 +1538,7 @@ __global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, con
             if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
             const double* p = a.exc_partial + ((size_t)eg.chunk0[g] * a.exc_ndmax + (d - eg.dof0[g])) * a.Bp + b;
             const size_t stride = (size_t)a.exc_ndmax * a.Bp;
-            double s = 0.0;
-            for (int ch = lane; ch < eg.nchunk[g]; ch += 32) s = __dadd_rn(s, p[(size_t)ch * stride]);
-            fw = __dadd_rn(fw, warp_sum_fixed(s));
+            fw = __dadd_rn(fw, warp_sum_fixed(lane_sum_strided(p, stride, eg.nchunk[g], lane)));
         }
     }
     const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
@@ -1541,23 +1614,34 @@ size_t excitation_smem_bytes(int nd, int chunk) {
     return 16 + (size_t)chunk * nd * 8 + (size_t)chunk * 2 * 8 + (size_t)chunk * 4 + 16;
 }
 
-template <int D>
+template <int D, bool INLINE>
 static cudaError_t launch_rad_t(const RadiationArgs& a, const RadPlanPtrs& p, dim3 grid, size_t smem, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_radiation<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_radiation<D, INLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
-    k_radiation<D><<<grid, kThreads, smem, st>>>(a, p);
+    k_radiation<D, INLINE><<<grid, kThreads, smem, st>>>(a, p);
     return cudaGetLastError();
 }
 
+bool radiation_plans_inline(const RadiationArgs& a) {      // which launch_radiation dispatches take an InlinePlan
+    return (a.D == 6 || a.D == 12) && a.Khyb == nullptr && a.Kfrag == nullptr;
+}
+
 cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const int* pr_old, const double* pr_wn,
-                             const double* pr_wo, const double* pr_wd, cudaStream_t st) {
-    RadPlanPtrs p{pr_new, pr_old, pr_wn, pr_wo, pr_wd};
+                             const double* pr_wo, const double* pr_wd, cudaStream_t st, const InlinePlan* ip) {
+    RadPlanPtrs p{pr_new, pr_old, pr_wn, pr_wo, pr_wd, nullptr, nullptr, nullptr, 0};
+    if (ip) {
+        if (!radiation_plans_inline(a)) return cudaErrorInvalidValue;
+        p.out_wd = ip->pr_wd; p.out_head = ip->pr_head; p.out_lead = ip->pr_lead; p.B = ip->B;
+        dim3 gridi((a.Bp + kTileInst - 1) / kTileInst, a.nchunk, 1);
+        const size_t smemi = radiation_smem_bytes(a.D, a.chunk);
+        return a.D == 6 ? launch_rad_t<6, true>(a, p, gridi, smemi, st) : launch_rad_t<12, true>(a, p, gridi, smemi, st);
+    }
     dim3 grid((a.Bp + kTileInst - 1) / kTileInst, a.nchunk, 1);
     const size_t smem = radiation_smem_bytes(a.D, a.chunk);
     if (a.D == 12 && a.Khyb != nullptr) {
@@ -1587,8 +1671,8 @@ cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const in
         return cudaGetLastError();
     }
     switch (a.D) {
-        case 6: return launch_rad_t<6>(a, p, grid, smem, st);
-        case 12: return launch_rad_t<12>(a, p, grid, smem, st);
+        case 6: return launch_rad_t<6, false>(a, p, grid, smem, st);
+        case 12: return launch_rad_t<12, false>(a, p, grid, smem, st);
         default:
             grid.z = a.D / 6;
             k_radiation_generic<<<grid, kThreads, 0, st>>>(a, p);
@@ -1596,29 +1680,34 @@ cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const in
     }
 }
 
-template <int ND>
+template <int ND, bool INLINE>
 static cudaError_t launch_exc_t(const ExcitationArgs& a, const ExcGroup& g, const ExcPlanPtrs& p, dim3 grid, size_t smem,
                                 cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_excitation<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_excitation<ND, INLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
-    k_excitation<ND><<<grid, kThreads, smem, st>>>(a, g, p);
+    k_excitation<ND, INLINE><<<grid, kThreads, smem, st>>>(a, g, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const int* idx, const double* w1,
-                              const double* w2, cudaStream_t st) {
+                              const double* w2, cudaStream_t st, bool plan_inline) {
     ExcPlanPtrs p{idx, w1, w2};
     dim3 grid((a.Bp + kTileInst - 1) / kTileInst, g.nchunk, 1);
     const size_t smem = excitation_smem_bytes(g.nd, a.chunk);
+    if (plan_inline) {
+        if (g.nd == 6) return launch_exc_t<6, true>(a, g, p, grid, smem, st);
+        if (g.nd == 12) return launch_exc_t<12, true>(a, g, p, grid, smem, st);
+        return cudaErrorInvalidValue;
+    }
     switch (g.nd) {
-        case 6: return launch_exc_t<6>(a, g, p, grid, smem, st);
-        case 12: return launch_exc_t<12>(a, g, p, grid, smem, st);
+        case 6: return launch_exc_t<6, false>(a, g, p, grid, smem, st);
+        case 12: return launch_exc_t<12, false>(a, g, p, grid, smem, st);
         default: return cudaErrorInvalidValue;   // groups are formed with nd in {6, 12} only
     }
 }

@@ -148,10 +148,15 @@ size_t excitation_smem_bytes(int nd, int chunk);
 cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st);
 int radiation_ctas_per_sm(int D, int chunk);
 int excitation_ctas_per_sm(int nd, int chunk);
+// Compact graph of a small ensemble: the convolution kernels plan their own lags / taps and the radiation kernel
+// appends the step's sample, so the step has no k_prestep level.  What k_finalize needs of the radiation plan (the
+// leading lags) is written to these arrays by the radiation kernel.
+struct InlinePlan { double* pr_wd; double* pr_head; int* pr_lead; int B; };
+bool radiation_plans_inline(const RadiationArgs& a);
 cudaError_t launch_radiation(const RadiationArgs& a, const int* pr_new, const int* pr_old, const double* pr_wn,
-                             const double* pr_wo, const double* pr_wd, cudaStream_t st);
+                             const double* pr_wo, const double* pr_wd, cudaStream_t st, const InlinePlan* ip = nullptr);
 cudaError_t launch_excitation(const ExcitationArgs& a, const ExcGroup& g, const int* idx, const double* w1,
-                              const double* w2, cudaStream_t st);
+                              const double* w2, cudaStream_t st, bool plan_inline = false);
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st);
 cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st);

@@ -201,15 +201,18 @@ def test_rm3_irregular_ensemble(rm3, snap, lookahead, rad_kernel):
     # bit-faithful bracketing differs from the oracle only by summation order / FMA contraction
     assert worst < (1e-11 if snap == 0.0 else 1e-9), worst
     launches = ens.profile()["kernel_launches"]
-    # small ensemble through hc_step = the compact graph: plan + append in one kernel, radiation, finalize (+ excitation)
-    if lookahead in (2, 4):  # 700 steps = 88 blocks of 8: 3 kernels per step + 3 per block (+ eta synthesis)
-        assert launches == 1 + 3 * 700 + 3 * 88, launches
+    # small ensemble through hc_step = the compact graph.  rad_kernel 1 (k_radiation<12>): the convolution kernels plan
+    # their own lags and the radiation kernel appends -> radiation, finalize (+ excitation) per step; the DMMA / hybrid
+    # radiation kernels keep a plan + append kernel in front
+    k = 2 if rad_kernel == 1 else 3
+    if lookahead in (2, 4):  # 700 steps = 88 blocks of 8: k kernels per step + 3 per block (+ eta synthesis)
+        assert launches == 1 + k * 700 + 3 * 88, launches
     elif lookahead == 3:  # background mode: one more block is prefetched on the side stream
-        assert launches == 1 + 3 * 700 + 3 * 89, launches
+        assert launches == 1 + k * 700 + 3 * 89, launches
     elif lookahead == 5:  # background DMMA mode: prefetched blocks are built in two halves (plan 2 + 2 launches); the
-        assert launches == 1 + 3 * 700 + 3 + 4 * 88 - 1, launches      # last one's second half is still pending
+        assert launches == 1 + k * 700 + 3 + 4 * 88 - 1, launches      # last one's second half is still pending
     else:
-        assert launches == 1 + 4 * 700, launches
+        assert launches == 1 + (k + 1) * 700, launches
 
 
 @pytest.mark.parametrize("snap,exc_la,m,rad_la,nb", [(1e-8, 5, 6, 2, 2), (1e-8, 1, 6, 3, 2), (1e-8, 1, 6, 2, 2),
@@ -247,16 +250,17 @@ def test_rm3_radiation_lookahead(rm3, snap, exc_la, m, rad_la, nb):
     st = ens.rad_block_stats()
     ngroups = 3 if nb == 3 else 1       # excitation IRF groups: bodies merged for D = 6 / 12, one per body otherwise
     nblocks = -(-699 // (8 * m))
+    per_step = (2 if nb < 3 else 3) + ngroups   # compact graph: radiation (+ plan kernel for D = 18), excitation, finalize
     if snap == 0.0:
-        assert launches == 1 + (3 + ngroups) * 700 and st["steps_served"] == 0, (launches, st)
+        assert launches == 1 + per_step * 700 and st["steps_served"] == 0, (launches, st)
         return
     assert st["steps_served"] == 699, st                # every step but the first (empty history)
     # rad_la = 2 plans one block ahead (one more pass started than blocks served)
     assert st["launches"] == nblocks + (1 if rad_la == 2 else 0), st
-    if exc_la == 1 and rad_la == 3:     # step 0 per-step (4), then 699 steps of 3 kernels + one whole pass per block
-        assert launches == 1 + (3 + ngroups) + (2 + ngroups) * 699 + nblocks, launches
+    if exc_la == 1 and rad_la == 3:     # step 0 per-step, then 699 steps of 3 kernels + one whole pass per block
+        assert launches == 1 + per_step + (2 + ngroups) * 699 + nblocks, launches
     elif exc_la == 1:                   # + one slice of the next block's pass after every step
-        assert launches <= 1 + (3 + ngroups) + (2 + ngroups) * 699 + 1 + 699, launches
+        assert launches <= 1 + per_step + (2 + ngroups) * 699 + 1 + 699, launches
 
 
 @pytest.mark.parametrize("rad_la,snap", [(1, 0.0), (1, 1e-8), (2, 1e-8)])
