@@ -1758,7 +1758,7 @@ cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    if (a.B <= kFinalizeWarpMaxB)      // small ensemble: a warp per (dof, instance)
+    if ((long long)a.B * a.D <= kFinalizeWarpMaxItems)      // small ensemble: a warp per (dof, instance)
         k_finalize_warp<<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);
     else
         k_finalize<<<(a.D * a.Bp + 255) / 256, 256, 0, st>>>(a, hs, eg);

@@ -396,6 +396,21 @@ def test_irregular_dt_and_ring_growth(sphere):
     assert ens.history_len() == insts[0].history_len() > 300
 
 
+def test_bracket_search_with_gaps_and_bursts(sphere):
+    """The bracket search guesses a lag's history index from the mean step and walks a few entries before it bisects
+    (hydro_forces.cpp:374-381 is a linear walk; the index is unique either way).  A long pause, a burst of tiny steps
+    and a change of step size put the guess far off, on both sides, for most lags."""
+    T, O = sphere
+    ens = hc.Ensemble(T, batch=2, dt_hint=0.01)
+    insts = [orc.Instance(O) for _ in range(2)]
+    dts = np.concatenate([np.full(300, 0.01), [0.8], np.full(400, 0.001), np.full(250, 0.02), [2.5], np.full(120, 0.013)])
+    times = np.concatenate([[0.0], np.cumsum(dts)])
+    (tot, hs, rad, wv), (rtot, rhs, rrad, rwv) = _run_pair(ens, insts, times, 6)
+    _assert_parity(rad, rrad, "radiation, gaps and bursts")
+    _assert_parity(tot, rtot, "total, gaps and bursts")
+    assert ens.history_len() == insts[0].history_len()
+
+
 def test_gravity_vector_and_body_count_generic_path():
     """3-body system (D = 18) runs the run-time-D radiation kernel; tilted gravity exercises the buoyancy cross term."""
     raw = synth.make_tables(num_bodies=3, rirf_steps=301, rirf_duration=15.0, exc_irf_steps=201, exc_half_window=10.0)
