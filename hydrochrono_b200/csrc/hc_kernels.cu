@@ -1487,63 +1487,68 @@ __global__ void __launch_bounds__(256) k_finalize(const FinalizeArgs a, const __
     if (h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
 }
 
-// k_finalize_warp: the same for SMALL ensembles (the drop-in B = 1 TestHydro): there the lag / tap chunks are short so
+// k_finalize_warp<G>: the same for SMALL ensembles (the drop-in B = 1 TestHydro): there the lag / tap chunks are short so
 // that the convolution kernels have CTAs to spread over, which leaves hundreds of partials per (dof, instance) -- 251 +
 // 286 for the RM3 shape -- and k_finalize's one thread per item sums them as one dependent chain (63 us cold, most of a
-// B = 1 step).  Here one WARP owns an item: lane l sums partials l, l + 32, ... in ascending order, a butterfly of
-// shuffles (symmetric, so every lane holds the same bits) adds the 32 lane sums, then the item is finished as above.
-// Deterministic; the association differs from k_finalize's, so the two agree to rounding (1e-16 relative), not bitwise --
-// which kernel serves an ensemble depends only on its size.
-__device__ __forceinline__ double warp_sum_fixed(double v) {
+// B = 1 step).  Here G lanes share an item: lane-group member `sub` sums partials sub, sub + G, ... in ascending order
+// (8 loads in flight), a butterfly of shuffles over the group (symmetric, so every member holds the same bits) adds the
+// G sums, then the item is finished as above.  G = 32 (one item per warp) is what is launched.  Deterministic; the
+// association differs from k_finalize's, so the results agree to rounding (1e-16 relative), not bitwise -- which kernel
+// serves an ensemble depends only on its size.
+template <int G>
+__device__ __forceinline__ double group_sum_fixed(double v) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    for (int off = 16; off >= 32 / G; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
     return v;
 }
 
-// lane's share of n strided partials: entries lane, lane + 32, ... in ascending order, four loads in flight at a time
-__device__ __forceinline__ double lane_sum_strided(const double* p, const size_t stride, const int n, const int lane) {
+// member's share of n strided partials: entries sub, sub + G, ... in ascending order, eight loads in flight at a time
+template <int G>
+__device__ __forceinline__ double member_sum_strided(const double* p, const size_t stride, const int n, const int sub,
+                                                     const bool live) {
     double s = 0.0;
-    for (int ch = lane; ch < n; ch += 128) {
-        double v[4];
+    if (!live) return s;
+    for (int ch = sub; ch < n; ch += 8 * G) {
+        double v[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (ch + 32 * i < n) ? p[(size_t)(ch + 32 * i) * stride] : 0.0;
+        for (int i = 0; i < 8; ++i) v[i] = (ch + G * i < n) ? p[(size_t)(ch + G * i) * stride] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (ch + 32 * i < n) s = __dadd_rn(s, v[i]);
+        for (int i = 0; i < 8; ++i)
+            if (ch + G * i < n) s = __dadd_rn(s, v[i]);
     }
     return s;
 }
 
+template <int G>
 __global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
                                                        const __grid_constant__ FinalizeGroups eg) {
+    constexpr int IPW = 32 / G;                        // items (consecutive instances of one dof) per warp
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int d = w / a.B, b = w - d * a.B;            // real instances only
+    const int bi = lane % IPW, sub = lane / IPW;
+    const int wpd = (a.B + IPW - 1) / IPW;             // warps per dof
+    const int d = w / wpd, b = (w - d * wpd) * IPW + bi;
     if (d >= a.D) return;                              // (uniform per warp)
+    const bool live = b < a.B;
     const StepHeader h = *a.hdr;
     const int D = a.D;
     double fr = 0.0, fw = 0.0;
-    if (!a.waves_only) {
-        const double* p = a.rad_partial + (size_t)d * a.Bp + b;
-        const size_t stride = (size_t)D * a.Bp;
-        fr = warp_sum_fixed(lane_sum_strided(p, stride, a.rad_nchunk, lane));
-    }
+    if (!a.waves_only)
+        fr = group_sum_fixed<G>(member_sum_strided<G>(a.rad_partial + (size_t)d * a.Bp + b, (size_t)D * a.Bp, a.rad_nchunk, sub, live));
     if (a.wave_mode == 2 && h.exc_src == 1) {
         const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
         const double* p = a.exc_cache + (((size_t)buf * a.exc_S * kLaT + pos) * D + d) * a.Bp + b;
-        const size_t sstride = (size_t)kLaT * D * a.Bp;
-        for (int sg = lane; sg < a.exc_S; sg += 32) fw = __dadd_rn(fw, p[(size_t)sg * sstride]);
-        fw = warp_sum_fixed(fw);
+        fw = group_sum_fixed<G>(member_sum_strided<G>(p, (size_t)kLaT * D * a.Bp, a.exc_S, sub, live));
     } else if (a.wave_mode == 2) {
         for (int g = 0; g < a.exc_ngroups; ++g) {
             if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
             const double* p = a.exc_partial + ((size_t)eg.chunk0[g] * a.exc_ndmax + (d - eg.dof0[g])) * a.Bp + b;
-            const size_t stride = (size_t)a.exc_ndmax * a.Bp;
-            fw = __dadd_rn(fw, warp_sum_fixed(lane_sum_strided(p, stride, eg.nchunk[g], lane)));
+            fw = __dadd_rn(fw, group_sum_fixed<G>(member_sum_strided<G>(p, (size_t)a.exc_ndmax * a.Bp, eg.nchunk[g], sub, live)));
         }
     }
+    if (!live) return;
     const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
-                                      a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6), &fr, &fw, lane == 0);
-    if (lane == 0 && h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
+                                      a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6), &fr, &fw, sub == 0);
+    if (sub == 0 && h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1758,8 +1763,11 @@ cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    if ((long long)a.B * a.D <= kFinalizeWarpMaxItems)      // small ensemble: a warp per (dof, instance)
-        k_finalize_warp<<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);
+    if ((long long)a.B * a.D <= kFinalizeWarpMaxItems) {     // small ensemble: a lane group per (dof, instance)
+        // (G = 8 -- four consecutive instances per warp, sector-efficient rows -- measured slower at every size: 53 vs
+        //  40 us at B = 16, 78 vs 67 us at B = 256: the dependent load rounds per lane count, not the sectors)
+        k_finalize_warp<32><<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);
+    }
     else
         k_finalize<<<(a.D * a.Bp + 255) / 256, 256, 0, st>>>(a, hs, eg);
     return cudaGetLastError();

@@ -1,3 +1,4 @@
 #!/bin/bash
+# round 2: hc_step latency of small ensembles (RM3 shape, irregular waves, full window, default options) vs ensemble size
 mkdir -p gpurun_out
-for B in 16 40 80 256; do for Dm in 1 0; do echo -n "direct=$Dm "; HC_COMPACT_DIRECT=$Dm python profiles/b_small_probe.py $B 1000 1500; done; done 2>&1 | tee gpurun_out/r02w_direct_vs_b.txt
+for B in 1 16 80 256; do python profiles/b_small_probe.py $B 1000 6010; done 2>&1 | tee gpurun_out/r02w_latency_vs_b.txt
