@@ -16,6 +16,9 @@
 //   k_finalize    reduces the lag-chunk partials in fixed order, adds hydrostatics and regular-wave
 //                 excitation, forms total = hydrostatic - radiation + waves
 //                                                        src/hydro_forces.cpp:263-322,758-760; src/wave_types.cpp:315-327
+//   k_radiation<D, true> / k_excitation<ND, true> / k_finalize_warp   the same three for a small ensemble's one-graph
+//                 step (the drop-in B = 1 TestHydro): convolution CTAs plan their own lags / taps and append the sample
+//                 (no k_prestep level); a warp, not a thread, per (dof, instance) in the finalize
 //   k_eta         free-surface elevation synthesis for every realisation
 //                                                        src/wave_types.cpp:14-59,717-769
 //   k_added_mass_mv  R += c * M * w, batched             src/chloadaddedmass.cpp:55-71
