@@ -319,6 +319,14 @@ class Ensemble:
         _check(lib.hc_waves_irregular(self._h, C.byref(p), s.ctypes.data_as(_capi.ip) if s is not None else None,
                                       _dp(hs), _dp(tp)))
 
+    def set_waves_series(self, dt, time, eta):
+        """Imported free-surface elevation (IrregularWaveParams::eta_file_path_, wave_types.cpp:480-500): time [n] and eta
+        [n] (shared) or [B][n] (per instance); dt = the spacing the excitation IRF is resampled to."""
+        t, e = _f64(time), _f64(eta)
+        if t.ndim != 1 or e.shape[-1] != t.size or e.ndim not in (1, 2) or (e.ndim == 2 and e.shape[0] != self.batch):
+            raise ValueError("time must be [n] and eta [n] or [batch][n]")
+        _check(lib.hc_waves_irregular_series(self._h, float(dt), t.size, _dp(t), _dp(e), int(e.ndim == 2)))
+
     def irregular_sizes(self):
         nf, ne = C.c_int(), C.c_int()
         le = (C.c_int * self.tables.num_bodies)()

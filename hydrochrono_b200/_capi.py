@@ -100,6 +100,7 @@ SIGNATURES = {
     "hc_waves_regular": (C.c_int, [vp, C.c_int, dp, dp, dp]),
     "hc_irregular_default_params": (None, [C.POINTER(IrregularParams)]),
     "hc_waves_irregular": (C.c_int, [vp, C.POINTER(IrregularParams), ip, dp, dp]),
+    "hc_waves_irregular_series": (C.c_int, [vp, C.c_double, C.c_int, dp, dp, C.c_int]),
     "hc_waves_irregular_sizes": (C.c_int, [vp, ip, ip, ip]),
     "hc_waves_irregular_spectrum": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp]),
     "hc_waves_irregular_eta": (C.c_int, [vp, C.c_int, dp, dp]),
@@ -137,6 +138,7 @@ SIGNATURES = {
     "hc_multi_waves_none": (C.c_int, [vp]),
     "hc_multi_waves_regular": (C.c_int, [vp, C.c_int, dp, dp, dp]),
     "hc_multi_waves_irregular": (C.c_int, [vp, C.POINTER(IrregularParams), ip, dp, dp]),
+    "hc_multi_waves_irregular_series": (C.c_int, [vp, C.c_double, C.c_int, dp, dp, C.c_int]),
     "hc_multi_step": (C.c_int, [vp, C.c_double, vp, vp, dp, vp, ip]),
     "hc_multi_step_device": (C.c_int, [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), dp, C.POINTER(vp)]),
     "hc_multi_get_components": (C.c_int, [vp, dp, dp, dp]),

@@ -199,6 +199,8 @@ struct hc_ensemble {
     int exc_chunk = 0, exc_total_chunks = 0, exc_ndmax = 0;
     DevBuf<double> d_exc_partial, d_eta, d_eta_t, d_omega, d_amp, d_phase;
     std::vector<double> eta_t_h, freqs_h, widths_h, wavenumbers_h;
+    double eta_grid_dt = 0.0;                     // nominal spacing of the eta grid (index guess of the excitation plans)
+    void setup_excitation_groups(double simulation_dt);
     std::vector<double> S_h;          // [nS][nf]  (nS = 1 shared or B)
     std::vector<double> phases_h;     // [B][nf]
     bool per_instance_spectrum = false;
@@ -656,7 +658,7 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
             pa.tau[g] = groups[g]->tau.p; pa.Le[g] = groups[g]->Le;
             pa.pe_idx[g] = groups[g]->idx.p; pa.pe_w1[g] = groups[g]->w1.p; pa.pe_w2[g] = groups[g]->w2.p;
         }
-        pa.eta_t = d_eta_t.p; pa.n_eta = n_eta; pa.eta_dt = ip.simulation_dt;
+        pa.eta_t = d_eta_t.p; pa.n_eta = n_eta; pa.eta_dt = eta_grid_dt;
     }
     if (phase == 1) {
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_BEGIN], stream));
@@ -685,7 +687,7 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
         if (per_step_exc) {
             ExcitationArgs ea{};
             ea.hdr = d_hdr.p; ea.eta = d_eta.p; ea.eta_t = d_eta_t.p; ea.partial = d_exc_partial.p;
-            ea.eta_dt = ip.simulation_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
+            ea.eta_dt = eta_grid_dt; ea.n_eta = n_eta; ea.Bp = Bp; ea.chunk = exc_chunk; ea.ndmax = exc_ndmax;
             for (size_t g = 0; g < groups.size(); ++g) {
                 Group& G = *groups[g];
                 ExcGroup eg{G.tau.p, G.fw.p, G.Le, G.nd, G.dof0, G.chunk0, G.nchunk};
@@ -999,7 +1001,7 @@ int hc_ensemble::enqueue_lookahead_block(int buf, double t0, cudaStream_t st, in
         LookaheadPlanArgs pa{};
         pa.times = d_times; pa.tau = G.tau.p; pa.fw = G.fw.p; pa.eta_t = d_eta_t.p;
         pa.idx = G.la_idx.p; pa.w1 = G.la_w1.p; pa.w2 = G.la_w2.p; pa.taps = G.la_taps.p;
-        pa.eta_dt = ip.simulation_dt; pa.n_eta = n_eta; pa.Le = G.Le; pa.nd = G.nd; pa.T = kLaT;
+        pa.eta_dt = eta_grid_dt; pa.n_eta = n_eta; pa.Le = G.Le; pa.nd = G.nd; pa.T = kLaT;
         pa.row0 = row0; pa.nrows = nrows; pa.frag_order = la_mma ? 1 : 0;
         CUDA_CHECK(launch_lookahead_plan(pa, st));
         LookaheadArgs la{};
@@ -1349,20 +1351,14 @@ void hc_irregular_default_params(hc_irregular_params* p) {
     p->peak_enhancement_factor = 1.0; p->is_normalized = 0; p->seed = 1;
 }
 
-hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const int* seeds, const double* Hs_arr,
-                             const double* Tp_arr) {
-    HC_GUARD_BEGIN
-    if (!p) fail(HC_ERR_INVALID, "null argument");
+// InitializeIRFVectors / ResampleIRF (wave_types.cpp:432-449,572-606) + the excitation groups' device tables; leaves the
+// ensemble in irregular-wave mode with an empty eta.
+void hc_ensemble::setup_excitation_groups(double simulation_dt) {
+    hc_ensemble* e = this;
     const hc_tables& T = *e->T;
-    e->use_device();
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    if (p->simulation_dt <= 0.0) fail(HC_ERR_INVALID, "simulation_dt must be positive for irregular waves");
-    const int B = e->B, Bp = e->Bp, D = e->D;
-    e->ip = *p;
-    // --- InitializeIRFVectors / ResampleIRF (wave_types.cpp:432-449,572-606) ---
-    e->irf = resample_excitation_irf(T, p->simulation_dt);
+    irf = resample_excitation_irf(T, simulation_dt);
     // group bodies that share one IRF time grid bit-for-bit (the usual case: one BEMIO run)
-    e->groups.clear();
+    groups.clear();
     bool all_same = true;
     for (int b = 1; b < T.N; ++b)
         if (e->irf[b].t != e->irf[0].t) all_same = false;
@@ -1409,6 +1405,20 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
     e->la_enabled = false; e->la_blk[0].valid = e->la_blk[1].valid = false; e->la_half_pending = -1;
     if (e->la_stream) CUDA_CHECK(cudaStreamSynchronize(e->la_stream));
     e->drop_graph();
+}
+
+hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const int* seeds, const double* Hs_arr,
+                             const double* Tp_arr) {
+    HC_GUARD_BEGIN
+    if (!p) fail(HC_ERR_INVALID, "null argument");
+    const hc_tables& T = *e->T;
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (p->simulation_dt <= 0.0) fail(HC_ERR_INVALID, "simulation_dt must be positive for irregular waves");
+    const int B = e->B, Bp = e->Bp;
+    e->ip = *p;
+    e->eta_grid_dt = p->simulation_dt;
+    e->setup_excitation_groups(p->simulation_dt);
     const bool have_sea = (Hs_arr || p->wave_height != 0.0) && (Tp_arr || p->wave_period != 0.0);
     // --- eta time grid (CreateFreeSurfaceElevation, wave_types.cpp:717-744) ---
     double t_irf_min = 0.0, t_irf_max = 0.0;
@@ -1482,6 +1492,54 @@ hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const
     // phases/amplitudes are only needed for the synthesis; keep omega/amp small arrays, free the big ones
     e->d_phase.release();
     if (e->per_instance_spectrum) e->d_amp.release();
+    return HC_OK;
+    HC_GUARD_END
+}
+
+// the free-surface elevation imported as a (time, eta) series instead of synthesised from a spectrum
+// (IrregularWaves::ReadEtaFromFile, src/wave_types.cpp:480-500, from InitializeIRFVectors :451-453).  The reference
+// snapshot never fills free_surface_time_sampled_ on this branch although ExcitationConvolution reads it (:784-785);
+// the grid used here is the intended one, the series' own time column.
+hc_status hc_waves_irregular_series(hc_ensemble* e, double simulation_dt, int n, const double* time, const double* eta,
+                                    int per_instance) {
+    HC_GUARD_BEGIN
+    if (!time || !eta) fail(HC_ERR_INVALID, "null argument");
+    if (simulation_dt <= 0.0) fail(HC_ERR_INVALID, "simulation_dt must be positive for irregular waves");
+    if (n < 2) fail(HC_ERR_INVALID, "an eta series needs at least two samples");
+    for (int k = 1; k < n; ++k)
+        if (!(time[k] > time[k - 1])) fail(HC_ERR_INVALID, "eta series: time must be strictly increasing (line " + std::to_string(k + 1) + ")");
+    e->use_device();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const int B = e->B, Bp = e->Bp;
+    hc_irregular_default_params(&e->ip);
+    e->ip.simulation_dt = simulation_dt;
+    e->ip.simulation_duration = time[n - 1] - time[0];
+    e->ip.wave_height = 0.0; e->ip.wave_period = 0.0;
+    e->setup_excitation_groups(simulation_dt);
+    e->eta_t_h.assign(time, time + n);
+    e->eta_grid_dt = (time[n - 1] - time[0]) / double(n - 1);
+    e->n_eta = n;
+    e->d_eta_t.upload(e->eta_t_h);
+    e->d_eta.alloc(size_t(n) * Bp);                            // zero-filled; padded lanes stay zero
+    // eta[sample][instance] on the device: transposed through a bounded pinned staging block
+    const int rows = std::max(1, std::min(n, int((size_t(8) << 20) / (size_t(Bp) * sizeof(double)))));
+    PinBuf stage;
+    stage.alloc(size_t(rows) * Bp * sizeof(double));
+    double* hs = static_cast<double*>(stage.p);
+    for (int k0 = 0; k0 < n; k0 += rows) {
+        const int nk = std::min(rows, n - k0);
+        for (int k = 0; k < nk; ++k) {
+            double* row = hs + size_t(k) * Bp;
+            if (per_instance) for (int b = 0; b < B; ++b) row[b] = eta[size_t(b) * n + k0 + k];
+            else for (int b = 0; b < B; ++b) row[b] = eta[k0 + k];
+        }
+        CUDA_CHECK(cudaMemcpyAsync(e->d_eta.p + size_t(k0) * Bp, hs, size_t(nk) * Bp * sizeof(double), cudaMemcpyHostToDevice,
+                                   e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    e->per_instance_spectrum = false;
+    e->freqs_h.clear(); e->widths_h.clear(); e->wavenumbers_h.clear(); e->S_h.clear(); e->phases_h.clear();
+    e->setup_lookahead();
     return HC_OK;
     HC_GUARD_END
 }

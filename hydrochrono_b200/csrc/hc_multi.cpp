@@ -180,6 +180,15 @@ hc_status hc_multi_waves_irregular(hc_multi_ensemble* m, const hc_irregular_para
     });
 }
 
+hc_status hc_multi_waves_irregular_series(hc_multi_ensemble* m, double simulation_dt, int n, const double* time,
+                                          const double* eta, int per_instance) {
+    if (!time || !eta) { hc::set_last_error("null argument"); return HC_ERR_INVALID; }
+    return m->run([=](hc::Worker& k) {
+        return hc_waves_irregular_series(k.ens, simulation_dt, n, time, per_instance ? eta + size_t(k.first) * n : eta,
+                                         per_instance);
+    });
+}
+
 hc_status hc_multi_step(hc_multi_ensemble* m, double t, const double* pose, const double* vel, const double g[3],
                         double* force, int* recomputed) {
     if (!pose || !vel || !g || !force) { hc::set_last_error("null argument"); return HC_ERR_INVALID; }

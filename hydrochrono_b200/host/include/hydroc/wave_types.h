@@ -141,6 +141,8 @@ class IrregularWaves : public WaveBase {
 
   private:
     void FetchSpectrum() const;
+    /// "time : eta" lines of IrregularWaveParams::eta_file_path_ (reference: src/wave_types.cpp:480-500).
+    static void ReadEtaFromFile(const std::string& path, std::vector<double>& time_data, std::vector<double>& eta_data);
     void FetchComponents() const;
     IrregularWaveParams params_;
     const WaveMode mode_ = WaveMode::irregular;

@@ -7,6 +7,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <sstream>
 #include <stdexcept>
 
 #include "hc_check.h"
@@ -138,9 +139,16 @@ void IrregularWaves::AddH5Data(std::vector<HydroData::IrregularWaveInfo>&, Hydro
 
 void IrregularWaves::Bind(hc_ensemble* ens, const HydroData::SimulationParameters& sim, unsigned int num_bodies) {
     WaveBase::Bind(ens, sim, num_bodies);
-    if (!params_.eta_file_path_.empty())
-        // reference: IrregularWaves::ReadEtaFromFile fills no time grid in this snapshot: unsupported
-        throw std::runtime_error("Unable to open file at: " + params_.eta_file_path_ + ". (eta import is not supported)");
+    if (!params_.eta_file_path_.empty()) {
+        // InitializeIRFVectors (src/wave_types.cpp:451-453): an eta file replaces the spectrum.  The reference snapshot
+        // fills no time grid on this branch; the file's own time column is the grid here.
+        std::vector<double> time, eta;
+        ReadEtaFromFile(params_.eta_file_path_, time, eta);
+        hc_throw_on_error(hc_waves_irregular_series(ens, params_.simulation_dt_, int(time.size()), time.data(), eta.data(), 0));
+        spectrum_fetched_ = false;
+        comp_omega_.clear(); comp_amp_.clear();
+        return;
+    }
     hc_irregular_params q;
     hc_irregular_default_params(&q);
     q.simulation_dt = params_.simulation_dt_;
@@ -157,6 +165,21 @@ void IrregularWaves::Bind(hc_ensemble* ens, const HydroData::SimulationParameter
     hc_throw_on_error(hc_waves_irregular(ens, &q, nullptr, nullptr, nullptr));
     spectrum_fetched_ = false;
     comp_omega_.clear(); comp_amp_.clear();
+}
+
+// "time : eta" per line (src/wave_types.cpp:480-500), same messages
+void IrregularWaves::ReadEtaFromFile(const std::string& path, std::vector<double>& time_data, std::vector<double>& eta_data) {
+    std::ifstream file(path);
+    if (!file) throw std::runtime_error("Unable to open file at: " + path + ".");
+    std::string line;
+    while (std::getline(file, line)) {
+        std::stringstream ss(line);
+        double time = 0.0, eta = 0.0;
+        char delimiter = 0;
+        if (!(ss >> time >> delimiter >> eta) || delimiter != ':') throw std::runtime_error("Could not parse line: " + line + ".");
+        time_data.push_back(time);
+        eta_data.push_back(eta);
+    }
 }
 
 void IrregularWaves::FetchSpectrum() const {
@@ -195,6 +218,12 @@ Eigen::VectorXd IrregularWaves::GetForceAtTime(double t) { return DeviceForce(t)
 
 // per-component omega = 2 pi f and amplitude = sqrt(2 S df) exactly as GetEtaIrregular forms them (:38-40)
 void IrregularWaves::FetchComponents() const {
+    int nf = 0, ne = 0;
+    if (ens_ && hc_waves_irregular_sizes(ens_, &nf, &ne, nullptr) == HC_OK && nf == 0) {
+        // no spectrum (eta imported from a file, or zero wave height): the reference's sums run over empty vectors
+        comp_omega_.clear(); comp_amp_.clear(); phases_.clear(); wavenumbers_.clear();
+        return;
+    }
     FetchSpectrum();
     if (comp_omega_.size() == freqs_.size()) return;
     comp_omega_.resize(freqs_.size()); comp_amp_.resize(freqs_.size());

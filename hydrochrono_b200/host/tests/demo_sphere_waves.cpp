@@ -2,10 +2,12 @@
 // (cf. tests/regression/sphere/reg_waves/sphere_reg_waves_test.cpp and irreg_waves/sphere_irreg_waves_test.cpp):
 // ground + prismatic joint (heave only) + TSDA damper, RegularWave or IrregularWaves attached to TestHydro.
 // usage: demo_sphere_waves <sphere.h5> <out.txt> regular <wave_num 1..10> [duration]
-//        demo_sphere_waves <sphere.h5> <out.txt> irregular [duration]
+//        demo_sphere_waves <sphere.h5> <out.txt> irregular [duration [eta_dump.txt]]   (dump: "time : eta" lines)
+//        demo_sphere_waves <sphere.h5> <out.txt> eta <eta_file.txt> [duration]          (IrregularWaveParams::eta_file_path_)
 #include <hydroc/hydro_forces.h>
 
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 
@@ -20,7 +22,11 @@ int main(int argc, char* argv[]) {
     const int wave_num = regular && argc > 4 ? std::atoi(argv[4]) : 1;
     double simulationDuration = 600.0;
     if (regular && argc > 5) simulationDuration = std::atof(argv[5]);
-    if (!regular && argc > 4) simulationDuration = std::atof(argv[4]);
+    const bool from_file = std::strcmp(argv[3], "eta") == 0;
+    if (from_file && argc < 5) { std::cerr << "eta mode needs a file" << std::endl; return 2; }
+    if (!regular && !from_file && argc > 4) simulationDuration = std::atof(argv[4]);
+    if (from_file && argc > 5) simulationDuration = std::atof(argv[5]);
+    const char* eta_dump = (!regular && !from_file && argc > 5) ? argv[5] : nullptr;
 
     const double task10_wave_amps[] = {0.177, 0.314, 0.380, 0.491, 0.706, 0.961, 1.256, 1.589, 1.962, 2.374};
     const double task10_wave_omegas[] = {2.094395102, 1.570796327, 1.427996661, 1.256637061, 1.047197551,
@@ -74,10 +80,19 @@ int main(int argc, char* argv[]) {
             wave_inputs.frequency_min_ = 0.001;
             wave_inputs.frequency_max_ = 1.0;
             wave_inputs.nfrequencies_ = 1000;
+            if (from_file) wave_inputs.eta_file_path_ = argv[4];      // the series replaces the spectrum (wave_types.cpp:451-453)
             waves = std::make_shared<IrregularWaves>(wave_inputs);
         }
         TestHydro hydro_forces(bodies, h5fname);
         hydro_forces.AddWaves(waves);
+        if (eta_dump) {
+            auto irr = std::static_pointer_cast<IrregularWaves>(waves);
+            const std::vector<double> tt = irr->GetFreeSurfaceTime(), ee = irr->GetFreeSurfaceElevation();
+            FILE* f = std::fopen(eta_dump, "w");
+            if (!f) { std::cerr << "cannot write " << eta_dump << std::endl; return 1; }
+            for (size_t i = 0; i < tt.size(); ++i) std::fprintf(f, "%.17g : %.17g\n", tt[i], ee[i]);
+            std::fclose(f);
+        }
 
         while (system.GetChTime() <= simulationDuration) {
             system.DoStepDynamics(timestep);

@@ -219,6 +219,15 @@ HC_API void hc_irregular_default_params(hc_irregular_params* p);
  * Synthesises eta for every instance on the device (src/wave_types.cpp:27-59,717-774). */
 HC_API hc_status hc_waves_irregular(hc_ensemble* e, const hc_irregular_params* p, const int* seeds,
                                     const double* wave_height, const double* wave_period);
+/* SURVEY a16 -- free-surface elevation imported as a (time, eta) series instead of synthesised from a spectrum
+ * (IrregularWaves::ReadEtaFromFile, src/wave_types.cpp:480-500, called from InitializeIRFVectors :451-453 when
+ * IrregularWaveParams::eta_file_path_ is set).  time[n] strictly increasing (the grid the excitation convolution
+ * interpolates on; the reference snapshot leaves that grid empty on this branch, :784-785 -- the file's time column is
+ * the intended one); eta is [n], shared by every instance, or [B][n] when per_instance != 0.  simulation_dt is the
+ * spacing the excitation IRF is resampled to (ResampleIRF, :572-606).  hc_waves_irregular_spectrum then fails as
+ * IrregularWaves::GetSpectrum does (:461-467); hc_waves_irregular_eta returns the series. */
+HC_API hc_status hc_waves_irregular_series(hc_ensemble* e, double simulation_dt, int n, const double* time,
+                                           const double* eta, int per_instance);
 /* Introspection of the irregular-wave setup (IrregularWaves::GetSpectrum / GetFreeSurfaceElevation /
  * GetFreeSurfaceTime / GetFrequenciesHz, wave_types.h:300-309). */
 HC_API hc_status hc_waves_irregular_sizes(const hc_ensemble* e, int* nfreq, int* n_eta, int* exc_steps /*[N]*/);
@@ -348,6 +357,8 @@ HC_API hc_status hc_multi_waves_regular(hc_multi_ensemble* m, int count /* 1 or 
                                         const double* omega, const double* phase /* may be NULL */);
 HC_API hc_status hc_multi_waves_irregular(hc_multi_ensemble* m, const hc_irregular_params* p, const int* seeds /* [B] or NULL */,
                                           const double* Hs /* [B] or NULL */, const double* Tp /* [B] or NULL */);
+HC_API hc_status hc_multi_waves_irregular_series(hc_multi_ensemble* m, double simulation_dt, int n, const double* time,
+                                                 const double* eta /* [n] or [B][n] */, int per_instance);
 /* One lock-step of every instance on every device: host [B][6N] arrays in global instance order (pinned recommended);
  * each shard uploads, evaluates and downloads its own slice concurrently -- the result gather is the slices landing
  * in `force`.  Synchronous at return.  Same status codes and time-keyed cache as hc_step. */

@@ -989,6 +989,28 @@ int orc_set_irregular(OrcInstance* o, double dt, double duration, double ramp, d
     ORC_CATCH
 }
 
+// Free-surface elevation imported as a (time, eta) series instead of synthesised from a spectrum
+// (IrregularWaves::ReadEtaFromFile, wave_types.cpp:480-500, called from InitializeIRFVectors :451-453).  The reference
+// snapshot never fills free_surface_time_sampled_ on this branch although ExcitationConvolution reads it (:784-785);
+// the intended grid is the file's time column (time_data_), which is what is used here.
+int orc_set_irregular_series(OrcInstance* o, double dt, int n, const double* time, const double* eta,
+                             OrcInstance* share_irf_from) {
+    ORC_TRY
+    if (n < 2) throw std::runtime_error("eta series needs at least two samples");
+    Waves W; W.mode = kIrregular;
+    W.ip.simulation_dt = dt;
+    if (share_irf_from && share_irf_from->I.W.irf && share_irf_from->I.W.ip.simulation_dt == dt &&
+        share_irf_from->I.T == o->I.T)
+        W.irf = share_irf_from->I.W.irf;
+    else
+        W.irf = BuildExcIRF(*o->I.T, dt);
+    W.eta_t.assign(time, time + n);
+    W.eta.assign(eta, eta + n);
+    o->I.W = std::move(W);
+    return 0;
+    ORC_CATCH
+}
+
 int orc_irregular_sizes(OrcInstance* o, int* nf, int* n_eta, int* Le /*[N]*/) {
     const Waves& W = o->I.W;
     if (W.mode != kIrregular) return -1;

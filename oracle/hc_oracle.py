@@ -45,6 +45,7 @@ def lib():
         L.orc_set_nowave.argtypes = [C.c_void_p]
         L.orc_set_regular.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.orc_set_irregular.argtypes = [C.c_void_p] + [C.c_double] * 9 + [C.c_int, C.c_int, C.c_void_p]
+        L.orc_set_irregular_series.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_irregular_sizes.argtypes = [C.c_void_p, _ip, _ip, _ip]
         L.orc_irregular_get.argtypes = [C.c_void_p] + [_dp] * 7
         L.orc_irregular_get_irf.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
@@ -178,6 +179,15 @@ class Instance:
                       is_normalized=False, seed=1, share_irf_from=None):
         rc = lib().orc_set_irregular(self.h, dt, duration, ramp, Hs, Tp, fmin, fmax, float(nfreq), gamma,
                                      int(is_normalized), seed, share_irf_from.h if share_irf_from else None)
+        if rc:
+            raise OracleError(_err())
+
+    def set_irregular_series(self, dt, time, eta, share_irf_from=None):
+        """Imported free-surface series (wave_types.cpp:480-500): the excitation convolution runs over (time, eta)."""
+        time = np.ascontiguousarray(time, dtype=np.float64); eta = np.ascontiguousarray(eta, dtype=np.float64)
+        assert time.shape == eta.shape and time.ndim == 1
+        rc = lib().orc_set_irregular_series(self.h, dt, len(time), _p(time), _p(eta),
+                                            share_irf_from.h if share_irf_from else None)
         if rc:
             raise OracleError(_err())
 

@@ -411,6 +411,77 @@ def test_bracket_search_with_gaps_and_bursts(sphere):
     assert ens.history_len() == insts[0].history_len()
 
 
+def test_imported_eta_series(sphere):
+    """SURVEY a16 -- the free-surface elevation imported as a (time, eta) series (IrregularWaveParams::eta_file_path_,
+    wave_types.cpp:451-453,480-500).  (i) a synthesised series fed back as an import reproduces the irregular-wave forces
+    bit for bit; (ii) oracle parity on that grid, per instance and shared; (iii) a coarse, non-uniform grid (true
+    interpolation on every tap); (iv) input validation."""
+    T, O = sphere
+    B, dt = 3, 0.015
+    irr = dict(dt=dt, duration=8.0, ramp=2.0, Hs=2.0, Tp=12.0, nfreq=100)
+    a = hc.Ensemble(T, batch=B, dt_hint=dt)
+    a.set_waves_irregular(seeds=[4, 5, 6], **irr)
+    series = [a.irregular(b) for b in range(B)]
+    eta_t = series[0]["eta_t"]
+    eta = np.stack([s["eta"] for s in series])
+    b_ = hc.Ensemble(T, batch=B, dt_hint=dt)
+    b_.set_waves_series(dt, eta_t, eta)
+    got = b_.irregular(1)
+    np.testing.assert_array_equal(got["eta_t"], eta_t)
+    np.testing.assert_array_equal(got["eta"], eta[1])
+    assert b_.irregular_sizes()[0] == 0                                  # no spectrum behind an imported series
+    with pytest.raises(hc.HydroError, match="Spectrum has not been created"):
+        hc._check(hc.lib.hc_waves_irregular_spectrum(b_._h, 0, None, None, None, None, None))
+    insts = []
+    for b in range(B):
+        i = orc.Instance(O)
+        i.set_irregular_series(dt, eta_t, eta[b], share_irf_from=insts[0] if insts else None)
+        insts.append(i)
+    times = _acc_times(200, dt)
+    fa, fb, fo, wv, rwv = [], [], [], [], []
+    for t in times:
+        pose, vel = _motion(6, B, t)
+        fa.append(a.step(t, pose, vel, G981).copy())
+        fb.append(b_.step(t, pose, vel, G981).copy())
+        wv.append(b_.components()[2].copy())
+        r = [i.force(t, pose[k], vel[k], G981, components=True) for k, i in enumerate(insts)]
+        fo.append(np.array([x[0] for x in r])); rwv.append(np.array([x[3] for x in r]))
+    np.testing.assert_array_equal(np.array(fa), np.array(fb))            # (i)
+    _assert_parity(np.array(wv), np.array(rwv), "excitation, imported series")        # (ii)
+    _assert_parity(np.array(fb), np.array(fo), "total, imported series")
+    assert np.abs(np.array(wv)).max() > 1e3
+    # shared series: every instance sees instance 0's elevation
+    c = hc.Ensemble(T, batch=B, dt_hint=dt)
+    c.set_waves_series(dt, eta_t, eta[0])
+    for n, t in enumerate(times[:40]):
+        pose, vel = _motion(6, B, t)
+        pose[:] = pose[0]; vel[:] = vel[0]
+        F = c.step(t, pose, vel, G981)
+        assert np.array_equal(F[0], F[1]) and np.array_equal(F[0], F[2])
+    # (iii) coarse non-uniform grid wide enough for the excitation IRF window at every step
+    tau = a.irregular(0)["irf"][0]["t"]
+    rng = np.random.default_rng(11)
+    g = np.cumsum(rng.uniform(0.03, 0.09, size=4000)) + (times[0] - tau[-1] - 1.0)
+    assert g[-1] > times[-1] - tau[0] + 1.0
+    e = 0.8 * np.sin(0.7 * g) + 0.3 * np.cos(1.9 * g + 0.4)
+    d = hc.Ensemble(T, batch=2, dt_hint=dt)
+    d.set_waves_series(dt, g, e)
+    oi = orc.Instance(O)
+    oi.set_irregular_series(dt, g, e)
+    wv, rwv = [], []
+    for t in times[:120]:
+        pose, vel = _motion(6, 2, t)
+        d.step(t, pose, vel, G981)
+        wv.append(d.components()[2][0].copy())
+        rwv.append(oi.force(t, pose[0], vel[0], G981, components=True)[3])
+    _assert_parity(np.array(wv)[:, None, :], np.array(rwv)[:, None, :], "excitation, non-uniform imported grid")
+    # (iv)
+    with pytest.raises(hc.HydroError, match="strictly increasing"):
+        d.set_waves_series(dt, np.array([0.0, 1.0, 1.0]), np.zeros(3))
+    with pytest.raises(hc.HydroError, match="at least two"):
+        d.set_waves_series(dt, np.array([0.0]), np.zeros(1))
+
+
 def test_gravity_vector_and_body_count_generic_path():
     """3-body system (D = 18) runs the run-time-D radiation kernel; tilted gravity exercises the buoyancy cross term."""
     raw = synth.make_tables(num_bodies=3, rirf_steps=301, rirf_duration=15.0, exc_irf_steps=201, exc_half_window=10.0)

@@ -99,6 +99,34 @@ def test_demo_sphere_irregular_waves_golden(host_build, sphere_h5, tmp_path):
 
 
 @pytest.mark.gpu
+def test_eta_file_import_reproduces_the_irregular_run(host_build, sphere_h5, tmp_path):
+    """SURVEY a16: IrregularWaveParams::eta_file_path_ (src/wave_types.cpp:451-453,480-500).  The irregular-wave demo
+    dumps its free-surface series in the reference's "time : eta" format; a second run that imports that file through
+    IrregularWaves must retrace the first run's heave trajectory exactly.  Parse errors carry the reference's messages."""
+    demo = os.path.join(host_build, "demo_sphere_waves")
+    o1, o2, eta = tmp_path / "irr.txt", tmp_path / "imp.txt", tmp_path / "eta.txt"
+    out = subprocess.run([demo, sphere_h5, str(o1), "irregular", "12.0", str(eta)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    first = open(eta).readline()
+    assert " : " in first
+    out2 = subprocess.run([demo, sphere_h5, str(o2), "eta", str(eta), "12.0"], capture_output=True, text=True)
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    t1, z1 = _read_traj(o1)
+    t2, z2 = _read_traj(o2)
+    np.testing.assert_array_equal(t1, t2)
+    np.testing.assert_array_equal(z1, z2)
+    assert np.ptp(z1) > 1e-3
+    # the wave force line printed at the end agrees too; the elevation helper has no spectrum to sum over
+    assert out.stdout.split("elevation")[0] == out2.stdout.split("elevation")[0]
+    bad = tmp_path / "bad.txt"
+    bad.write_text("0.0 : 0.1\n0.015 ; 0.2\n")
+    out3 = subprocess.run([demo, sphere_h5, str(o2), "eta", str(bad), "1.0"], capture_output=True, text=True)
+    assert out3.returncode == 1 and "Could not parse line: 0.015 ; 0.2." in out3.stderr
+    out4 = subprocess.run([demo, sphere_h5, str(o2), "eta", str(tmp_path / "missing.txt"), "1.0"], capture_output=True, text=True)
+    assert out4.returncode == 1 and "Unable to open file at:" in out4.stderr
+
+
+@pytest.mark.gpu
 def test_api_surface_two_bodies(host_build, tmp_path):
     h5 = tmp_path / "rm3_like.h5"
     h5io.write_bemio(h5, synth.rm3_like(rirf_steps=201, rirf_duration=10.0, exc_irf_steps=201, exc_half_window=5.0))

@@ -68,6 +68,29 @@ def test_sphere_irregular_waves(tables):
     assert n1 <= 1e-7 and n2 <= 2e-4, (n1, n2)
 
 
+def test_imported_eta_series_reproduces_the_irregular_run(tables):
+    """SURVEY a16 (wave_types.cpp:451-453,480-500): the oracle fed the free-surface series of an irregular-wave set-up as
+    an imported (time, eta) table gives the same forces bit for bit -- the excitation convolution only sees the table;
+    a text round trip with 17 significant digits ("time : eta" lines, the reference's file format) changes nothing."""
+    a = orc.Instance(tables)
+    a.set_irregular(dt=common.SPHERE_DT, duration=6.0, ramp=1.0, Hs=2.0, Tp=12.0, nfreq=64, seed=9)
+    d = a.irregular()
+    lines = ["%.17g : %.17g" % (t, e) for t, e in zip(d["eta_t"], d["eta"])]
+    tt = np.array([float(x.split(":")[0]) for x in lines]); ee = np.array([float(x.split(":")[1]) for x in lines])
+    np.testing.assert_array_equal(tt, d["eta_t"]); np.testing.assert_array_equal(ee, d["eta"])
+    b = orc.Instance(tables)
+    b.set_irregular_series(common.SPHERE_DT, tt, ee, share_irf_from=a)
+    gv = np.array([0.0, 0.0, -9.81])
+    t = 0.0
+    for n in range(60):
+        pose = 0.05 * np.sin(0.9 * t + np.arange(6)); vel = 0.045 * np.cos(0.9 * t + np.arange(6))
+        fa, fb = a.force(t, pose, vel, gv), b.force(t, pose, vel, gv)
+        np.testing.assert_array_equal(fa, fb)
+        t += common.SPHERE_DT
+    assert abs(fa[2]) > 1.0
+    assert b.irregular()["freqs"].size == 0          # no spectrum behind an imported series
+
+
 def test_iea_sphere_cli_golden(tables):
     """tests/regression/run_hydrochrono/iea_sphere/decay: the CLI harness' gate is RMS-relative error <= 0.02
     (run_tests.py:235, compare_results.py:103-107).  The golden was produced with Chrono's HHT integrator; the
