@@ -531,6 +531,13 @@ class MultiEnsemble:
         _check(lib.hc_multi_waves_irregular(self._h, C.byref(p), sd.ctypes.data_as(_capi.ip) if sd is not None else None,
                                             _dp(hs), _dp(tp)))
 
+    def set_waves_series(self, dt, time, eta):
+        """Imported free-surface elevation: time [n], eta [n] (shared) or [B][n] in global instance order."""
+        t, e = _f64(time), _f64(eta)
+        if t.ndim != 1 or e.shape[-1] != t.size or e.ndim not in (1, 2) or (e.ndim == 2 and e.shape[0] != self.batch):
+            raise ValueError("time must be [n] and eta [n] or [batch][n]")
+        _check(lib.hc_multi_waves_irregular_series(self._h, float(dt), t.size, _dp(t), _dp(e), int(e.ndim == 2)))
+
     def step(self, t, pose, vel, gvec=(0.0, 0.0, -9.81), out=None):
         """One lock-step of every instance on every device; host [B][6N] arrays in global instance order."""
         pose, vel, g = _f64(pose), _f64(vel), _f64(gvec)

@@ -937,7 +937,24 @@ def test_multi_device_handle_matches_single_ensemble(rm3):
     with pytest.raises(hc.HydroError):                      # time going backwards is reported with the shard it came from
         multi.step(0.0, pose, vel)
     one.close(); multi.close()
-    for e in parts:
+    # imported per-instance free-surface series: every shard receives its own rows of eta[B][n]
+    eta_t = parts[0].irregular(0)["eta_t"]
+    eta = np.stack([parts[k].irregular(i)["eta"] for k, s in enumerate(sh) for i in (0, s["count"] - 1)])   # 6 series
+    m2 = hc.MultiEnsemble(T, batch=6, devices=devices, dt_hint=dt)
+    m2.set_waves_series(dt, eta_t, eta)
+    singles = []
+    for i in range(6):
+        e = hc.Ensemble(T, batch=2, dt_hint=dt)            # (shards of 6 over 3 devices hold 2 instances each)
+        e.set_waves_series(dt, eta_t, eta[2 * (i // 2):2 * (i // 2) + 2])
+        singles.append(e)
+    for t in _acc_times(20, dt):
+        pose, vel = _motion(D, 6, t)
+        F = m2.step(t, pose, vel)
+        for k in range(3):
+            np.testing.assert_array_equal(F[2 * k:2 * k + 2], singles[2 * k].step(t, pose[2 * k:2 * k + 2], vel[2 * k:2 * k + 2]))
+    assert np.abs(m2.components()[2]).max() > 1.0
+    m2.close()
+    for e in parts + singles:
         e.close()
 
 
