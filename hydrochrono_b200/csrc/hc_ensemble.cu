@@ -165,6 +165,7 @@ struct hc_ensemble {
     size_t stage_bytes = 0;
     bool compact_ok = false, defer_launch = false;
     double* h_force_dev = nullptr;                // device-side address of the pinned force buffer (compact graph writes it directly)
+    bool compact_fork = true;                     // HC_COMPACT_FORK=0: excitation and radiation convolutions in sequence (diagnostic)
     bool compact_inline = true;                   // HC_COMPACT_INLINE=0: keep the plan kernel in the compact graph (diagnostic)
     bool compact_capture = false;                 // enqueue_phase is recording the compact graph (state already on the device)
     cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
@@ -678,7 +679,7 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
         if (compact_capture) graph_c_inline = plan_inline;
         if (!plan_inline && (!rb_use || per_step_exc)) CUDA_CHECK(launch_prestep(pa, compact_capture ? 3 : 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
-        const bool fork = compact_capture && per_step_exc && run_rad;
+        const bool fork = compact_capture && compact_fork && per_step_exc && run_rad;
         cudaStream_t es = fork ? copy_stream : stream;
         if (fork) {
             CUDA_CHECK(cudaEventRecord(ev_cfork, stream));
@@ -1227,6 +1228,8 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
     if (e->compact_ok) {
+        const char* vf = std::getenv("HC_COMPACT_FORK");
+        if (vf && std::atoi(vf) == 0) e->compact_fork = false;
         const char* vi = std::getenv("HC_COMPACT_INLINE");
         if (vi && std::atoi(vi) == 0) e->compact_inline = false;
         const char* v = std::getenv("HC_COMPACT_DIRECT");            // diagnostic: 0 = forces come back through a copy node
