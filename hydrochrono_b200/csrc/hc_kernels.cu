@@ -1766,7 +1766,12 @@ cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    if ((long long)a.B * a.D <= kFinalizeWarpMaxItems) {     // small ensemble: a lane group per (dof, instance)
+    static long long warp_items = -1;
+    if (warp_items < 0) {
+        const char* v = std::getenv("HC_FINALIZE_WARP_ITEMS");       // diagnostic override of the threshold
+        warp_items = v ? std::atoll(v) : kFinalizeWarpMaxItems;
+    }
+    if ((long long)a.B * a.D <= warp_items) {     // small ensemble: a lane group per (dof, instance)
         // (G = 8 -- four consecutive instances per warp, sector-efficient rows -- measured slower at every size: 53 vs
         //  40 us at B = 16, 78 vs 67 us at B = 256: the dependent load rounds per lane count, not the sectors)
         k_finalize_warp<32><<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);
