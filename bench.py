@@ -873,13 +873,13 @@ def main():
                         "kernel_ms": kms["radiation"],
                         "kernel_ms_note": "launch_ms = one whole pass = the sum of its per-step slices, each timed with "
                                           "CUDA events on its stream in the profiling pass; radiation per step = "
-                                          "launch_ms / %d + k_step<12>" % rb_T,
+                                          "launch_ms / %d + k_step<%d>" % (rb_T, DOFS),
                         "hbm_view": {"algorithmic_bytes_per_step": rad_bytes, "gbs": ach, "hbm_peak": peak, "frac": ach / peak,
                                      "note": "SURVEY 8(d) bytes of the per-step formulation over the measured radiation "
                                              "time per step: the block pass reads each history row once per %d steps, "
                                              "so the per-step HBM roofline no longer binds (frac > 1); "
-                                             "--rad-lookahead 1 measures the per-step kernel k_radiation<12> against "
-                                             "that roofline" % rb_T}}
+                                             "--rad-lookahead 1 measures the per-step kernel k_radiation<%d> against "
+                                             "that roofline" % (rb_T, DOFS)}}
             step_bytes = hist_bytes / rb_T + (B * 8 * (EXC_STEPS + 8) // 8)
         step_s = t_dev / K
         e2e = world * B * K / t_e2e
@@ -924,7 +924,7 @@ def main():
                                          "traffic": (traffic or {}).get("exc_block_dram_bytes_per_launch"),
                                          "traffic_note": "dram bytes per k_exc_block launch (one launch per 8 steps)"}
                                         if not args.no_lookahead else
-                                        {"kernel": "k_excitation<12>", "bound": "hbm", "achieved": ach_exc, "peak": peak,
+                                        {"kernel": "k_excitation<%d>" % DOFS, "bound": "hbm", "achieved": ach_exc, "peak": peak,
                                          "unit": "GB/s", "frac": (ach_exc / peak) if ach_exc else None,
                                          "algorithmic_bytes_per_launch": exc_bytes, "kernel_ms": kms["excitation"],
                                          "traffic": (traffic or {}).get("excitation_dram_bytes_per_launch")})},
@@ -937,7 +937,7 @@ def main():
             "kernel_ms": kms,
             "kernel_ms_note": "isolated kernel durations (the profiling pass runs every kernel back-to-back in one "
                               "stream).  excitation = look-ahead block time / 8.  With the radiation look-ahead on: "
-                              "radiation = this step's slice of the next block's k_rad_block<12> pass + k_step<12> (append, "
+                              "radiation = this step's slice of the next block's k_rad_block<D> pass + k_step<D> (append, "
                               "block partials, rows appended since the snapshot AND finalize, fused), finalize ~ 0.  "
                               "In the timed region the excitation block of the next 8 steps and the slices of the next "
                               "radiation block run on side streams underneath the per-step kernels and the host <-> "
