@@ -589,7 +589,11 @@ __global__ void __launch_bounds__(kHybThreads, 3) k_radiation_hybrid12(const Rad
 // k_step<D> (phase 2 of every step served by a block) appends the step's velocities, sums the row-chunk partials in
 // fixed order, adds the second sum (at most 16 rows) and finishes the step like k_finalize.
 // ------------------------------------------------------------------------------------------
-size_t rad_block_smem_bytes(int D, int R) { return 16 + size_t(R + kRbT - 1) * rb_stride(D) * sizeof(double); }
+// (D = 6: one lag of slack -- the pair loop's predicated-off read of the second row's A in an odd last iteration may be
+//  issued speculatively one lag past the R + 7 the bulk copy fills)
+size_t rad_block_smem_bytes(int D, int R) {
+    return 16 + size_t(R + kRbT - 1 + (D == 6 ? 1 : 0)) * rb_stride(D) * sizeof(double);
+}
 
 template <int D>
 __global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadBlockArgs a) {
@@ -639,6 +643,60 @@ __global__ void __launch_bounds__(128, (D <= 12) ? 3 : 2) k_rad_block(const RadB
             dst[ks] = __ldg(reinterpret_cast<const double2*>(p + (size_t)c * a.Bp));
         }
     };
+    if constexpr (D == 6) {
+        // Single body: 6 columns would pad to 2 k-steps of 4 (a quarter of the DMMAs multiplying zeros).  Two consecutive
+        // rows are 12 columns = 3 exact k-steps: k-step 0 = row u, columns 0-3; k-step 1 = columns 4-5 of rows u and
+        // u + 1; k-step 2 = row u + 1, columns 0-3 (any split of the K dimension is a valid product; A keeps its tile
+        // layout -- in k-step 1 lanes (g, e = 1) and (g + 1, e = 0) read the same word, the rest distinct banks but for
+        // one 2-way overlap per half warp).  An odd last row runs with the second row's A zeroed.
+        auto slot_of = [&](int u) {
+            int slot = (a.head0 - 1 - off - a.m * u) % a.cap;
+            return slot < 0 ? slot + a.cap : slot;
+        };
+        const int e1 = q >> 1;                                   // k-step 1: which row of the pair this lane's column is in
+        auto load_pair = [&](int u, bool two, double2* dst) {
+            const double* p0 = hl + (size_t)slot_of(u) * row_stride;
+            const double* p1 = two ? hl + (size_t)slot_of(u + 1) * row_stride : p0;
+            dst[0] = __ldg(reinterpret_cast<const double2*>(p0 + (size_t)q * a.Bp));
+            dst[1] = __ldg(reinterpret_cast<const double2*>((e1 ? p1 : p0) + (size_t)(4 + (q & 1)) * a.Bp));
+            dst[2] = __ldg(reinterpret_cast<const double2*>(p1 + (size_t)q * a.Bp));
+        };
+        double2 cur[3], nxt[3];
+        if (active && nr > 0) load_pair(r0, nr > 1, cur);
+        mbar_wait(bar, 0);
+        if (active) {
+            const double* kl = Ks + (size_t)g * STRIDE;
+            for (int i = 0; i < nr; i += 2) {
+                const int r = r0 + i;
+                const bool two = i + 1 < nr;
+                if (i + 2 < nr) load_pair(r + 2, i + 3 < nr, nxt);
+                const double* kr = kl + (size_t)i * STRIDE;      // lag (r + g0 + g + 1) = tile lag i + g
+                const bool on0 = r <= rmax_g, on1 = two && (r + 1 <= rmax_g);
+                const bool onm = e1 ? on1 : on0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double a0 = on0 ? kr[d * DP + q] : 0.0;
+                    const double a1 = onm ? kr[(size_t)e1 * STRIDE + d * DP + 4 + (q & 1)] : 0.0;
+                    const double a2 = on1 ? kr[STRIDE + d * DP + q] : 0.0;
+                    dmma8x8x4(C[d][0][0], C[d][0][1], a0, cur[0].x);
+                    dmma8x8x4(C[d][1][0], C[d][1][1], a0, cur[0].y);
+                    dmma8x8x4(C[d][0][0], C[d][0][1], a1, cur[1].x);
+                    dmma8x8x4(C[d][1][0], C[d][1][1], a1, cur[1].y);
+                    dmma8x8x4(C[d][0][0], C[d][0][1], a2, cur[2].x);
+                    dmma8x8x4(C[d][1][0], C[d][1][1], a2, cur[2].y);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) cur[ks] = nxt[ks];
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double* o = a.partial + (((size_t)(rho + a.m * g) * a.nchunk + chunk) * D + d) * a.Bp + b0 + 4 * q;
+                *reinterpret_cast<double2*>(o) = make_double2(C[d][0][0], C[d][1][0]);
+                *reinterpret_cast<double2*>(o + 2) = make_double2(C[d][0][1], C[d][1][1]);
+            }
+        }
+        return;
+    }
     double2 cur[KS], nxt[KS];
     if (active && nr > 0) load_row(r0, cur);
     mbar_wait(bar, 0);
