@@ -169,6 +169,10 @@ struct hc_ensemble {
     bool compact_inline = true;                   // HC_COMPACT_INLINE=0: keep the plan kernel in the compact graph (diagnostic)
     bool compact_capture = false;                 // enqueue_phase is recording the compact graph (state already on the device)
     cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
+    cudaStream_t fork_stream = nullptr;           // second branch of a captured graph (never runs work outside a capture)
+    bool phase1_capture = false;                  // enqueue_phase is recording the phase-1 graph of the per-step path
+    int fork_max_batch = 2048;                    // phase-1 graph: parallel convolution branches up to this ensemble size
+    void ensure_fork_objects();
     cudaGraph_t graph_c = nullptr;
     cudaGraphExec_t graph_c_exec = nullptr;
     int graph_c_key = -1;
@@ -251,6 +255,7 @@ struct hc_ensemble {
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (ev_cfork) cudaEventDestroy(ev_cfork);
         if (ev_cjoin) cudaEventDestroy(ev_cjoin);
+        if (fork_stream) cudaStreamDestroy(fork_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_inputs) cudaEventDestroy(ev_inputs);
         if (ev_force) cudaEventDestroy(ev_force);
@@ -679,11 +684,13 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
         if (compact_capture) graph_c_inline = plan_inline;
         if (!plan_inline && (!rb_use || per_step_exc)) CUDA_CHECK(launch_prestep(pa, compact_capture ? 3 : 2, stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_PLAN], stream));
-        const bool fork = compact_capture && compact_fork && per_step_exc && run_rad;
-        cudaStream_t es = fork ? copy_stream : stream;
+        // (the same fork in the phase-1 graph of an ensemble small enough for the two kernels to be latency-bound
+        //  rather than HBM-bound: measured in DESIGN.md section 4)
+        const bool fork = (compact_capture || (phase1_capture && B <= fork_max_batch)) && compact_fork && per_step_exc && run_rad;
+        cudaStream_t es = fork ? fork_stream : stream;
         if (fork) {
             CUDA_CHECK(cudaEventRecord(ev_cfork, stream));
-            CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_cfork, 0));
+            CUDA_CHECK(cudaStreamWaitEvent(fork_stream, ev_cfork, 0));
         }
         if (per_step_exc) {
             ExcitationArgs ea{};
@@ -695,7 +702,7 @@ void hc_ensemble::enqueue_phase(int phase, bool with_events) {
                 CUDA_CHECK(launch_excitation(ea, eg, G.idx.p, G.w1.p, G.w2.p, es, plan_inline));
             }
         }
-        if (fork) CUDA_CHECK(cudaEventRecord(ev_cjoin, copy_stream));
+        if (fork) CUDA_CHECK(cudaEventRecord(ev_cjoin, fork_stream));
         if (with_events) CUDA_CHECK(cudaEventRecord(ev[EV_EXC], stream));
         if (run_rad) {
             const InlinePlan ipl{d_pr_wd.p, d_pr_head.p, d_pr_lead.p, B};
@@ -789,15 +796,19 @@ void hc_ensemble::launch_phase(int phase) {
         if (ge) cudaGraphExecDestroy(ge);
         if (g) cudaGraphDestroy(g);
         ge = nullptr; g = nullptr;
+        ensure_fork_objects();
         CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        phase1_capture = (phase == 1);
         try {
             enqueue_phase(phase, false);
         } catch (...) {
+            phase1_capture = false;
             cudaGraph_t tmp = nullptr;
             cudaStreamEndCapture(stream, &tmp);
             if (tmp) cudaGraphDestroy(tmp);
             throw;
         }
+        phase1_capture = false;
         CUDA_CHECK(cudaStreamEndCapture(stream, &g));
         CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
         graph_key[phase] = key;
@@ -1084,16 +1095,20 @@ int hc_ensemble::lookahead_slot(double t) {
 
 // Compact host path: the staged inputs (header, velocities, pose: one pinned block) go up in ONE copy, every kernel of
 // the step runs, the forces come back into the pinned force buffer -- all nodes of one captured graph.
+void hc_ensemble::ensure_fork_objects() {
+    if (fork_stream) return;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&fork_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_cfork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_cjoin, cudaEventDisableTiming));
+}
+
 void hc_ensemble::run_compact() {
     const int key = (phase_uses_lookahead ? 1 : 0) | (skip_radiation ? 4 : 0);
     if (!graph_c_exec || graph_c_key != key) {
         if (graph_c_exec) cudaGraphExecDestroy(graph_c_exec);
         if (graph_c) cudaGraphDestroy(graph_c);
         graph_c_exec = nullptr; graph_c = nullptr;
-        if (!ev_cfork) {
-            CUDA_CHECK(cudaEventCreateWithFlags(&ev_cfork, cudaEventDisableTiming));
-            CUDA_CHECK(cudaEventCreateWithFlags(&ev_cjoin, cudaEventDisableTiming));
-        }
+        ensure_fork_objects();
         CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         compact_capture = true;
         try {
@@ -1227,9 +1242,13 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     if (e->compact_ok) e->h_stage.alloc(e->stage_bytes);
     e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
-    if (e->compact_ok) {
+    {
         const char* vf = std::getenv("HC_COMPACT_FORK");
         if (vf && std::atoi(vf) == 0) e->compact_fork = false;
+        const char* vm = std::getenv("HC_FORK_MAX_BATCH");         // diagnostic override
+        if (vm) e->fork_max_batch = std::atoi(vm);
+    }
+    if (e->compact_ok) {
         const char* vi = std::getenv("HC_COMPACT_INLINE");
         if (vi && std::atoi(vi) == 0) e->compact_inline = false;
         const char* v = std::getenv("HC_COMPACT_DIRECT");            // diagnostic: 0 = forces come back through a copy node
