@@ -127,6 +127,16 @@ def test_eta_file_import_reproduces_the_irregular_run(host_build, sphere_h5, tmp
 
 
 @pytest.mark.gpu
+def test_b1_latency_probe_runs(host_build, sphere_h5):
+    """The C++ latency probe of the drop-in case (hc_step at B = 1 through the C ABI, and the first ComponentFunc
+    evaluation at a new ChTime through TestHydro): both paths evaluate the same forces."""
+    out = subprocess.run([os.path.join(host_build, "bench_b1_latency"), sphere_h5, "1", "0.015", "40", "20"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "C ABI hc_step, B = 1, D = 6: median" in out.stdout and "first call at a new time: median" in out.stdout
+
+
+@pytest.mark.gpu
 def test_api_surface_two_bodies(host_build, tmp_path):
     h5 = tmp_path / "rm3_like.h5"
     h5io.write_bemio(h5, synth.rm3_like(rirf_steps=201, rirf_duration=10.0, exc_irf_steps=201, exc_half_window=5.0))
