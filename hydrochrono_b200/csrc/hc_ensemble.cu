@@ -1238,7 +1238,9 @@ hc_status hc_ensemble_create(const hc_tables* t, const hc_ensemble_opts* opts, h
     e->d_vel.p = reinterpret_cast<double*>(e->d_stage.p + 256);
     e->d_pose.p = e->d_vel.p + bd;
     static_assert(sizeof(StepHeader) <= 256, "step header must fit its slot of the staging block");
-    e->compact_ok = e->stage_bytes <= 64 * 1024 && opts->use_graph;
+    size_t compact_max = 64 * 1024;
+    if (const char* v = std::getenv("HC_COMPACT_MAX_BYTES")) compact_max = size_t(std::atoll(v));   // diagnostic override
+    e->compact_ok = e->stage_bytes <= compact_max && opts->use_graph;
     if (e->compact_ok) e->h_stage.alloc(e->stage_bytes);
     e->d_force.alloc(bd); e->d_comp.alloc(3 * bd);
     e->h_pose.alloc(bd * sizeof(double)); e->h_vel.alloc(bd * sizeof(double)); e->h_force.alloc(bd * sizeof(double));
