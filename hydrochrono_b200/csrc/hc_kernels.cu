@@ -1612,6 +1612,46 @@ __global__ void __launch_bounds__(256) k_finalize_warp(const FinalizeArgs a, con
     if (sub == 0 && h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
 }
 
+// k_finalize_split<G>: the same for MID-SIZE ensembles on the per-step path (hundreds to a few thousand instances): still
+// hundreds of partials per item (143 + 147 at 1024 instances of the RM3 shape: k_finalize 41 us, the longest kernel of
+// the step), but enough instances for coalesced rows.  One CTA = 32 consecutive instances of one dof x G warps; warp g
+// sums partials g, g + G, ... (8 loads in flight, lanes = instances: whole 256-byte rows), shared memory holds the G
+// sums per instance, warp 0 adds them in ascending g and finishes the items.  Deterministic.
+template <int G>
+__global__ void __launch_bounds__(32 * G) k_finalize_split(const FinalizeArgs a, const __grid_constant__ HydrostaticTables hs,
+                                                           const __grid_constant__ FinalizeGroups eg) {
+    __shared__ double s_fr[G][32], s_fw[G][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int tiles = (a.B + 31) / 32;
+    const int d = blockIdx.x / tiles, b = (blockIdx.x - d * tiles) * 32 + lane;
+    const bool live = b < a.B;
+    const StepHeader h = *a.hdr;
+    const int D = a.D;
+    double fr = 0.0, fw = 0.0;
+    if (!a.waves_only)
+        fr = member_sum_strided<G>(a.rad_partial + (size_t)d * a.Bp + b, (size_t)D * a.Bp, a.rad_nchunk, grp, live);
+    if (a.wave_mode == 2 && h.exc_src == 1) {
+        const int buf = h.exc_slot / kLaT, pos = h.exc_slot - buf * kLaT;
+        const double* p = a.exc_cache + (((size_t)buf * a.exc_S * kLaT + pos) * D + d) * a.Bp + b;
+        fw = member_sum_strided<G>(p, (size_t)kLaT * D * a.Bp, a.exc_S, grp, live);
+    } else if (a.wave_mode == 2) {
+        for (int g = 0; g < a.exc_ngroups; ++g) {
+            if (d < eg.dof0[g] || d >= eg.dof0[g] + eg.nd[g]) continue;
+            const double* p = a.exc_partial + ((size_t)eg.chunk0[g] * a.exc_ndmax + (d - eg.dof0[g])) * a.Bp + b;
+            fw = __dadd_rn(fw, member_sum_strided<G>(p, (size_t)a.exc_ndmax * a.Bp, eg.nchunk[g], grp, live));
+        }
+    }
+    s_fr[grp][lane] = fr; s_fw[grp][lane] = fw;
+    __syncthreads();
+    if (grp != 0 || !live) return;
+    fr = 0.0; fw = 0.0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) { fr = __dadd_rn(fr, s_fr[g][lane]); fw = __dadd_rn(fw, s_fw[g][lane]); }
+    const double total = finalize_one(a, hs, eg, h, d, b, false, 0.0,
+                                      a.waves_only ? nullptr : h.pose + (size_t)b * a.D + 6 * (d / 6), &fr, &fw, true);
+    if (h.force2 && !a.waves_only) h.force2[(size_t)b * a.D + d] = total;
+}
+
 // ------------------------------------------------------------------------------------------
 // k_eta: eta[k][b] = sum_i amp_i cos(k_i*0 - omega_i t_k + phase_{b,i}), ramped.  One thread = one instance
 // x KT consecutive samples; the sum runs over i in ascending order like the reference's loop.
@@ -1824,12 +1864,22 @@ cudaError_t launch_prestep(const PrestepArgs& a, int mode, cudaStream_t st) {
 
 cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, const FinalizeGroups& eg,
                             cudaStream_t st) {
-    static long long warp_items = -1;
-    if (warp_items < 0) {
-        const char* v = std::getenv("HC_FINALIZE_WARP_ITEMS");       // diagnostic override of the threshold
-        warp_items = v ? std::atoll(v) : kFinalizeWarpMaxItems;
+    static int mode = -1;                                           // 0 auto, 1 thread per item, 2 warp per item, 3 split
+    if (mode < 0) {
+        const char* m = std::getenv("HC_FINALIZE_MODE");            // diagnostic override
+        mode = m ? std::atoi(m) : 0;
     }
-    if ((long long)a.B * a.D <= warp_items) {     // small ensemble: a lane group per (dof, instance)
+    int nparts = a.rad_nchunk;
+    if (a.wave_mode == 2) for (int g = 0; g < a.exc_ngroups; ++g) nparts = std::max(nparts, a.rad_nchunk + eg.nchunk[g]);
+    int pick = mode;
+    // measured (RM3 shape, per-step path, us per step, warp / split / thread): B = 16: 42.8 / 41.1 / -, 256: 71.1 / 68.5 / -,
+    // 512: 102 / 92 / -, 1024: 136 / 121 / 136, 2048: - / 182 / 181, 4096: - / 295 / 285  (profiles/r02w5_finalize_modes.txt)
+    if (pick == 0) pick = (a.B <= kFinalizeWarpMaxB) ? 2 : (nparts >= kFinalizeSplitMinParts ? 3 : 1);
+    if (pick == 3) {
+        k_finalize_split<16><<<a.D * ((a.B + 31) / 32), 32 * 16, 0, st>>>(a, hs, eg);
+        return cudaGetLastError();
+    }
+    if (pick == 2) {     // small ensemble: a lane group per (dof, instance)
         // (G = 8 -- four consecutive instances per warp, sector-efficient rows -- measured slower at every size: 53 vs
         //  40 us at B = 16, 78 vs 67 us at B = 256: the dependent load rounds per lane count, not the sectors)
         k_finalize_warp<32><<<(a.D * a.B * 32 + 255) / 256, 256, 0, st>>>(a, hs, eg);

@@ -161,9 +161,10 @@ cudaError_t launch_finalize(const FinalizeArgs& a, const HydrostaticTables& hs, 
                             cudaStream_t st);
 cudaError_t launch_eta(const EtaArgs& a, cudaStream_t st);
 // ---- excitation look-ahead: the wave force of T consecutive (predicted) step times in one pass over eta ----
-constexpr int kFinalizeWarpMaxItems = 8192;   // ensembles of up to this many (dof, instance) items: k_finalize_warp (a warp per
-                                             // item) instead of k_finalize.  Measured crossover (RM3 shape, per-step kernels):
-                                             // 110 vs 133 us per step at 512 instances, equal at 1024, 207 vs 184 us at 2048
+// Which finalize kernel serves an ensemble (depends only on its size and chunking, never on the step):
+constexpr int kFinalizeWarpMaxB = 8;          // up to this many instances: k_finalize_warp (a warp per (dof, instance))
+constexpr int kFinalizeSplitMinParts = 96;    // beyond that, with at least this many partials per item: k_finalize_split;
+                                              // otherwise k_finalize (a thread per item: large ensembles, few long chunks)
 constexpr int kLaT = 8;        // block length = warps per CTA of k_exc_block
 constexpr int kLaRows = 32;    // eta rows per shared-memory stage
 struct LookaheadPlanArgs {
