@@ -1,0 +1,155 @@
+"""Differential test of the host layer's hydro.yaml parser against the REFERENCE's own parser.
+
+src/hydro_yaml_parser.cpp + hydro_types.h are the one piece of the reference that builds from its own sources (SURVEY.md
+8c).  oracle/Makefile compiles them where they lie into oracle/_ref/ref_yaml_dump (and the same dump driver over this
+repo's parser into oracle/_ref/our_yaml_dump); both print every field of the YAMLHydroData that ReadHydroYAML returns, or
+EXCEPTION.  The corpus: every *.hydro.yaml shipped with the reference plus synthetic files that walk the parser's branches
+(scalar period and its synonyms, amplitude vs height, inline / block sweeps, booleans, quoting, comments, per-body and
+system-wide TaperedDirect options, the convolution section, malformed numbers, missing sections).
+
+Known deviation, asserted here: BLOCK-form period sweeps
+
+    period:
+      range: { start: 10.0, stop: 13.0, step: 1.0, inclusive: true }
+
+are rejected by the reference snapshot ("waves.period: invalid or empty specification") -- its period-block exit test
+(`indent <= period_block_indent`, hydro_yaml_parser.cpp:537-540) fires on the `period:` line itself, so the nested keys
+of :441-524 are never reached, and its own demos/yaml/f3of/f3of_rao.hydro.yaml does not load.  This repo's parser
+implements the documented format (the sweep feeds the ensemble's batch axis, SetupHydroSweepFromYAML); everything else
+is identical.  CPU only; skipped where /root/reference (hence the reference binary) is absent."""
+import glob
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_yaml_dump")
+OUR_BIN = os.path.join(ROOT, "oracle", "_ref", "our_yaml_dump")
+REF_TREE = "/root/reference"
+
+BASE = """hydrodynamics:
+  bodies:
+    - name: body1
+      h5_file: hydroData/sphere.h5
+%(body)s
+  waves:
+%(waves)s
+%(extra)s
+"""
+REG = "    type: regular\n    height: 1\n    period: 5"
+CASES = {
+    "scalar": dict(waves="    type: regular\n    height: 2.0\n    period: 8.0\n    direction: 10\n    phase: 0.5"),
+    "synonyms_T": dict(waves="    type: regular\n    H: 1.5\n    T: 7.5"),
+    "synonyms_Tp": dict(waves="    type: irregular\n    h: 2.5\n    Tp: 9.0\n    spectrum: jonswap\n    seed: 42"),
+    "synonyms_p": dict(waves="    type: regular\n    a: 0.75\n    p: 6"),
+    "amp_and_height": dict(waves="    type: regular\n    a: 0.75\n    height: 3.0\n    period: 6"),
+    "amplitude_word": dict(waves="    type: regular\n    amplitude: 0.5\n    period: 6"),
+    "inline_values": dict(waves="    type: regular\n    height: 1\n    period: { values: [6.0, 7.5, 9] }"),
+    "inline_values_list": dict(waves="    type: regular\n    height: 1\n    period: [6.0, 7.5, 9]"),
+    "inline_linspace": dict(waves="    type: regular\n    height: 1\n    period: { linspace: { start: 2.0, stop: 5.0, num: 4 } }"),
+    "inline_range": dict(waves="    type: regular\n    height: 1\n    period: { range: { start: 2.0, stop: 5.0, step: 1.0 } }"),
+    "no_wave": dict(waves="    type: no_wave"),
+    "still": dict(waves="    type: still"),
+    "quoted": dict(waves="    type: \"irregular\"\n    height: '2.0'\n    period: \"8.0\"   # trailing comment\n"
+                         "    spectrum: 'pierson_moskowitz'"),
+    "bools": dict(waves=REG, body="      include_excitation: no\n      include_radiation: Off\n"
+                                  "      radiation_calculation: state_space"),
+    "bools2": dict(waves=REG, body="      include_excitation: TRUE\n      include_radiation: 0"),
+    "body_td": dict(waves=REG, body="      radiation_convolution_mode: TaperedDirect\n      td_smoothing: moving_average\n"
+                                    "      td_window_length: 9\n      td_rms_threshold_factor: 0.05\n"
+                                    "      td_taper_fraction_remaining: 0.4\n      td_export_plot_csv: true"),
+    "global_td": dict(waves=REG, extra="  radiation_convolution_mode: TaperedDirect\n  td_smoothing: moving_average\n"
+                                       "  td_window_length: 11\n  td_export_plot_csv: yes"),
+    "conv_section": dict(waves=REG, extra="  convolution:\n    mode: TaperedDirect\n    smoothing:\n      type: moving_average\n"
+                                          "      window_length: 9\n      order: 2\n    taper:\n      start_percent: 0.6\n"
+                                          "      end_percent: 0.9\n      final_amplitude: 0.05\n      end_time: 20\n"
+                                          "    diagnostics:\n      export_csv: on"),
+    "conv_smoothing_inline": dict(waves=REG, extra="  convolution:\n    mode: Baseline\n    smoothing: sg"),
+    "bad_numbers": dict(waves="    type: regular\n    height: abc\n    period: 5x\n    direction: \n    seed: notanint"),
+    "zero_period": dict(waves="    type: regular\n    height: 1\n    period: 0"),
+    "neg_period": dict(waves="    type: regular\n    height: 1\n    period: -3"),
+    "no_period_regular": dict(waves="    type: regular\n    height: 1"),
+    "two_bodies": dict(waves=REG, body="    - name: body2\n      h5_file: /abs/path/x.h5\n      include_excitation: false"),
+    "tabs_and_spaces": dict(waves="    type:   regular   \n    height:\t1\n    period: 5"),
+    "empty_waves": dict(waves="    # nothing"),
+    "uppercase_keys": dict(waves="    Type: regular\n    Height: 2\n    Period: 4\n    Direction: 3\n    Phase: 1\n    Seed: 5\n"
+                                 "    Spectrum: jonswap"),
+    "linspace_bad": dict(waves="    type: regular\n    height: 1\n    period: { linspace: { start: 2.0, stop: 5.0, num: 1 } }"),
+    "range_bad": dict(waves="    type: regular\n    height: 1\n    period: { range: { start: 5.0, stop: 2.0, step: 1.0 } }"),
+    "values_empty": dict(waves="    type: regular\n    height: 1\n    period: { values: [] }"),
+    "range_noninteger": dict(waves="    type: regular\n    height: 1\n    period: { range: { start: 1.0, stop: 2.05, step: 0.3 } }"),
+}
+RAW = {
+    "no_hydro_key": "model:\n  x: 1\n",
+    "empty": "",
+    "nobodies": "hydrodynamics:\n  waves:\n    type: regular\n    height: 1\n    period: 3\n",
+}
+# block-form sweeps: the known deviation (see the module docstring) -> expected period_values of THIS parser
+BLOCK = {
+    "block_values": ("    type: regular\n    height: 1\n    period:\n      values: [6.0, 7.0]", "period_values 2: 6 7"),
+    "block_linspace": ("    type: regular\n    height: 1\n    period:\n      linspace: { start: 2.0, stop: 5.0, num: 4 }",
+                       "period_values 4: 2 3 4 5"),
+    "block_range_excl": ("    type: regular\n    height: 1\n    period:\n      range: { start: 2.0, stop: 5.0, step: 1.0, "
+                         "inclusive: false }", "period_values 3: 2 3 4"),
+    "block_range_incl": ("    type: regular\n    height: 1\n    period:\n      #values: [6.0, 7.0, 8.0, 9.0]\n"
+                         "      range: { start: 10.0, stop: 13.0, step: 1.0, inclusive: true }", "period_values 4: 10 11 12 13"),
+}
+
+
+@pytest.fixture(scope="module")
+def dumpers():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    if not os.path.exists(REF_BIN):
+        pytest.skip("the reference tree is not present here: no reference parser to compare with")
+    return REF_BIN, OUR_BIN
+
+
+def _dump(binary, path):
+    out = subprocess.run([binary, str(path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return out.stdout, out.stderr
+
+
+def test_synthetic_corpus_parses_identically(dumpers, tmp_path):
+    ref, our = dumpers
+    files = {}
+    for name, c in CASES.items():
+        files[name] = BASE % dict(body=c.get("body", ""), waves=c["waves"], extra=c.get("extra", ""))
+    files.update(RAW)
+    n_exc = 0
+    for name, text in files.items():
+        f = tmp_path / (name + ".hydro.yaml")
+        f.write_text(text)
+        r, o = _dump(ref, f)[0], _dump(our, f)[0]
+        assert r == o, "%s:\n--- reference\n%s--- this repo\n%s" % (name, r, o)
+        n_exc += "EXCEPTION" in r
+    r, o = _dump(ref, tmp_path / "missing.hydro.yaml")[0], _dump(our, tmp_path / "missing.hydro.yaml")[0]
+    assert r == o and "EXCEPTION" in r
+    assert 8 <= n_exc < len(files) - 15          # the corpus exercises both the accepting and the throwing branches
+
+
+def test_reference_yaml_files_parse_identically(dumpers):
+    ref, our = dumpers
+    if not os.path.isdir(REF_TREE):
+        pytest.skip("the reference tree is not present here")
+    files = sorted(glob.glob(os.path.join(REF_TREE, "**", "*.hydro.yaml"), recursive=True))
+    assert len(files) >= 10
+    deviating = []
+    for f in files:
+        r, o = _dump(ref, f)[0], _dump(our, f)[0]
+        if r != o:
+            deviating.append(os.path.basename(f))
+            assert "EXCEPTION" in r and "period_values 4: 10 11 12 13" in o, f      # the block-form sweep, nothing else
+    assert deviating in ([], ["f3of_rao.hydro.yaml"]), deviating
+
+
+def test_block_form_sweeps_are_the_one_known_deviation(dumpers, tmp_path):
+    ref, our = dumpers
+    for name, (waves, expect) in BLOCK.items():
+        f = tmp_path / (name + ".hydro.yaml")
+        f.write_text(BASE % dict(body="", waves=waves, extra=""))
+        r, rerr = _dump(ref, f)
+        o, _ = _dump(our, f)
+        assert "EXCEPTION" in r and "invalid or empty specification" in rerr, name
+        assert expect in o.splitlines(), (name, o)
