@@ -19,6 +19,7 @@ implements the documented format (the sweep feeds the ensemble's batch axis, Set
 is identical.  CPU only; skipped where /root/reference (hence the reference binary) is absent."""
 import glob
 import os
+import random
 import subprocess
 
 import pytest
@@ -153,3 +154,77 @@ def test_block_form_sweeps_are_the_one_known_deviation(dumpers, tmp_path):
         o, _ = _dump(our, f)
         assert "EXCEPTION" in r and "invalid or empty specification" in rerr, name
         assert expect in o.splitlines(), (name, o)
+
+
+def _fuzz_file(rnd):
+    def num():
+        return rnd.choice(["2.0", "0", "-1", "1e1", "3.25", "12", "0.5", "  7  ", "'3.5'", "\"4\"", "5 # c", "abc", ""])
+    L = ["hydrodynamics:", "  bodies:"]
+    for b in range(rnd.randint(1, 3)):
+        L.append("    - name: body%d" % (b + 1))
+        L.append("      h5_file: %s" % rnd.choice(["x.h5", "/a/b.h5", "../d/e.h5", "'q.h5'"]))
+        for k, vs in [("include_excitation", ["true", "false", "no", "On", "0", "1", "Yes", "maybe"]),
+                      ("include_radiation", ["true", "false", "off"]), ("radiation_calculation", ["convolution", "state_space"]),
+                      ("radiation_convolution_mode", ["TaperedDirect", "Baseline"]), ("td_smoothing", ["sg", "moving_average"]),
+                      ("td_window_length", ["7", "abc", "3"]), ("td_rms_threshold_factor", ["0.1", "x"]),
+                      ("td_taper_fraction_remaining", ["0.3"]), ("td_export_plot_csv", ["true", "no"])]:
+            if rnd.random() < 0.3:
+                L.append("      %s: %s" % (k, rnd.choice(vs)))
+    L.append("  waves:")
+    L.append("    type: %s" % rnd.choice(["regular", "irregular", "no_wave", "still", "Regular", "IRREGULAR"]))
+    W = []
+    if rnd.random() < 0.8:
+        W.append("%s: %s" % (rnd.choice(["height", "h", "H"]), num()))
+    if rnd.random() < 0.4:
+        W.append("%s: %s" % (rnd.choice(["a", "amplitude", "A"]), num()))
+    r, pk = rnd.random(), rnd.choice(["period", "T", "Tp", "p", "Period"])
+    if r < 0.5:
+        W.append("%s: %s" % (pk, num()))
+    elif r < 0.65:
+        W.append("%s: { values: [%s] }" % (pk, ", ".join(rnd.choice(["4", "5.5", "6", "x"]) for _ in range(rnd.randint(0, 4)))))
+    elif r < 0.75:
+        W.append("%s: { linspace: { start: 1, stop: %s, num: %s } }" % (pk, rnd.choice(["2", "0"]), rnd.choice(["3", "1", "x"])))
+    elif r < 0.85:
+        W.append("%s: { range: { start: 1, stop: %s, step: %s, inclusive: %s } }"
+                 % (pk, rnd.choice(["2", "0", "2.05"]), rnd.choice(["0.5", "0", "0.3"]), rnd.choice(["true", "false"])))
+    for k in ["direction", "phase", "spectrum", "seed"]:
+        if rnd.random() < 0.5:
+            W.append("%s: %s" % (k, rnd.choice(["jonswap", "pierson_moskowitz"]) if k == "spectrum" else num()))
+    rnd.shuffle(W)
+    L += ["    " + w for w in W]
+    if rnd.random() < 0.3:
+        L += ["  convolution:", "    mode: %s" % rnd.choice(["TaperedDirect", "Baseline"])]
+        if rnd.random() < 0.6:
+            L += ["    smoothing:", "      type: %s" % rnd.choice(["sg", "moving_average", "savitzky_golay"]),
+                  "      window_length: %s" % rnd.choice(["5", "9", "x"])]
+        if rnd.random() < 0.6:
+            L += ["    taper:", "      start_percent: %s" % rnd.choice(["0.5", "x"]), "      end_percent: 0.9",
+                  "      final_amplitude: 0.1", "      end_time: %s" % rnd.choice(["10", "-1"])]
+        if rnd.random() < 0.6:
+            L += ["    diagnostics:", "      export_csv: %s" % rnd.choice(["true", "no"])]
+    if rnd.random() < 0.3:
+        for k, vs in [("radiation_convolution_mode", ["TaperedDirect", "Baseline"]), ("td_smoothing", ["sg", "moving_average"]),
+                      ("td_window_length", ["7", "x"]), ("td_export_plot_csv", ["true", "0"])]:
+            if rnd.random() < 0.5:
+                L.append("  %s: %s" % (k, rnd.choice(vs)))
+    if rnd.random() < 0.15:
+        L.insert(rnd.randint(1, len(L)), "    # comment")
+    return "\n".join(L) + "\n"
+
+
+def test_fuzzed_corpus_parses_identically(dumpers, tmp_path):
+    """600 seeded random hydro.yaml files (inline forms only: block-form sweeps are the known deviation): the two
+    parsers print the same structure, or both throw, for every one of them."""
+    ref, our = dumpers
+    rnd = random.Random(11)
+    files = []
+    for n in range(600):
+        f = tmp_path / ("g%04d.hydro.yaml" % n)
+        f.write_text(_fuzz_file(rnd))
+        files.append(str(f))
+    r = subprocess.run([ref] + files, capture_output=True, text=True)
+    o = subprocess.run([our] + files, capture_output=True, text=True)
+    assert r.returncode == 0 and o.returncode == 0
+    assert r.stdout == o.stdout
+    n_exc = r.stdout.count("EXCEPTION")
+    assert 100 < n_exc < 500, n_exc          # both outcomes are well represented
